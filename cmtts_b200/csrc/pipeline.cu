@@ -1,0 +1,497 @@
+// Stage-level entry points of the C ABI: each one enqueues the kernel sequence of one seam of the
+// reference's hot path (see include/cmtts_b200.h for the seam -> reference file:line map).
+#include "../../include/cmtts_b200.h"
+#include "common.cuh"
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+// implemented in rowops.cu
+int cmtts_cwt_pitch_impl(const float* cwt, int cwt_dim, const float* cwt_b, const float* f0stats, int f0s_ld,
+                         float std_scale, float eps, int use_uv, float mel_min, float mel_span,
+                         const float* xf, const float* pitch_emb, int n_pitch, float* cond,
+                         float* f0_denorm, long long* pitch_idx, float* rec_scratch, float* stat_scratch,
+                         int B, int L, int C, cudaStream_t s);
+int cmtts_step_sinusoid_impl(const float* t, const float* freq, float* out, int B, int C, cudaStream_t s);
+
+// --------------------------------------------------------------------------------------------
+// error text
+// --------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void cmtts_set_error(const char* msg, const char* file, int line) {
+    snprintf(g_err, sizeof(g_err), "%s (%s:%d)", msg, file, line);
+}
+extern "C" const char* cmtts_last_error(void) { return g_err; }
+extern "C" int cmtts_abi_version(void) { return CMTTS_ABI_VERSION; }
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+struct Carver {
+    char* base; size_t off; size_t cap;
+    Carver(void* p, size_t c) : base((char*)p), off(0), cap(c) {}
+    template <typename T> T* take(size_t n) {
+        size_t bytes = align_up(n * sizeof(T));
+        T* r = (T*)(base + off);
+        off += bytes;
+        return r;
+    }
+    bool ok() const { return off <= cap; }
+};
+
+inline const float* F(const void* const* w, int i) { return (const float*)w[i]; }
+
+// plain "same" conv / linear helper: x (B,M,Cin) -> out (B,M,N)
+ConvParams conv_same(const float* x, int B, int M, int Cin, const float* w, const float* bias, int N, int k,
+                     int dil, float* out) {
+    ConvParams p = conv_params_default();
+    p.x = x; p.x_bstride = (long long)M * Cin; p.x_ld = Cin; p.Lin = M; p.Cin = Cin;
+    p.w = w; p.taps = k;
+    for (int i = 0; i < k; ++i) p.shift[i] = (i - (k - 1) / 2) * dil;
+    p.out = out; p.out_bstride = (long long)M * N; p.out_ld = N; p.M = M; p.N = N; p.B = B;
+    p.bias = bias;
+    return p;
+}
+
+}  // namespace
+
+// ============================================================================================
+// encoder
+// ============================================================================================
+extern "C" size_t cmtts_encoder_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t T) {
+    const size_t n = (size_t)B * T, C = d->hidden;
+    return align_up(n * C * 4) * 3 + align_up(n * 3 * C * 4) + align_up(n * 4 * C * 4);
+}
+
+extern "C" int cmtts_encoder_forward(const cmtts_dims* d, const void* const* w, const int64_t* tokens,
+                                     const int64_t* src_lens, int64_t B_, int64_t T_, float* enc_out,
+                                     void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = (int)B_, T = (int)T_, C = d->hidden;
+    CMTTS_REQUIRE(ws_bytes >= cmtts_encoder_workspace_bytes(d, B_, T_), "encoder: workspace too small");
+    if (B == 0 || T == 0) return CMTTS_OK;
+    Carver cv(ws, ws_bytes);
+    const size_t n = (size_t)B * T;
+    float* x = cv.take<float>(n * C);
+    float* h = cv.take<float>(n * C);
+    float* att = cv.take<float>(n * C);
+    float* qkv = cv.take<float>(n * 3 * C);
+    float* ff = cv.take<float>(n * 4 * C);
+    const long long* lens = (const long long*)src_lens;
+
+    CMTTS_TRY(launch_embed_tokens((const long long*)tokens, F(w, CMTTS_ENC_EMB), F(w, CMTTS_ENC_PE), d->pe_rows,
+                                  sqrtf((float)C), x, B, T, C, lens, s));
+    for (int l = 0; l < d->enc_layers; ++l) {
+        const int o = CMTTS_ENC_LAYER0 + l * CMTTS_ENC_PER_LAYER;
+        // pre-LN (eps 1e-12, blocks.py:96); padded rows are all-zero -> LN gives the bias, as in torch
+        CMTTS_TRY(launch_layernorm(x, F(w, o + 0), F(w, o + 1), 1e-12f, h, B, T, C, nullptr, s));
+        ConvParams p = conv_same(h, B, T, C, F(w, o + 2), nullptr, 3 * C, 1, 1, qkv);
+        CMTTS_TRY(launch_conv1d_simt(p, s));
+        CMTTS_TRY(launch_attention(qkv, lens, att, B, T, C, d->enc_heads, s));
+        p = conv_same(att, B, T, C, F(w, o + 3), nullptr, C, 1, 1, x);   // x = (x + attn W_o) * nonpad
+        p.res1 = x; p.res1_bstride = (long long)T * C; p.res1_ld = C; p.lens = lens;
+        CMTTS_TRY(launch_conv1d_simt(p, s));
+        CMTTS_TRY(launch_layernorm(x, F(w, o + 4), F(w, o + 5), 1e-12f, h, B, T, C, nullptr, s));
+        p = conv_same(h, B, T, C, F(w, o + 6), F(w, o + 7), 4 * C, d->ffn_kernel, 1, ff);
+        p.beta = (float)pow((double)d->ffn_kernel, -0.5);                   // blocks.py:540
+        p.act = d->ffn_act;
+        CMTTS_TRY(launch_conv1d_simt(p, s));
+        p = conv_same(ff, B, T, 4 * C, F(w, o + 8), F(w, o + 9), C, 1, 1, x);
+        p.res1 = x; p.res1_bstride = (long long)T * C; p.res1_ld = C; p.lens = lens;
+        CMTTS_TRY(launch_conv1d_simt(p, s));
+    }
+    const int o = CMTTS_ENC_LAYER0 + d->enc_layers * CMTTS_ENC_PER_LAYER;
+    CMTTS_TRY(launch_layernorm(x, F(w, o), F(w, o + 1), 1e-5f, enc_out, B, T, C, lens, s));   // modules.py:74,99
+    return CMTTS_OK;
+}
+
+// ============================================================================================
+// variance adaptor
+// ============================================================================================
+namespace {
+struct VaIdx {
+    int spk_w, spk_b, dur0, dur_head, en_alpha, en0, en_head, pe_c, en_bins, en_emb, st0, cwt_in, pe_h,
+        cwt_alpha, cwt0, cwt_head, cwt_b, pitch_emb, count;
+    explicit VaIdx(const cmtts_dims* d) {
+        int c = 0;
+        spk_w = c++; spk_b = c++;
+        dur0 = c; c += 4 * d->dur_layers; dur_head = c; c += 2;
+        en_alpha = c++; en0 = c; c += 4 * d->pred_layers; en_head = c; c += 2;
+        pe_c = c++; en_bins = c++; en_emb = c++;
+        st0 = c; c += 6;
+        cwt_in = c; c += 2;
+        pe_h = c++;
+        cwt_alpha = c++; cwt0 = c; c += 4 * d->pred_layers; cwt_head = c; c += 2;
+        cwt_b = c++; pitch_emb = c++;
+        count = c;
+    }
+};
+
+// [pad -> Conv1d -> ReLU -> LayerNorm(eps 1e-12)] x n, then LN+Linear head (modules.py:477-509, :527-555).
+// `lens` != NULL applies the duration predictor's masking after every layer.
+int predictor_stack(const cmtts_dims* d, const void* const* w, int conv0, int head, int n_layers, int k,
+                    const float* x, int Cin, int B, int T, const long long* lens, int odim, float scale,
+                    float* bufa, float* bufb, float* out, cudaStream_t s) {
+    const int Fc = d->filter;
+    const float* cur = x;
+    int cin = Cin;
+    for (int i = 0; i < n_layers; ++i) {
+        ConvParams p = conv_same(cur, B, T, cin, F(w, conv0 + 4 * i), F(w, conv0 + 4 * i + 1), Fc, k, 1, bufa);
+        p.act = ACT_RELU;
+        CMTTS_TRY(launch_conv1d_simt(p, s));
+        if (i + 1 < n_layers) {
+            CMTTS_TRY(launch_layernorm(bufa, F(w, conv0 + 4 * i + 2), F(w, conv0 + 4 * i + 3), 1e-12f, bufb, B, T, Fc, lens, s));
+            cur = bufb; cin = Fc;
+        } else {
+            CMTTS_TRY(launch_ln_head(bufa, F(w, conv0 + 4 * i + 2), F(w, conv0 + 4 * i + 3), 1e-12f, F(w, head),
+                                     F(w, head + 1), odim, scale, out, B, T, Fc, lens, s));
+        }
+    }
+    return CMTTS_OK;
+}
+}  // namespace
+
+extern "C" size_t cmtts_variance_token_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t T) {
+    const size_t n = (size_t)B * T;
+    const size_t big = d->hidden > d->filter ? d->hidden : d->filter;
+    return align_up(n * big * 4) * 4 + align_up((size_t)B * d->cwt_hidden * 4) * 2 + align_up(n * 4);
+}
+
+extern "C" int cmtts_variance_token(const cmtts_dims* d, const void* const* w, const float* enc,
+                                    const int64_t* src_lens, const float* spker_embeds, float e_control,
+                                    float d_control, int64_t B_, int64_t T_, float* out1, float* log_d,
+                                    float* d_rounded, float* e_pred, int64_t* e_idx, int64_t* cumsum,
+                                    int64_t* mel_lens, float* spk_emb, float* f0_stats, void* ws,
+                                    size_t ws_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = (int)B_, T = (int)T_, C = d->hidden, Fc = d->filter;
+    CMTTS_REQUIRE(ws_bytes >= cmtts_variance_token_workspace_bytes(d, B_, T_), "variance_token: workspace too small");
+    if (B == 0 || T == 0) return CMTTS_OK;
+    const VaIdx ix(d);
+    Carver cv(ws, ws_bytes);
+    const size_t n = (size_t)B * T;
+    const size_t big = C > Fc ? C : Fc;
+    float* x = cv.take<float>(n * big);
+    float* xp = cv.take<float>(n * big);
+    float* bufa = cv.take<float>(n * big);
+    float* bufb = cv.take<float>(n * big);
+    float* st1 = cv.take<float>((size_t)B * d->cwt_hidden);
+    float* st2 = cv.take<float>((size_t)B * d->cwt_hidden);
+    float* e_raw = cv.take<float>(n);
+    const long long* lens = (const long long*)src_lens;
+
+    // x = encoder_out (+ speaker embedding broadcast over ALL token positions, modules.py:349-352)
+    cudaMemcpyAsync(x, enc, n * C * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    if (d->multi_speaker) {
+        CMTTS_REQUIRE(spker_embeds != nullptr && spk_emb != nullptr, "Speaker embedding should not be None");  // cmtts.py:80
+        ConvParams p = conv_same(spker_embeds, 1, B, d->spk_dim, F(w, ix.spk_w), F(w, ix.spk_b), C, 1, 1, spk_emb);
+        CMTTS_TRY(launch_conv1d_simt(p, s));
+        CMTTS_TRY(launch_add_rowvec(x, spk_emb, B, T, C, s));
+    }
+    // duration predictor (masked)
+    CMTTS_TRY(predictor_stack(d, w, ix.dur0, ix.dur_head, d->dur_layers, d->dur_kernel, x, C, B, T, lens, 1, 1.f,
+                              bufa, bufb, log_d, s));
+    // energy predictor: + alpha * PE[pos], conv stack unmasked (modules.py:319-329, :542-555)
+    CMTTS_TRY(launch_add_positional(x, F(w, ix.pe_c), d->pe_rows, F(w, ix.en_alpha), xp, B, T, C, s));
+    CMTTS_TRY(predictor_stack(d, w, ix.en0, ix.en_head, d->pred_layers, d->pred_kernel, xp, C, B, T, nullptr, 1, 1.f,
+                              bufa, bufb, e_raw, s));
+    CMTTS_TRY(launch_energy_embed(x, e_raw, e_control, F(w, ix.en_bins), d->energy_bins - 1, F(w, ix.en_emb), out1,
+                                  (long long*)e_idx, e_pred, B, T, C, s));
+    // durations
+    CMTTS_TRY(launch_round_durations(log_d, d_control, lens, d_rounded, (long long*)cumsum, (long long*)mel_lens, B, T, s));
+    // cwt_stats_layers on output_1[:, 0, :] (modules.py:279): Linear-ReLU-Linear-ReLU-Linear(2, padded to 4)
+    {
+        const int h = d->cwt_hidden;
+        ConvParams p = conv_same(out1, 1, B, C, F(w, ix.st0), F(w, ix.st0 + 1), h, 1, 1, st1);
+        p.x_ld = T * C; p.act = ACT_RELU;
+        CMTTS_TRY(launch_conv1d_simt(p, s));
+        p = conv_same(st1, 1, B, h, F(w, ix.st0 + 2), F(w, ix.st0 + 3), h, 1, 1, st2);
+        p.act = ACT_RELU;
+        CMTTS_TRY(launch_conv1d_simt(p, s));
+        p = conv_same(st2, 1, B, h, F(w, ix.st0 + 4), F(w, ix.st0 + 5), 4, 1, 1, f0_stats);
+        CMTTS_TRY(launch_conv1d_simt(p, s));
+    }
+    return CMTTS_OK;
+}
+
+extern "C" size_t cmtts_variance_frame_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t L) {
+    const size_t n = (size_t)B * L;
+    return align_up(n * d->hidden * 4) + align_up(n * d->cwt_hidden * 4) * 2 + align_up(n * d->filter * 4) * 2 +
+           align_up(n * 4) + align_up((size_t)B * 2 * 4);
+}
+
+extern "C" int cmtts_variance_frame(const cmtts_dims* d, const void* const* w, const float* out1,
+                                    const int64_t* cumsum, const int64_t* mel_lens, const float* f0_stats,
+                                    float p_control, int64_t B_, int64_t T_, int64_t L_, float* cond,
+                                    int64_t* mel2ph, float* cwt, float* f0_denorm, int64_t* pitch_idx,
+                                    void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = (int)B_, T = (int)T_, L = (int)L_, C = d->hidden, h = d->cwt_hidden, Fc = d->filter;
+    CMTTS_REQUIRE(ws_bytes >= cmtts_variance_frame_workspace_bytes(d, B_, L_), "variance_frame: workspace too small");
+    if (B == 0 || L == 0) return CMTTS_OK;
+    const VaIdx ix(d);
+    Carver cv(ws, ws_bytes);
+    const size_t n = (size_t)B * L;
+    float* xf = cv.take<float>(n * C);
+    float* hin = cv.take<float>(n * h);
+    float* hp = cv.take<float>(n * h);
+    float* bufa = cv.take<float>(n * Fc);
+    float* bufb = cv.take<float>(n * Fc);
+    float* rec = cv.take<float>(n);
+    float* stat = cv.take<float>((size_t)B * 2);
+
+    CMTTS_TRY(launch_length_regulate(out1, (const long long*)cumsum, (const long long*)mel_lens, xf,
+                                     (long long*)mel2ph, B, T, L, C, s));
+    ConvParams p = conv_same(xf, B, L, C, F(w, ix.cwt_in), F(w, ix.cwt_in + 1), h, 1, 1, hin);
+    CMTTS_TRY(launch_conv1d_simt(p, s));
+    CMTTS_TRY(launch_add_positional(hin, F(w, ix.pe_h), d->pe_rows, F(w, ix.cwt_alpha), hp, B, L, h, s));
+    CMTTS_TRY(predictor_stack(d, w, ix.cwt0, ix.cwt_head, d->pred_layers, d->pred_kernel, hp, h, B, L, nullptr,
+                              d->cwt_out, p_control, bufa, bufb, cwt, s));
+    // f0_stats rows are (mean, std, 0, 0): the last stats Linear is padded to 4 outputs
+    CMTTS_TRY(cmtts_cwt_pitch_impl(cwt, d->cwt_out, F(w, ix.cwt_b), f0_stats, 4, d->cwt_std_scale, d->pitch_eps,
+                                   d->use_uv, d->f0_mel_min, d->f0_mel_span, xf, F(w, ix.pitch_emb), d->pitch_bins,
+                                   cond, f0_denorm, (long long*)pitch_idx, rec, stat, B, L, C, s));
+    return CMTTS_OK;
+}
+
+// ============================================================================================
+// denoiser
+// ============================================================================================
+extern "C" size_t cmtts_denoiser_prepare_workspace_bytes(const cmtts_dims* d, int64_t B) {
+    return align_up((size_t)B * d->res_channels * 4) * 2 + align_up((size_t)B * d->res_channels * 4 * 4);
+}
+
+extern "C" int cmtts_denoiser_prepare(const cmtts_dims* d, const void* const* w, const float* t,
+                                      const float* spk_emb, int64_t B_, float* ds_all, float* dsp_all,
+                                      void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = (int)B_, C = d->res_channels, NL = d->res_layers * C;
+    CMTTS_REQUIRE(ws_bytes >= cmtts_denoiser_prepare_workspace_bytes(d, B_), "denoiser_prepare: workspace too small");
+    if (B == 0) return CMTTS_OK;
+    Carver cv(ws, ws_bytes);
+    float* e = cv.take<float>((size_t)B * C);
+    float* sv = cv.take<float>((size_t)B * C);
+    float* h = cv.take<float>((size_t)B * 4 * C);
+    CMTTS_TRY(cmtts_step_sinusoid_impl(t, F(w, CMTTS_DN_FREQ), e, B, C, s));
+    ConvParams p = conv_same(e, 1, B, C, F(w, CMTTS_DN_MLP0), nullptr, 4 * C, 1, 1, h);
+    CMTTS_TRY(launch_conv1d_simt(p, s));
+    CMTTS_TRY(launch_mish(h, (long long)B * 4 * C, s));
+    p = conv_same(h, 1, B, 4 * C, F(w, CMTTS_DN_MLP2), nullptr, C, 1, 1, sv);
+    CMTTS_TRY(launch_conv1d_simt(p, s));
+    p = conv_same(sv, 1, B, C, F(w, CMTTS_DN_DPROJ), nullptr, NL, 1, 1, ds_all);
+    CMTTS_TRY(launch_conv1d_simt(p, s));
+    if (d->multi_speaker) {
+        CMTTS_REQUIRE(spk_emb != nullptr && dsp_all != ds_all, "denoiser_prepare: multi-speaker needs spk_emb and a separate dsp_all");
+        p = conv_same(spk_emb, 1, B, d->hidden, F(w, CMTTS_DN_SPROJ), nullptr, NL, 1, 1, dsp_all);
+        p.res1 = ds_all; p.res1_bstride = 0; p.res1_ld = NL;
+        CMTTS_TRY(launch_conv1d_simt(p, s));
+    } else if (dsp_all != ds_all) {
+        cudaMemcpyAsync(dsp_all, ds_all, (size_t)B * NL * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    }
+    return CMTTS_OK;
+}
+
+extern "C" size_t cmtts_denoiser_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t L) {
+    return align_up((size_t)B * L * d->res_channels * 4) * 5;
+}
+
+extern "C" int cmtts_denoiser_forward(const cmtts_dims* d, const void* const* w, const float* x_t,
+                                      const float* cond, const float* ds_all, const float* dsp_all,
+                                      float c_in, float c_out, float c_skip, int64_t B_, int64_t L_,
+                                      float* out, float* model_out, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = (int)B_, L = (int)L_, C = d->res_channels, M = d->n_mels, H = d->hidden;
+    CMTTS_REQUIRE(ws_bytes >= cmtts_denoiser_workspace_bytes(d, B_, L_), "denoiser: workspace too small");
+    if (B == 0 || L == 0) return CMTTS_OK;
+    Carver cv(ws, ws_bytes);
+    const size_t n = (size_t)B * L;
+    float* x = cv.take<float>(n * C);
+    float* y = cv.take<float>(n * C);
+    float* g = cv.take<float>(n * C);
+    float* skip = cv.take<float>(n * C);
+    float* v = cv.take<float>(n * C);
+    const long long NL = (long long)d->res_layers * C;
+    const long long bs = (long long)L * C;
+
+    // input_projection + ReLU (+ReLU): relu(W (c_in x_t) + b)   modules.py:621-624, karras_diffusion.py:405
+    ConvParams p = conv_same(x_t, B, L, M, F(w, CMTTS_DN_IN_W), F(w, CMTTS_DN_IN_B), C, 1, 1, x);
+    p.alpha = c_in; p.act = ACT_RELU;
+    CMTTS_TRY(launch_conv1d_simt(p, s));
+    for (int l = 0; l < d->res_layers; ++l) {
+        const int o = CMTTS_DN_LAYER0 + l * CMTTS_DN_PER_LAYER;
+        // y = x + diffusion_step + conditioner (+ speaker)      blocks.py:669-678
+        p = conv_same(cond, B, L, H, F(w, o + 0), F(w, o + 1), C, 1, 1, y);
+        p.addvec = dsp_all + (long long)l * C; p.addvec_bstride = NL;
+        p.res1 = x; p.res1_bstride = bs; p.res1_ld = C;
+        CMTTS_TRY(launch_conv1d_simt(p, s));
+        // sigmoid(gate) * tanh(filter) of the k=3 conv           blocks.py:677-681
+        p = conv_same(y, B, L, C, F(w, o + 2), F(w, o + 3), 2 * C, 3, 1, g);
+        p.act = ACT_GATED; p.out_ld = C; p.out_bstride = bs;
+        CMTTS_TRY(launch_conv1d_simt(p, s));
+        // x = (out[:C] + residual) / sqrt(2), residual = x + diffusion_step     blocks.py:676, :683-686
+        p = conv_same(g, B, L, C, F(w, o + 4), F(w, o + 5), C, 1, 1, x);
+        p.addvec = ds_all + (long long)l * C; p.addvec_bstride = NL;
+        p.res1 = x; p.res1_bstride = bs; p.res1_ld = C;
+        p.out_scale = (float)(1.0 / sqrt(2.0));
+        CMTTS_TRY(launch_conv1d_simt(p, s));
+        // skip accumulation (running sum instead of torch.stack, modules.py:629-634)
+        p = conv_same(g, B, L, C, F(w, o + 6), F(w, o + 7), C, 1, 1, skip);
+        p.accumulate = (l > 0);
+        CMTTS_TRY(launch_conv1d_simt(p, s));
+    }
+    const int o = CMTTS_DN_LAYER0 + d->res_layers * CMTTS_DN_PER_LAYER;
+    p = conv_same(skip, B, L, C, F(w, o + 0), F(w, o + 1), C, 1, 1, v);
+    p.alpha = (float)(1.0 / sqrt((double)d->res_layers)); p.act = ACT_RELU;
+    CMTTS_TRY(launch_conv1d_simt(p, s));
+    // F = W v + b ; out = c_out F + c_skip x_t                  modules.py:637, karras_diffusion.py:406
+    p = conv_same(v, B, L, C, F(w, o + 2), F(w, o + 3), M, 1, 1, out);
+    p.beta = c_out;
+    if (model_out) { p.aux_out = model_out; p.aux_bstride = (long long)L * M; p.aux_ld = M; }
+    if (c_skip != 0.f) { p.res1 = x_t; p.res1_bstride = (long long)L * M; p.res1_ld = M; p.res1_scale = c_skip; }
+    CMTTS_TRY(launch_conv1d_simt(p, s));
+    return CMTTS_OK;
+}
+
+extern "C" int cmtts_renoise(const float* x0, const float* noise, float s1, float s2, float* out, int64_t n, void* stream) {
+    return launch_renoise(x0, noise, s1, s2, out, (long long)n, (cudaStream_t)stream);
+}
+
+// ============================================================================================
+// HiFi-GAN
+// ============================================================================================
+namespace {
+struct HifiCfg {
+    int n_levels, C0, n_kernels, n_dil, pre_k, post_k;
+    const int32_t *rates, *up_taps, *up_shift0, *ksize, *dil;
+    explicit HifiCfg(const int32_t* c) {
+        n_levels = c[0]; C0 = c[1]; n_kernels = c[2]; n_dil = c[3]; pre_k = c[4]; post_k = c[5];
+        rates = c + 6; up_taps = rates + n_levels; up_shift0 = up_taps + n_levels;
+        ksize = up_shift0 + n_levels; dil = ksize + n_kernels;
+    }
+    long long max_level_elems_per_frame() const {
+        long long best = C0, rate = 1; int ch = C0;
+        for (int i = 0; i < n_levels; ++i) { rate *= rates[i]; ch /= 2; if (rate * ch > best) best = rate * ch; }
+        return best;
+    }
+    int hop() const { int h = 1; for (int i = 0; i < n_levels; ++i) h *= rates[i]; return h; }
+};
+}  // namespace
+
+extern "C" size_t cmtts_hifigan_workspace_bytes(const int32_t* cfg, int64_t B, int64_t L) {
+    const HifiCfg c(cfg);
+    return align_up((size_t)B * L * c.max_level_elems_per_frame() * 4) * 4;
+}
+
+extern "C" int cmtts_hifigan_forward(const int32_t* cfg, const void* const* w, const float* mel, int64_t B_,
+                                     int64_t L_, float* wav, int16_t* wav_i16, float max_wav_value, void* ws,
+                                     size_t ws_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const HifiCfg c(cfg);
+    const int B = (int)B_, L = (int)L_;
+    CMTTS_REQUIRE(ws_bytes >= cmtts_hifigan_workspace_bytes(cfg, B_, L_), "hifigan: workspace too small");
+    CMTTS_REQUIRE((long long)L * c.hop() < (1ll << 31), "hifigan: sequence too long");
+    if (B == 0 || L == 0) return CMTTS_OK;
+    Carver cv(ws, ws_bytes);
+    const size_t lvl = (size_t)B * L * c.max_level_elems_per_frame();
+    float* up = cv.take<float>(lvl);
+    float* yb = cv.take<float>(lvl);
+    float* tb = cv.take<float>(lvl);
+    float* xs = cv.take<float>(lvl);
+
+    int wi = 0;
+    // conv_pre (hifigan/models.py:150)
+    ConvParams p = conv_same(mel, B, L, 80, F(w, wi), F(w, wi + 1), c.C0, c.pre_k, 1, xs);
+    p.Cin = 80;
+    wi += 2;
+    CMTTS_TRY(launch_conv1d_simt(p, s));
+    int ch = c.C0, len = L;
+    const float inv_nk = 1.0f / (float)c.n_kernels;
+    for (int i = 0; i < c.n_levels; ++i) {
+        const int r = c.rates[i], cout = ch / 2;
+        // lrelu(0.1) -> ConvTranspose1d as a packed conv: N = r * cout, taps over input shifts
+        // (models.py:152-153).  The MRF average /num_kernels of the previous level is folded in
+        // as alpha (leaky_relu is positively homogeneous).
+        p = conv_params_default();
+        p.x = xs; p.x_bstride = (long long)len * ch; p.x_ld = ch; p.Lin = len; p.Cin = ch;
+        p.w = F(w, wi); p.bias = F(w, wi + 1); p.taps = c.up_taps[i];
+        for (int t = 0; t < p.taps; ++t) p.shift[t] = c.up_shift0[i] + t;
+        p.pre_lrelu = 1; p.pre_slope = 0.1f;
+        p.alpha = (i > 0) ? inv_nk : 1.f;
+        p.out = up; p.N = r * cout; p.out_ld = r * cout; p.out_bstride = (long long)len * r * cout;
+        p.M = len; p.B = B;
+        wi += 2;
+        CMTTS_TRY(launch_conv1d_simt(p, s));
+        len *= r; ch = cout;
+        const long long bs = (long long)len * ch;
+        for (int j = 0; j < c.n_kernels; ++j) {
+            const int k = c.ksize[j];
+            const float* yin = up;
+            for (int m = 0; m < c.n_dil; ++m) {
+                const int dl = c.dil[j * c.n_dil + m];
+                // xt = c1(lrelu(x))                                models.py:98-99
+                p = conv_same(yin, B, len, ch, F(w, wi), F(w, wi + 1), ch, k, dl, tb);
+                p.pre_lrelu = 1; p.pre_slope = 0.1f;
+                CMTTS_TRY(launch_conv1d_simt(p, s));
+                // x = c2(lrelu(xt)) + x                            models.py:100-102
+                const bool last = (m == c.n_dil - 1);
+                p = conv_same(tb, B, len, ch, F(w, wi + 2), F(w, wi + 3), ch, k, 1, last ? xs : yb);
+                p.pre_lrelu = 1; p.pre_slope = 0.1f;
+                p.res1 = yin; p.res1_bstride = bs; p.res1_ld = ch;
+                p.accumulate = (last && j > 0);                     // xs += resblock_j(x), models.py:155-159
+                CMTTS_TRY(launch_conv1d_simt(p, s));
+                yin = yb;
+                wi += 4;
+            }
+        }
+    }
+    // x / num_kernels -> lrelu(0.01) -> conv_post -> tanh (-> int16)   models.py:160-163
+    CMTTS_TRY(launch_conv_post(xs, F(w, wi), F(w, wi + 1), 0.01f, (float)c.n_kernels, wav, wav_i16, max_wav_value,
+                               B, len, ch, c.post_k, s));
+    return CMTTS_OK;
+}
+
+extern "C" int cmtts_transpose_bcl_blc(const float* x, float* out, int64_t B, int64_t C, int64_t L, void* stream) {
+    return launch_transpose_bcl_to_blc(x, out, (int)B, (int)C, (int)L, (cudaStream_t)stream);
+}
+
+// ============================================================================================
+// single-op entry points
+// ============================================================================================
+extern "C" int cmtts_conv1d(const cmtts_conv_desc* c, const float* x, const float* w, const float* bias,
+                            const float* addvec, const float* res, const int64_t* lens, float* out, void* stream) {
+    ConvParams p = conv_params_default();
+    p.x = x; p.x_bstride = c->x_bstride; p.x_ld = c->x_ld; p.Lin = c->Lin; p.Cin = c->Cin;
+    p.w = w; p.taps = c->taps;
+    CMTTS_REQUIRE(c->taps >= 1 && c->taps <= CMTTS_MAX_TAPS, "conv1d: taps");
+    for (int i = 0; i < c->taps; ++i) p.shift[i] = c->shift[i];
+    p.pre_lrelu = c->pre_lrelu; p.pre_slope = c->pre_slope;
+    p.out = out; p.out_bstride = c->out_bstride; p.out_ld = c->out_ld; p.M = c->M; p.N = c->N; p.B = c->B;
+    p.bias = bias; p.alpha = c->alpha; p.beta = c->beta; p.act = c->act; p.act_slope = c->act_slope;
+    p.addvec = addvec; p.addvec_bstride = c->addvec_bstride;
+    p.res1 = res; p.res1_bstride = c->res_bstride; p.res1_ld = c->res_ld; p.res1_scale = c->res_scale;
+    p.out_scale = c->out_scale; p.lens = (const long long*)lens; p.accumulate = c->accumulate;
+    return launch_conv1d_simt(p, (cudaStream_t)stream);
+}
+
+extern "C" int cmtts_layernorm(const float* x, const float* w, const float* b, float eps, float* out,
+                               int64_t B, int64_t T, int64_t C, const int64_t* lens, void* stream) {
+    return launch_layernorm(x, w, b, eps, out, (int)B, (int)T, (int)C, (const long long*)lens, (cudaStream_t)stream);
+}
+
+extern "C" int cmtts_attention(const float* qkv, const int64_t* src_lens, float* out, int64_t B, int64_t T,
+                               int64_t C, int64_t heads, void* stream) {
+    return launch_attention(qkv, (const long long*)src_lens, out, (int)B, (int)T, (int)C, (int)heads, (cudaStream_t)stream);
+}
+
+extern "C" int cmtts_length_regulate(const float* x, const int64_t* cumsum, const int64_t* mel_lens, float* out,
+                                     int64_t* mel2ph, int64_t B, int64_t T, int64_t L, int64_t C, void* stream) {
+    return launch_length_regulate(x, (const long long*)cumsum, (const long long*)mel_lens, out, (long long*)mel2ph,
+                                  (int)B, (int)T, (int)L, (int)C, (cudaStream_t)stream);
+}
+
+extern "C" int cmtts_round_durations(const float* log_d, float d_control, const int64_t* src_lens, float* d_rounded,
+                                     int64_t* cumsum, int64_t* mel_lens, int64_t B, int64_t T, void* stream) {
+    return launch_round_durations(log_d, d_control, (const long long*)src_lens, d_rounded, (long long*)cumsum,
+                                  (long long*)mel_lens, (int)B, (int)T, (cudaStream_t)stream);
+}

@@ -1,0 +1,338 @@
+"""Host-side mirror of the reference's acoustic-model seam.
+
+`CMTotalTTS` keeps the call protocol of model/cm_tool/tts_net.py:40-183:
+
+    model, diffusion = create_model_and_diffusion_tts(use_fp16, weight_schedule, tts_model_config, ...)
+    model.load_state_dict(torch.load(".../CMDenoiserTTS/model000000.pt")); model.to(dev); model.eval()
+    dpen, denoise_fun = model.get_segmentation_model()
+    out_dict = dpen(speakers=, texts=, src_lens=, spker_embeds=)          # cmtts.py:44-122
+    y = model(x[B,1,L,80], timesteps[B], speakers=, texts=, src_lens=, spker_embeds=)   # tts_net.py:75
+
+but every tensor op runs in libcmtts_b200.so (hand-written sm_100a CUDA) through the C ABI.
+PyTorch is used for device memory, streams and the module-like surface only.  There is no CPU
+path: tensors must live on a CUDA device and the library must be built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .config import ModelSpec
+from .weights import PackedAcoustic
+
+
+class _Workspace:
+    """Grow-only scratch buffers in HBM, one per stage, reused across calls on the same stream."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs: Dict[str, torch.Tensor] = {}
+
+    def get(self, name: str, nbytes: int) -> torch.Tensor:
+        b = self.bufs.get(name)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            self.bufs[name] = b
+        return b
+
+
+class DurationPitchSpeakerNet:
+    """`duration_pitch_energy_net` callable: FastSpeech2 FFT encoder + variance adaptor
+    (model/cmtts.py:44-122, inference branch)."""
+
+    def __init__(self, owner: "CMTotalTTS"):
+        self.owner = owner
+
+    def __call__(self, speakers=None, texts=None, src_lens=None, mels=None, mel_lens=None,
+                 p_targets=None, e_targets=None, d_targets=None, mel2phs=None, spker_embeds=None,
+                 p_control=1.0, e_control=1.0, d_control=1.0) -> dict:
+        if p_targets is not None or e_targets is not None or d_targets is not None:
+            raise NotImplementedError("teacher-forced targets are a training path (out of scope)")
+        max_mel_len = None if mels is None else int(mels.shape[2])  # cmtts.py:60-63
+        return self.owner.dpen(texts, src_lens, spker_embeds, max_mel_len, float(p_control),
+                               float(e_control), float(d_control))
+
+
+class CMTotalTTS:
+    """B200-native stand-in for model/cm_tool/tts_net.py:CMTotalTTS (inference only)."""
+
+    def __init__(self, use_fp16=False, args=None, preprocess_config=None, model_config=None,
+                 train_config=None, spec: Optional[ModelSpec] = None, **_ignored):
+        if use_fp16:
+            raise NotImplementedError("use_fp16 converts the torso for training; inference here is fp32-class")
+        if spec is None:
+            spec = ModelSpec.from_reference_configs(preprocess_config, model_config, train_config)
+        self.spec = spec
+        self.device = torch.device("cpu")
+        self._sd: Optional[Dict[str, torch.Tensor]] = None
+        self.packed: Optional[PackedAcoustic] = None
+        self.training = False
+        self.duration_pitch_energy_net = DurationPitchSpeakerNet(self)
+        self._ws: Optional[_Workspace] = None
+        self.lib = _lib.load()
+
+    # ---- nn.Module-like surface used by synthesize.py:79-86 ---------------------------------
+    def load_state_dict(self, state_dict, strict: bool = True):
+        self._sd = {k: v.detach().to("cpu") for k, v in state_dict.items()}
+        if self.device.type == "cuda":
+            self._repack()
+        return self
+
+    def state_dict(self):
+        return dict(self._sd) if self._sd is not None else {}
+
+    def to(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.CmttsError("cmtts_b200 runs on CUDA devices only (no CPU fallback)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = device
+        if self._sd is not None:
+            self._repack()
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", torch.cuda.current_device() if device is None else device))
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode=True):
+        if mode:
+            raise NotImplementedError("training is out of scope for the B200 inference path")
+        return self
+
+    def parameters(self):
+        return iter(())
+
+    def _repack(self):
+        self.packed = PackedAcoustic(self.spec, self._sd, self.device)
+        self._dims = self.packed.dims()
+        self._ws = _Workspace(self.device)
+
+    def _ready(self):
+        if self.packed is None:
+            raise _lib.CmttsError("CMTotalTTS: call load_state_dict(...) and .to('cuda') first")
+
+    # ---- encoder + variance adaptor --------------------------------------------------------
+    def dpen(self, texts: torch.Tensor, src_lens: torch.Tensor, spker_embeds: Optional[torch.Tensor],
+             max_mel_len: Optional[int] = None, p_control=1.0, e_control=1.0, d_control=1.0,
+             l_max_hook=None) -> dict:
+        """Returns the reference's out_dict (cmtts.py:108-121) plus the integer side products
+        (`mel2ph`, `e_idx`, `pitch_idx`).  One host sync: `mel_lens` must reach the host to size
+        the frame-rate tensors (the reference syncs B*T times in LengthRegulator.expand).
+        `l_max_hook(local_max) -> global_max` lets the multi-GPU driver all-reduce L_max."""
+        self._ready()
+        lib, s, dev = self.lib, self.spec, self.device
+        if s.multi_speaker and spker_embeds is None:
+            raise AssertionError("Speaker embedding should not be None")  # cmtts.py:80
+        texts = texts.to(dev, torch.int64).contiguous()
+        src_lens = src_lens.to(dev, torch.int64).contiguous()
+        B, T = texts.shape
+        spk_in = None if spker_embeds is None or not s.multi_speaker else \
+            spker_embeds.to(dev, torch.float32).contiguous()
+        self.packed_check_rows(T)
+        d = C.byref(self._dims)
+        st = _lib.stream_ptr(dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        i64 = dict(dtype=torch.int64, device=dev)
+        H = s.hidden
+        with torch.cuda.device(dev):
+            enc = torch.empty(B, T, H, **f32)
+            ws = self._ws.get("enc", lib.cmtts_encoder_workspace_bytes(d, B, T))
+            _lib.check(lib.cmtts_encoder_forward(d, self.packed.enc.ptrs, _lib.ptr(texts), _lib.ptr(src_lens), B, T,
+                                                 _lib.ptr(enc), _lib.ptr(ws), ws.numel(), st), "encoder_forward")
+            out1 = torch.empty(B, T, H, **f32)
+            log_d = torch.empty(B, T, **f32)
+            d_rounded = torch.empty(B, T, **f32)
+            e_pred = torch.empty(B, T, **f32)
+            e_idx = torch.empty(B, T, **i64)
+            cumsum = torch.empty(B, 2, T, **i64)
+            mel_lens = torch.empty(B, **i64)
+            spk = torch.empty(B, H, **f32) if s.multi_speaker else None
+            f0_stats = torch.empty(B, 4, **f32)
+            ws = self._ws.get("vat", lib.cmtts_variance_token_workspace_bytes(d, B, T))
+            _lib.check(lib.cmtts_variance_token(
+                d, self.packed.va.ptrs, _lib.ptr(enc), _lib.ptr(src_lens), _lib.ptr(spk_in), e_control, d_control,
+                B, T, _lib.ptr(out1), _lib.ptr(log_d), _lib.ptr(d_rounded), _lib.ptr(e_pred), _lib.ptr(e_idx),
+                _lib.ptr(cumsum), _lib.ptr(mel_lens), _lib.ptr(spk), _lib.ptr(f0_stats), _lib.ptr(ws), ws.numel(), st),
+                "variance_token")
+            # the one host round trip of the path: output length is data dependent
+            local_max = int(mel_lens.max().item()) if B > 0 else 0
+            if l_max_hook is not None:
+                local_max = int(l_max_hook(local_max))
+            L = int(max_mel_len) if max_mel_len else local_max
+            self.packed_check_rows(L)
+            cond = torch.empty(B, L, H, **f32)
+            mel2ph = torch.empty(B, L, **i64)
+            cwt = torch.empty(B, L, s.cwt_out, **f32)
+            f0_denorm = torch.empty(B, L, **f32)
+            pitch_idx = torch.empty(B, L, **i64)
+            if L > 0:
+                d = C.byref(self._dims)
+                ws = self._ws.get("vaf", lib.cmtts_variance_frame_workspace_bytes(d, B, L))
+                _lib.check(lib.cmtts_variance_frame(
+                    d, self.packed.va.ptrs, _lib.ptr(out1), _lib.ptr(cumsum), _lib.ptr(mel_lens), _lib.ptr(f0_stats),
+                    p_control, B, T, L, _lib.ptr(cond), _lib.ptr(mel2ph), _lib.ptr(cwt), _lib.ptr(f0_denorm),
+                    _lib.ptr(pitch_idx), _lib.ptr(ws), ws.numel(), st), "variance_frame")
+        ar_t = torch.arange(T, device=dev)
+        ar_l = torch.arange(local_max, device=dev)
+        return {
+            "cond": cond,
+            "p_targets": None,
+            "p_predictions": {"pitch_pred": None, "f0_denorm": f0_denorm, "cwt": cwt,
+                              "f0_mean": f0_stats[:, 0], "f0_std": f0_stats[:, 1]},
+            "e_predictions": e_pred,
+            "log_d_predictions": log_d,
+            "d_rounded": d_rounded,
+            "mel_lens": mel_lens,
+            "mel_masks": ar_l[None, :] >= mel_lens[:, None],       # get_mask_from_lengths(mel_len)
+            "src_masks": ar_t[None, :] >= src_lens[:, None],
+            "speaker_emb": spk,
+            "src_lens": src_lens,
+            # extras (not in the reference dict)
+            "enc": enc, "mel2ph": mel2ph, "e_idx": e_idx, "pitch_idx": pitch_idx,
+        }
+
+    def packed_check_rows(self, n: int):
+        if n + 2 > self.packed.pe_rows:
+            self.packed.ensure_pe_rows(n)
+            self._dims = self.packed.dims()
+
+    # ---- denoiser ----------------------------------------------------------------------------
+    def prepare_steps(self, timesteps: torch.Tensor, speaker_emb: Optional[torch.Tensor]):
+        """Step-embedding MLP and the per-layer diffusion/speaker projections (blocks.py:633-640,
+        :669-674): sigma-only work, hoisted out of the solver loop."""
+        self._ready()
+        lib, s, dev = self.lib, self.spec, self.device
+        t = timesteps.to(dev, torch.float32).contiguous()
+        B = t.shape[0]
+        n = s.res_layers * s.res_channels
+        ds_all = torch.empty(B, n, dtype=torch.float32, device=dev)
+        dsp_all = torch.empty(B, n, dtype=torch.float32, device=dev) if s.multi_speaker else ds_all
+        d = C.byref(self._dims)
+        ws = self._ws.get("dnp", lib.cmtts_denoiser_prepare_workspace_bytes(d, B))
+        with torch.cuda.device(dev):
+            _lib.check(lib.cmtts_denoiser_prepare(d, self.packed.dn.ptrs, _lib.ptr(t),
+                                                  _lib.ptr(speaker_emb) if s.multi_speaker else None, B,
+                                                  _lib.ptr(ds_all), _lib.ptr(dsp_all), _lib.ptr(ws), ws.numel(),
+                                                  _lib.stream_ptr(dev)), "denoiser_prepare")
+        return ds_all, dsp_all
+
+    def denoise_step(self, x_t: torch.Tensor, cond: torch.Tensor, steps: Tuple[torch.Tensor, torch.Tensor],
+                     c_in: float = 1.0, c_out: float = 1.0, c_skip: float = 0.0, want_model_out: bool = False):
+        """out = c_out * F(c_in * x_t) + c_skip * x_t on (B,1,L,M) / (B,L,M) channels-last mels."""
+        self._ready()
+        lib, s, dev = self.lib, self.spec, self.device
+        shape = x_t.shape
+        x = x_t.to(dev, torch.float32).contiguous().view(-1, shape[-2], shape[-1])
+        B, L, M = x.shape
+        if M != s.n_mels or tuple(cond.shape) != (B, L, s.hidden):
+            raise ValueError(f"denoise_step: x {tuple(shape)} / cond {tuple(cond.shape)} mismatch")
+        cond = cond.to(dev, torch.float32).contiguous()
+        out = torch.empty_like(x)
+        mo = torch.empty_like(x) if want_model_out else None
+        d = C.byref(self._dims)
+        ws = self._ws.get("dn", lib.cmtts_denoiser_workspace_bytes(d, B, L))
+        with torch.cuda.device(dev):
+            _lib.check(lib.cmtts_denoiser_forward(d, self.packed.dn.ptrs, _lib.ptr(x), _lib.ptr(cond),
+                                                  _lib.ptr(steps[0]), _lib.ptr(steps[1]), c_in, c_out, c_skip, B, L,
+                                                  _lib.ptr(out), _lib.ptr(mo), _lib.ptr(ws), ws.numel(),
+                                                  _lib.stream_ptr(dev)), "denoiser_forward")
+        out = out.view(shape)
+        return (out, mo.view(shape)) if want_model_out else out
+
+    def get_segmentation_model(self):
+        """tts_net.py:66-73 -> (dpen callable, denoise_fun(mel[B,1,L,80]... ) in the reference's
+        argument order: denoise_fun(mel, diffusion_step, conditioner[B,L,256], speaker_emb)."""
+
+        def denoise_fun(mel, diffusion_step, conditioner, speaker_emb, mask=None):
+            steps = self.prepare_steps(diffusion_step, speaker_emb)
+            return self.denoise_step(mel, conditioner, steps)
+
+        return self.duration_pitch_energy_net, denoise_fun
+
+    def forward(self, x, timesteps, speakers=None, texts=None, src_lens=None, spker_embeds=None,
+                p_control=1.0, e_control=1.0, d_control=1.0, pitch=None, **kwargs):
+        """tts_net.py:75-183: conditioner from (texts, src_lens, spker_embeds), padded to x's length,
+        then the denoiser on x (already scaled by c_in by the caller).  -> (B,1,L,80)."""
+        if pitch is not None:
+            raise NotImplementedError("training targets are out of scope")
+        out = self.dpen(texts, src_lens, spker_embeds, int(x.shape[2]), p_control, e_control, d_control)
+        steps = self.prepare_steps(timesteps, out["speaker_emb"])
+        return self.denoise_step(x, out["cond"], steps)
+
+    __call__ = forward
+
+    def get_tts_loss(self):
+        return None
+
+
+class CMDenoiserTTS:
+    """tts_net.py:13-37 — denoiser-only wrapper (unused by the reference's scripts, kept for API
+    completeness): forward(x[B,1,L,80], timesteps, conditioner[B,L,256], speaker_emb)."""
+
+    def __init__(self, total: CMTotalTTS):
+        self.total = total
+
+    def forward(self, x, timesteps, conditioner=None, speaker_emb=None, mask=None):
+        steps = self.total.prepare_steps(timesteps, speaker_emb)
+        return self.total.denoise_step(x, conditioner, steps)
+
+    __call__ = forward
+
+
+class KarrasDenoiser:
+    """model/cm_tool/karras_diffusion.py:KarrasDenoiser — the inference members only."""
+
+    def __init__(self, sigma_data: float = 0.5, sigma_max=80.0, sigma_min=0.002, rho=7.0,
+                 weight_schedule="karras", distillation=False, loss_norm="mel_loss"):
+        self.sigma_data, self.sigma_max, self.sigma_min, self.rho = sigma_data, sigma_max, sigma_min, rho
+        self.weight_schedule, self.distillation, self.loss_norm = weight_schedule, distillation, loss_norm
+        self.num_timesteps = 40
+
+    def get_scalings(self, sigma):
+        c_skip = self.sigma_data ** 2 / (sigma ** 2 + self.sigma_data ** 2)
+        c_out = sigma * self.sigma_data / (sigma ** 2 + self.sigma_data ** 2) ** 0.5
+        c_in = 1 / (sigma ** 2 + self.sigma_data ** 2) ** 0.5
+        return c_skip, c_out, c_in
+
+    def get_scalings_for_boundary_condition(self, sigma):
+        """karras_diffusion.py:87-102."""
+        c_skip = self.sigma_data ** 2 / ((sigma - self.sigma_min) ** 2 + self.sigma_data ** 2)
+        c_out = (sigma - self.sigma_min) * self.sigma_data / (sigma ** 2 + self.sigma_data ** 2) ** 0.5
+        c_in = 1 / (sigma ** 2 + self.sigma_data ** 2) ** 0.5
+        return c_skip, c_out, c_in
+
+    def scalar_plan(self, sigma_value: float):
+        """The fp32 scalars the reference's tensor ops produce for a uniform sigma
+        (`t * s_in` is an fp32 tensor; all following ops are fp32): (c_skip, c_out, c_in, 250 ln sigma)."""
+        sig = torch.tensor([sigma_value], dtype=torch.float64).to(torch.float32)
+        fn = self.get_scalings_for_boundary_condition if self.distillation else self.get_scalings
+        c_skip, c_out, c_in = fn(sig)
+        rescaled_t = 1000 * 0.25 * torch.log(sig + 1e-44)
+        return float(c_skip), float(c_out), float(c_in), float(rescaled_t)
+
+    def denoise(self, model, x_t, sigmas, **model_kwargs):
+        """karras_diffusion.py:392-407 (generic form: any model callable, per-sample sigmas)."""
+        fn = self.get_scalings_for_boundary_condition if self.distillation else self.get_scalings
+        c_skip, c_out, c_in = [v[(...,) + (None,) * (x_t.ndim - v.ndim)] for v in fn(sigmas)]
+        rescaled_t = 1000 * 0.25 * torch.log(sigmas + 1e-44)
+        model_output = model(c_in * x_t, rescaled_t, **model_kwargs)
+        denoised = c_out * model_output + c_skip * x_t
+        return model_output, denoised
+
+
+def create_model_and_diffusion_tts(use_fp16, weight_schedule, tts_model_config, sigma_min=0.002,
+                                   sigma_max=80.0, distillation=False, loss_norm="mel_loss", **kwargs):
+    """model/cm_tool/script_util.py:56-75."""
+    model = CMTotalTTS(use_fp16=use_fp16, **tts_model_config)
+    diffusion = KarrasDenoiser(sigma_data=0.5, sigma_max=sigma_max, sigma_min=sigma_min,
+                               distillation=distillation, weight_schedule=weight_schedule, loss_norm=loss_norm)
+    return model, diffusion

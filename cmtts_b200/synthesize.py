@@ -1,0 +1,164 @@
+"""Synthesis driver with the reference's protocol (synthesize.py:35-153, p_rtf_cm.py:174-230).
+
+    tool = CMTotalTTSSynthesize(model_path, restore_step, args, preprocess_config, model_config, train_config)
+    out_put = tool.synthesize(batch)        # batch = the reference's 7-tuple; out_put[0] = mel (B, L, 80),
+                                            # out_put[10] = src_lens, out_put[11] = mel_lens
+
+Differences from the reference that do not change results: the checkpoint is loaded once (the
+reference reloads it for every batch, synthesize.py:203), the conditioner is computed once per
+batch instead of T+1 times, and the pre-pass result is reused by the sampler.
+`Pipeline` is the whole hot path (host batch -> int16 wavs) used by bench.py and the multi-GPU
+driver.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import time
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import HifiGanSpec, ModelSpec
+from .model import CMTotalTTS, KarrasDenoiser, create_model_and_diffusion_tts
+from .sampler import karras_sample_tts, sampler_plan
+from .vocoder import Generator, vocoder_infer
+
+
+def to_device(data, device):
+    """utils/tools.py:103-112 — the 7-tuple inference batch:
+    (ids, raw_texts, speakers, texts, src_lens, max_src_len, spker_embeds)."""
+    if len(data) != 7:
+        raise ValueError("inference batches are 7-tuples (utils/tools.py:103-112)")
+    ids, raw_texts, speakers, texts, src_lens, max_src_len, spker_embeds = data
+    speakers = torch.as_tensor(np.asarray(speakers)).long().to(device)
+    texts = torch.as_tensor(np.asarray(texts)).long().to(device)
+    src_lens = torch.as_tensor(np.asarray(src_lens)).to(device)
+    if spker_embeds is not None:
+        spker_embeds = torch.as_tensor(np.asarray(spker_embeds)).float().to(device)
+    return [ids, raw_texts, speakers, texts, src_lens, max_src_len, spker_embeds]
+
+
+class CMTotalTTSSynthesize:
+    """synthesize.py:35-153."""
+
+    def __init__(self, model_path, model_step_num, args, preprocess_config, model_config, train_config,
+                 p_control=1.0, e_control=1.0, d_control=1.0, device=None, spec: Optional[ModelSpec] = None):
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.CMDenoiserTTS_path = os.path.join(model_path, "CMDenoiserTTS", "model{:06d}.pt".format(model_step_num))
+        self.args = args
+        self.train_config = train_config
+        self.p_control, self.e_control, self.d_control = p_control, e_control, d_control
+        self.model, self.diffusion = self.load_cm_model(args, preprocess_config, model_config, train_config, spec)
+        self.duration_pitch_energy_net, self.denoise_net = self.model.get_segmentation_model()
+
+    def load_cm_model(self, args, preprocess_config, model_config, train_config, spec=None):
+        cm = dict(train_config.get("cm", {})) if train_config else {}
+        mode = cm.get("training_mode", "consistency_distillation")
+        if mode == "progdist":
+            distillation = False
+        elif "consistency" in mode:
+            distillation = True
+        else:
+            raise ValueError(f"unknown training mode {mode}")   # synthesize.py:66
+        if spec is not None:
+            model = CMTotalTTS(spec=spec)
+            diffusion = KarrasDenoiser(sigma_data=0.5, sigma_max=spec.sigma_max, sigma_min=spec.sigma_min,
+                                       distillation=distillation)
+        else:
+            model, diffusion = create_model_and_diffusion_tts(
+                use_fp16=cm.get("use_fp16", False), weight_schedule=cm.get("weight_schedule", "uniform"),
+                tts_model_config={"args": args, "train_config": train_config,
+                                  "preprocess_config": preprocess_config, "model_config": model_config},
+                sigma_min=cm.get("sigma_min", 0.002), sigma_max=cm.get("sigma_max", 80.0),
+                distillation=distillation, loss_norm=cm.get("loss_norm", "mel_loss"))
+        model.load_state_dict(torch.load(self.CMDenoiserTTS_path, map_location="cpu", weights_only=True))
+        model.to(self.device)
+        model.eval()
+        return model, diffusion
+
+    def synthesize(self, batch, T: Optional[int] = None, generator=None, trace=None):
+        T = int(T if T is not None else getattr(self.args, "T", 1))
+        kw = {"speakers": batch[2], "texts": batch[3], "src_lens": batch[4], "spker_embeds": batch[-1]}
+        out_dict = self.duration_pitch_energy_net(**kw)
+        batch_size, seq_len, _ = out_dict["cond"].size()
+        sampler, steps, ts = sampler_plan(T)
+        s = self.model.spec
+        sample = karras_sample_tts(
+            diffusion=self.diffusion, model=self.model, shape=(batch_size, 1, seq_len, s.n_mels),
+            model_kwargs=kw, device=self.device, sigma_max=self.diffusion.sigma_max,
+            sigma_min=self.diffusion.sigma_min, sampler=sampler, steps=steps, ts=ts,
+            generator=generator, cond_dict=out_dict, trace=trace)
+        out_put = [None] * 12
+        out_put[0] = sample
+        out_put[10] = kw["src_lens"]
+        out_put[11] = out_dict["mel_lens"]
+        self.last_out_dict = out_dict
+        return out_put
+
+
+class Pipeline:
+    """Whole hot path on one GPU: host phoneme ids (+ speaker embeddings) -> mels -> int16 wavs.
+
+    Mirrors what p_rtf_cm.py:174-226 strings together (encoder + variance adaptor, T solver steps,
+    HiFi-GAN on the whole padded batch, x32768 -> int16, crop to mel_len * hop)."""
+
+    def __init__(self, spec: ModelSpec, acoustic_sd: Dict[str, torch.Tensor], hifigan_sd: Dict[str, torch.Tensor],
+                 device, distillation: bool = True):
+        self.spec = spec
+        self.device = torch.device(device)
+        self.model = CMTotalTTS(spec=spec).load_state_dict(acoustic_sd).to(self.device)
+        self.diffusion = KarrasDenoiser(sigma_data=spec.sigma_data, sigma_max=spec.sigma_max,
+                                        sigma_min=spec.sigma_min, rho=spec.rho, distillation=distillation)
+        self.vocoder = Generator(hspec=spec.hifigan).load_state_dict(hifigan_sd).to(self.device)
+
+    def acoustic(self, texts, src_lens, spker_embeds, T: int, generator=None, l_max_hook=None, trace=None):
+        out = self.model.dpen(texts, src_lens, spker_embeds, None, l_max_hook=l_max_hook)
+        B, L, _ = out["cond"].shape
+        sampler, steps, ts = sampler_plan(T)
+        kw = {"texts": texts, "src_lens": src_lens, "spker_embeds": spker_embeds}
+        mel = karras_sample_tts(self.diffusion, self.model, (B, 1, L, self.spec.n_mels), steps=steps,
+                                model_kwargs=kw, device=self.device, sigma_min=self.spec.sigma_min,
+                                sigma_max=self.spec.sigma_max, sampler=sampler, ts=ts, generator=generator,
+                                cond_dict=out, trace=trace)
+        return mel, out
+
+    def __call__(self, texts, src_lens, spker_embeds=None, T: int = 1, generator=None, want_float_wav: bool = False,
+                 l_max_hook=None):
+        mel, out = self.acoustic(texts, src_lens, spker_embeds, T, generator, l_max_hook)
+        wav, w16 = self.vocoder.run(mel, want_float=want_float_wav, want_int16=True,
+                                    max_wav_value=self.spec.max_wav_value)
+        return {"mel": mel, "mel_lens": out["mel_lens"], "wav_i16": w16, "wav": wav, "dpen": out}
+
+    def crop(self, w16_host: np.ndarray, mel_lens: Sequence[int]) -> List[np.ndarray]:
+        """utils/model.py:201-203."""
+        return [w16_host[i, : int(n) * self.spec.hop_length] for i, n in enumerate(mel_lens)]
+
+
+def rtf_like_reference(pipe: Pipeline, texts, src_lens, spker_embeds, T: int, out_wav_path: Optional[str] = None):
+    """RTF exactly as p_rtf_cm.py:190-230 defines it: the timer starts AFTER the encoder/variance
+    pre-pass, and stops after sampling, vocoding the whole batch, D2H, int16 conversion and writing
+    the FIRST wav; divided by the duration of that first utterance.  Returns (rtf_ref, rtf_total, elapsed)."""
+    dev = pipe.device
+    out = pipe.model.dpen(texts, src_lens, spker_embeds, None)
+    torch.cuda.synchronize(dev)
+    t0 = time.time()
+    B, L, _ = out["cond"].shape
+    sampler, steps, ts = sampler_plan(T)
+    kw = {"texts": texts, "src_lens": src_lens, "spker_embeds": spker_embeds}
+    mel = karras_sample_tts(pipe.diffusion, pipe.model, (B, 1, L, pipe.spec.n_mels), steps=steps, model_kwargs=kw,
+                            device=dev, sigma_min=pipe.spec.sigma_min, sigma_max=pipe.spec.sigma_max,
+                            sampler=sampler, ts=ts, cond_dict=out)
+    _, w16 = pipe.vocoder.run(mel, want_float=False, want_int16=True, max_wav_value=pipe.spec.max_wav_value)
+    host = w16.cpu().numpy()
+    mel_lens = out["mel_lens"].cpu().tolist()
+    wavs = pipe.crop(host, mel_lens)
+    if out_wav_path is not None:
+        from scipy.io import wavfile
+        wavfile.write(out_wav_path, pipe.spec.sampling_rate, wavs[0])
+    elapsed = time.time() - t0
+    dur0 = mel_lens[0] * pipe.spec.hop_length / pipe.spec.sampling_rate
+    total = sum(mel_lens) * pipe.spec.hop_length / pipe.spec.sampling_rate
+    return elapsed / dur0, elapsed / total, elapsed

@@ -1,0 +1,272 @@
+"""Checkpoint layout -> device-resident, kernel-ready weight tables.
+
+Input is exactly what the reference loads: the flat `state_dict` of `CMTotalTTS`
+(`<model_path>/CMDenoiserTTS/model{step:06d}.pt`, synthesize.py:44-48, :79-83) and the HiFi-GAN
+checkpoint `{"generator": state_dict}` with `weight_g`/`weight_v` (utils/model.py:170-184).
+Output are fp32 tensors in HBM re-packed for the channels-last implicit-GEMM kernels
+(conv weights as [tap][Cin][Cout]) plus ctypes pointer tables in the order
+csrc/pipeline.cu expects (include/cmtts_b200.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import F0_MEL_MAX, F0_MEL_MIN, HifiGanSpec, ModelSpec
+from .synthetic import fold_weight_norm
+
+TE = "duration_pitch_energy_net.text_encoder."
+VA = "duration_pitch_energy_net.variance_adaptor."
+SPK = "duration_pitch_energy_net.speaker_emb."
+
+ACT_CODES = {"relu": 1, "gelu": 2, "swish": 6}
+
+
+def sinusoid_table(n: int, dim: int) -> torch.Tensor:
+    """SinusoidalPositionalEmbedding.get_embedding (model/blocks.py:44-60), fp32 on CPU so the
+    table holds the same bits the reference indexes; row 0 (padding_idx) is zero."""
+    half = dim // 2
+    e = math.log(10000) / (half - 1)
+    e = torch.exp(torch.arange(half, dtype=torch.float) * -e)
+    e = torch.arange(n, dtype=torch.float).unsqueeze(1) * e.unsqueeze(0)
+    tab = torch.cat([torch.sin(e), torch.cos(e)], dim=1).view(n, -1)
+    if dim % 2 == 1:
+        tab = torch.cat([tab, torch.zeros(n, 1)], dim=1)
+    tab[0, :] = 0
+    return tab
+
+
+def conv_w(w: torch.Tensor) -> torch.Tensor:
+    """(Cout, Cin, k) -> [k][Cin][Cout]."""
+    return w.permute(2, 1, 0).contiguous()
+
+
+def lin_w(w: torch.Tensor) -> torch.Tensor:
+    """(out, in) -> [in][out]."""
+    return w.t().contiguous()
+
+
+def gate_permutation(C: int, tile: int = 64) -> torch.Tensor:
+    """Column order for the gated k=3 conv: each 128-wide GEMM tile holds 64 gate columns followed
+    by the 64 matching filter columns (torch.chunk(y, 2, dim=1) pairs channel c with c + C,
+    model/blocks.py:680)."""
+    idx = []
+    for t in range(C // tile):
+        idx += list(range(t * tile, (t + 1) * tile))            # gates
+        idx += list(range(C + t * tile, C + (t + 1) * tile))    # filters
+    return torch.tensor(idx, dtype=torch.long)
+
+
+def pack_conv_transpose(w: torch.Tensor, bias: torch.Tensor, stride: int, padding: int):
+    """ConvTranspose1d(Cin, Cout, k, stride u, padding p) as an ordinary conv with u*Cout output
+    channels: out[q*u + r, co] = sum_{delta, ci} x[q + delta, ci] * w[ci, co, r + p - delta*u].
+    Returns (packed [taps][Cin][u*Cout], bias replicated u times, first delta)."""
+    cin, cout, k = w.shape
+    u, p = stride, padding
+    if (k - u) != 2 * p:
+        raise NotImplementedError("ConvTranspose1d packing needs k - stride == 2 * padding (output length = stride * L)")
+    deltas = [dl for dl in range(-k, k + 1) if any(0 <= r + p - dl * u < k for r in range(u))]
+    d0, d1 = min(deltas), max(deltas)
+    out = torch.zeros(d1 - d0 + 1, cin, u * cout, dtype=w.dtype)
+    for dl in range(d0, d1 + 1):
+        for r in range(u):
+            j = r + p - dl * u
+            if 0 <= j < k:
+                out[dl - d0, :, r * cout:(r + 1) * cout] = w[:, :, j]
+    return out.contiguous(), bias.repeat(u).contiguous(), d0
+
+
+class _Table:
+    """Keeps the device tensors alive next to the ctypes pointer array that references them."""
+
+    def __init__(self, device):
+        self.device = device
+        self.tensors: List[Optional[torch.Tensor]] = []
+
+    def add(self, t: Optional[torch.Tensor]) -> int:
+        if t is not None:
+            t = t.detach().to(torch.float32).contiguous().to(self.device)
+            if t.data_ptr() % 16 != 0:
+                raise _lib.CmttsError("weight tensor not 16-byte aligned")
+        self.tensors.append(t)
+        return len(self.tensors) - 1
+
+    def finish(self):
+        self.ptrs = _lib.pointer_table(self.tensors)
+        return self
+
+
+class PackedAcoustic:
+    """Encoder + variance adaptor + denoiser weights of one CMTotalTTS checkpoint."""
+
+    def __init__(self, spec: ModelSpec, sd: Dict[str, torch.Tensor], device, pe_rows: int = 4096):
+        self.spec = spec
+        self.device = torch.device(device)
+        self.pe_rows = int(pe_rows)
+        sd = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
+        self._check_layout(sd)
+        self.sd_cpu = sd
+        self._pack(sd)
+
+    # -- layout check ------------------------------------------------------------------------
+    def _check_layout(self, sd):
+        s = self.spec
+        need = {
+            TE + "embed_tokens.weight": (s.vocab, s.hidden),
+            TE + "layers.0.op.self_attn.in_proj_weight": (3 * s.hidden, s.hidden),
+            TE + "layers.0.op.ffn.ffn_1.weight": (4 * s.hidden, s.hidden, s.ffn_kernel),
+            VA + "energy_bins": (s.energy_bins - 1,),
+            VA + "cwt_predictor.1.linear.weight": (s.cwt_out, s.filter_size),
+            VA + "pitch_embed.weight": (s.pitch_bins, s.hidden),
+            "net.input_projection.0.conv.weight": (s.res_channels, s.n_mels, 1),
+            f"net.residual_layers.{s.res_layers - 1}.conv_layer.conv.weight": (2 * s.res_channels, s.res_channels, 3),
+            "net.output_projection.conv.weight": (s.n_mels, s.res_channels, 1),
+        }
+        if s.multi_speaker:
+            need[SPK + "weight"] = (s.hidden, s.ext_speaker_dim)
+            need["net.residual_layers.0.speaker_projection.linear.weight"] = (s.res_channels, s.hidden)
+        for k, shp in need.items():
+            if k not in sd:
+                raise KeyError(f"checkpoint is missing {k!r} (expected the CMTotalTTS state_dict layout)")
+            if tuple(sd[k].shape) != tuple(shp):
+                raise ValueError(f"{k}: shape {tuple(sd[k].shape)} != expected {shp} for spec {s.name}")
+
+    def dims(self) -> _lib.Dims:
+        s = self.spec
+        return _lib.Dims(
+            hidden=s.hidden, enc_layers=s.enc_layers, enc_heads=s.enc_heads, ffn_kernel=s.ffn_kernel,
+            ffn_act=ACT_CODES[s.ffn_act], filter=s.filter_size, dur_layers=s.dur_layers,
+            dur_kernel=s.dur_kernel, pred_layers=s.pred_layers, pred_kernel=s.pred_kernel,
+            cwt_hidden=s.cwt_hidden, cwt_out=s.cwt_out, use_uv=int(s.use_uv), energy_bins=s.energy_bins,
+            pitch_bins=s.pitch_bins, n_mels=s.n_mels, res_layers=s.res_layers, res_channels=s.res_channels,
+            multi_speaker=int(s.multi_speaker), spk_dim=s.ext_speaker_dim, pe_rows=self.pe_rows,
+            cwt_std_scale=s.cwt_std_scale, pitch_eps=s.pitch_norm_eps,
+            f0_mel_min=float(np.float32(F0_MEL_MIN)), f0_mel_span=float(np.float32(F0_MEL_MAX - F0_MEL_MIN)),
+        )
+
+    # -- packing -----------------------------------------------------------------------------
+    def _pack(self, sd):
+        s, dev = self.spec, self.device
+        H, C = s.hidden, s.res_channels
+        pe_c = sinusoid_table(self.pe_rows, H)
+        pe_h = sinusoid_table(self.pe_rows, s.cwt_hidden)
+
+        enc = _Table(dev)
+        enc.add(sd[TE + "embed_tokens.weight"])
+        enc.add(pe_c)
+        for l in range(s.enc_layers):
+            p = f"{TE}layers.{l}.op."
+            enc.add(sd[p + "layer_norm1.weight"]); enc.add(sd[p + "layer_norm1.bias"])
+            enc.add(lin_w(sd[p + "self_attn.in_proj_weight"]))
+            enc.add(lin_w(sd[p + "self_attn.out_proj.weight"]))
+            enc.add(sd[p + "layer_norm2.weight"]); enc.add(sd[p + "layer_norm2.bias"])
+            enc.add(conv_w(sd[p + "ffn.ffn_1.weight"])); enc.add(sd[p + "ffn.ffn_1.bias"])
+            enc.add(lin_w(sd[p + "ffn.ffn_2.weight"])); enc.add(sd[p + "ffn.ffn_2.bias"])
+        enc.add(sd[TE + "layer_norm.weight"]); enc.add(sd[TE + "layer_norm.bias"])
+        self.enc = enc.finish()
+
+        va = _Table(dev)
+        if s.multi_speaker:
+            va.add(lin_w(sd[SPK + "weight"])); va.add(sd[SPK + "bias"])
+        else:
+            va.add(None); va.add(None)
+
+        def predictor(prefix, n_layers, with_alpha):
+            if with_alpha:
+                va.add(sd[prefix + "pos_embed_alpha"].reshape(1).repeat(4))
+            for i in range(n_layers):
+                va.add(conv_w(sd[f"{prefix}conv.{i}.1.weight"])); va.add(sd[f"{prefix}conv.{i}.1.bias"])
+                va.add(sd[f"{prefix}conv.{i}.3.weight"]); va.add(sd[f"{prefix}conv.{i}.3.bias"])
+            va.add(sd[prefix + "linear.weight"]); va.add(sd[prefix + "linear.bias"])
+
+        predictor(VA + "duration_predictor.", s.dur_layers, False)
+        predictor(VA + "energy_predictor.", s.pred_layers, True)
+        va.add(pe_c)
+        va.add(sd[VA + "energy_bins"])
+        va.add(sd[VA + "energy_embedding.weight"])
+        va.add(lin_w(sd[VA + "cwt_stats_layers.0.weight"])); va.add(sd[VA + "cwt_stats_layers.0.bias"])
+        va.add(lin_w(sd[VA + "cwt_stats_layers.2.weight"])); va.add(sd[VA + "cwt_stats_layers.2.bias"])
+        w4 = torch.zeros(s.cwt_hidden, 4); w4[:, :2] = sd[VA + "cwt_stats_layers.4.weight"].t()
+        b4 = torch.zeros(4); b4[:2] = sd[VA + "cwt_stats_layers.4.bias"]
+        va.add(w4); va.add(b4)
+        va.add(lin_w(sd[VA + "cwt_predictor.0.weight"])); va.add(sd[VA + "cwt_predictor.0.bias"])
+        va.add(pe_h)
+        predictor(VA + "cwt_predictor.1.", s.pred_layers, True)
+        # inverse_cwt_torch, utils/pitch_tools.py:246: (arange(10) + 1 + 2.5) ** -2.5 in fp32
+        cwt_b = (torch.arange(0, 10).float() + 1 + 2.5) ** (-2.5)
+        va.add(torch.cat([cwt_b, torch.zeros(2)]))
+        va.add(sd[VA + "pitch_embed.weight"])
+        self.va = va.finish()
+
+        dn = _Table(dev)
+        dn.add(conv_w(sd["net.input_projection.0.conv.weight"])); dn.add(sd["net.input_projection.0.conv.bias"])
+        half = C // 2
+        # DiffusionEmbedding, model/blocks.py:635-637 (arange int64 * python float -> fp32, exp fp32)
+        freq = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1)))
+        dn.add(freq.to(torch.float32))
+        dn.add(lin_w(sd["net.mlp.0.linear.weight"])); dn.add(lin_w(sd["net.mlp.2.linear.weight"]))
+        dn.add(torch.cat([lin_w(sd[f"net.residual_layers.{l}.diffusion_projection.linear.weight"])
+                          for l in range(s.res_layers)], dim=1))
+        if s.multi_speaker:
+            dn.add(torch.cat([lin_w(sd[f"net.residual_layers.{l}.speaker_projection.linear.weight"])
+                              for l in range(s.res_layers)], dim=1))
+        else:
+            dn.add(None)
+        perm = gate_permutation(C)
+        for l in range(s.res_layers):
+            p = f"net.residual_layers.{l}."
+            dn.add(conv_w(sd[p + "conditioner_projection.conv.weight"])); dn.add(sd[p + "conditioner_projection.conv.bias"])
+            dn.add(conv_w(sd[p + "conv_layer.conv.weight"])[:, :, perm]); dn.add(sd[p + "conv_layer.conv.bias"][perm])
+            wo, bo = sd[p + "output_projection.conv.weight"], sd[p + "output_projection.conv.bias"]
+            dn.add(conv_w(wo[:C])); dn.add(bo[:C].clone())
+            dn.add(conv_w(wo[C:])); dn.add(bo[C:].clone())
+        dn.add(conv_w(sd["net.skip_projection.conv.weight"])); dn.add(sd["net.skip_projection.conv.bias"])
+        dn.add(conv_w(sd["net.output_projection.conv.weight"])); dn.add(sd["net.output_projection.conv.bias"])
+        self.dn = dn.finish()
+
+    def ensure_pe_rows(self, n: int) -> None:
+        """Sinusoid tables auto-grow like the reference's (model/blocks.py:65-72)."""
+        if n + 2 > self.pe_rows:
+            self.pe_rows = int(2 ** math.ceil(math.log2(n + 2)))
+            self._pack(self.sd_cpu)
+
+
+class PackedHifiGan:
+    """HiFi-GAN generator weights with weight-norm folded (hifigan/models.py:167-174)."""
+
+    def __init__(self, hspec: HifiGanSpec, generator_sd: Dict[str, torch.Tensor], device):
+        self.hspec = hspec
+        self.device = torch.device(device)
+        sd = fold_weight_norm({k: v.detach().to("cpu", torch.float32) for k, v in generator_sd.items()})
+        t = _Table(self.device)
+        C0 = hspec.upsample_initial_channel
+        if tuple(sd["conv_pre.weight"].shape) != (C0, hspec.n_mels, 7):
+            raise ValueError("conv_pre.weight shape does not match the HiFi-GAN config")
+        t.add(conv_w(sd["conv_pre.weight"])); t.add(sd["conv_pre.bias"])
+        taps, shift0 = [], []
+        for i, (u, k) in enumerate(zip(hspec.upsample_rates, hspec.upsample_kernel_sizes)):
+            w, b, d0 = pack_conv_transpose(sd[f"ups.{i}.weight"], sd[f"ups.{i}.bias"], u, (k - u) // 2)
+            t.add(w); t.add(b)
+            taps.append(w.shape[0]); shift0.append(d0)
+        nk = len(hspec.resblock_kernel_sizes)
+        nd = len(hspec.resblock_dilation_sizes[0])
+        for i in range(len(hspec.upsample_rates)):
+            for j in range(nk):
+                r = i * nk + j
+                for m in range(nd):
+                    t.add(conv_w(sd[f"resblocks.{r}.convs1.{m}.weight"])); t.add(sd[f"resblocks.{r}.convs1.{m}.bias"])
+                    t.add(conv_w(sd[f"resblocks.{r}.convs2.{m}.weight"])); t.add(sd[f"resblocks.{r}.convs2.{m}.bias"])
+        wp = sd["conv_post.weight"]            # (1, C, k)
+        t.add(wp[0].t().contiguous())          # [k][C]
+        t.add(sd["conv_post.bias"].reshape(1).repeat(4))
+        self.table = t.finish()
+        dil = [d for ds in hspec.resblock_dilation_sizes for d in ds]
+        cfg = [len(hspec.upsample_rates), C0, nk, nd, 7, wp.shape[2]] + list(hspec.upsample_rates) + taps + shift0 \
+            + list(hspec.resblock_kernel_sizes) + dil
+        self.cfg = (C.c_int32 * len(cfg))(*cfg)
+        self.hop = hspec.hop

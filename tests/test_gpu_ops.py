@@ -1,0 +1,126 @@
+"""Single-op checks of the CUDA kernels against plain torch fp32 (on the device or CPU)."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cmtts_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def conv1d_cl(x, w_pk, bias=None, shifts=(0,), pre_slope=None, act=0, alpha=1.0, beta=1.0, res=None, res_scale=1.0,
+              addvec=None, out_scale=1.0, lens=None, accumulate_into=None, act_slope=0.0):
+    lib = _lib.load()
+    B, M, Cin = x.shape
+    taps, _, N = w_pk.shape
+    nout = N // 2 if act == 5 else N
+    out = accumulate_into if accumulate_into is not None else torch.empty(B, M, nout, device=x.device)
+    d = _lib.ConvDesc(B=B, M=M, Lin=M, Cin=Cin, N=N, taps=taps, x_ld=Cin, out_ld=nout, res_ld=nout,
+                      x_bstride=M * Cin, out_bstride=M * nout, res_bstride=M * nout,
+                      addvec_bstride=N, pre_lrelu=int(pre_slope is not None), pre_slope=pre_slope or 0.0,
+                      alpha=alpha, beta=beta, act=act, act_slope=act_slope, res_scale=res_scale, out_scale=out_scale,
+                      accumulate=int(accumulate_into is not None))
+    for i, s in enumerate(shifts):
+        d.shift[i] = s
+    _lib.check(lib.cmtts_conv1d(C.byref(d), _lib.ptr(x), _lib.ptr(w_pk), _lib.ptr(bias), _lib.ptr(addvec),
+                                _lib.ptr(res), _lib.ptr(lens), _lib.ptr(out), _lib.stream_ptr()), "conv1d")
+    return out
+
+
+@pytest.mark.parametrize("B,L,Cin,Cout,k,dil", [(2, 37, 32, 64, 3, 1), (1, 300, 80, 512, 7, 1), (3, 129, 64, 64, 11, 5),
+                                               (2, 50, 256, 80, 1, 1), (1, 200, 128, 32, 7, 3), (2, 1, 16, 4, 1, 1)])
+def test_conv1d_matches_torch(B, L, Cin, Cout, k, dil):
+    g = torch.Generator().manual_seed(k * 100 + Cin)
+    x = torch.randn(B, L, Cin, generator=g).to(DEV)
+    w = (torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5).to(DEV)
+    b = torch.randn(Cout, generator=g).to(DEV)
+    ref = F.conv1d(F.leaky_relu(x, 0.1).transpose(1, 2), w, b, dilation=dil, padding=(k - 1) // 2 * dil).transpose(1, 2)
+    shifts = [(i - (k - 1) // 2) * dil for i in range(k)]
+    out = conv1d_cl(x, w.permute(2, 1, 0).contiguous(), b, shifts, pre_slope=0.1)
+    torch.cuda.synchronize()
+    assert (out - ref).abs().max().item() <= 2e-5
+
+
+def test_conv1d_epilogues():
+    g = torch.Generator().manual_seed(1)
+    B, L, Cin, N = 2, 70, 64, 128
+    x = torch.randn(B, L, Cin, generator=g).to(DEV)
+    w = (torch.randn(1, Cin, N, generator=g) / 8).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(B, L, N, generator=g).to(DEV)
+    vec = torch.randn(B, N, generator=g).to(DEV)
+    lens = torch.tensor([70, 33], device=DEV)
+    base = x @ w[0]
+    # gelu((acc + b) * beta)
+    out = conv1d_cl(x, w, b, act=2, beta=1 / 3)
+    assert (out - F.gelu((base + b) / 3)).abs().max() <= 1e-5
+    # residual + addvec + out_scale + row mask
+    out = conv1d_cl(x, w, b, res=res, addvec=vec, out_scale=0.5, lens=lens, alpha=2.0)
+    ref = (base * 2 + b + vec[:, None] + res) * 0.5
+    ref[1, 33:] = 0
+    assert (out - ref).abs().max() <= 1e-5
+    # accumulate
+    acc = res.clone()
+    conv1d_cl(x, w, b, accumulate_into=acc)
+    assert (acc - (res + base + b)).abs().max() <= 1e-5
+    # gated: tile = 64 gates | 64 filters
+    out = conv1d_cl(x, w, b, act=5)
+    y = base + b
+    ref = torch.sigmoid(y[..., :64]) * torch.tanh(y[..., 64:])
+    assert out.shape == (B, L, 64) and (out - ref).abs().max() <= 1e-5
+    torch.cuda.synchronize()
+
+
+def test_layernorm_and_attention():
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(2)
+    B, T, Cc, H = 3, 45, 256, 2
+    x = torch.randn(B, T, Cc, generator=g).to(DEV)
+    w = torch.randn(Cc, generator=g).to(DEV); b = torch.randn(Cc, generator=g).to(DEV)
+    lens = torch.tensor([45, 7, 1], device=DEV)
+    out = torch.empty_like(x)
+    _lib.check(lib.cmtts_layernorm(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), 1e-12, _lib.ptr(out), B, T, Cc, None, _lib.stream_ptr()), "ln")
+    assert (out - F.layer_norm(x, (Cc,), w, b, 1e-12)).abs().max() <= 1e-5
+    qkv = torch.randn(B, T, 3 * Cc, generator=g).to(DEV)
+    att = torch.empty(B, T, Cc, device=DEV)
+    _lib.check(lib.cmtts_attention(_lib.ptr(qkv), _lib.ptr(lens), _lib.ptr(att), B, T, Cc, H, _lib.stream_ptr()), "attn")
+    q, k, v = qkv.chunk(3, -1)
+    d = Cc // H
+    def heads(t): return t.view(B, T, H, d).transpose(1, 2)
+    sc = (heads(q) * d ** -0.5) @ heads(k).transpose(-1, -2)
+    mask = torch.arange(T, device=DEV)[None, :] >= lens[:, None]
+    sc = sc.masked_fill(mask[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(sc, -1) @ heads(v)).transpose(1, 2).reshape(B, T, Cc)
+    torch.cuda.synchronize()
+    assert (att - ref).abs().max() <= 1e-5
+
+
+def test_length_regulator_bit_exact_including_zero_durations():
+    from oracle import cmtts_oracle as O
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    B, T, Cc = 4, 33, 256
+    x = torch.randn(B, T, Cc, generator=g)
+    src_lens = torch.tensor([33, 20, 1, 5])
+    log_d = torch.randn(B, T, generator=g) * 0.8 + 1.2
+    log_d[0, 3] = -5.0                      # rounds to zero frames
+    log_d[3, :5] = -5.0                     # whole utterance empty -> mel_len 0
+    log_d = log_d * (torch.arange(T)[None] < src_lens[:, None])
+    ref_d = O.round_durations(log_d)
+    ref_x, ref_len = O.length_regulate(x, ref_d, None)
+    ref_m2p = O.dur_to_mel2ph(ref_d, torch.arange(T)[None] >= src_lens[:, None])
+    L = int(ref_len.max())
+    dl = log_d.to(DEV); xd = x.to(DEV); sl = src_lens.to(DEV)
+    d_r = torch.empty(B, T, device=DEV); cs = torch.empty(B, 2, T, dtype=torch.int64, device=DEV)
+    ml = torch.empty(B, dtype=torch.int64, device=DEV)
+    _lib.check(lib.cmtts_round_durations(_lib.ptr(dl), 1.0, _lib.ptr(sl), _lib.ptr(d_r), _lib.ptr(cs), _lib.ptr(ml), B, T, _lib.stream_ptr()), "round")
+    out = torch.empty(B, L, Cc, device=DEV); m2p = torch.empty(B, L, dtype=torch.int64, device=DEV)
+    _lib.check(lib.cmtts_length_regulate(_lib.ptr(xd), _lib.ptr(cs), _lib.ptr(ml), _lib.ptr(out), _lib.ptr(m2p), B, T, L, Cc, _lib.stream_ptr()), "lr")
+    torch.cuda.synchronize()
+    assert torch.equal(d_r.cpu(), ref_d)
+    assert torch.equal(ml.cpu(), ref_len) and int(ml[3]) == 0
+    assert torch.equal(out.cpu(), ref_x)                     # gathered rows bitwise equal
+    assert torch.equal(m2p.cpu()[:, : ref_m2p.shape[1]], ref_m2p)
