@@ -9,8 +9,11 @@
 #define CMTTS_ERR_WORKSPACE (-3)
 #define CMTTS_ERR_UNSUPPORTED (-4)
 
+extern unsigned long long g_cmtts_launches;   // kernels launched by this library (bench evidence)
+
 #define CMTTS_CHECK_LAUNCH()                                  \
     do {                                                      \
+        ++g_cmtts_launches;                                   \
         cudaError_t e__ = cudaPeekAtLastError();              \
         if (e__ != cudaSuccess) { cmtts_set_error(cudaGetErrorString(e__), __FILE__, __LINE__); return CMTTS_ERR_CUDA; } \
     } while (0)

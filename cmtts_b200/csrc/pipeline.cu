@@ -23,6 +23,8 @@ void cmtts_set_error(const char* msg, const char* file, int line) {
 }
 extern "C" const char* cmtts_last_error(void) { return g_err; }
 extern "C" int cmtts_abi_version(void) { return CMTTS_ABI_VERSION; }
+unsigned long long g_cmtts_launches = 0;
+extern "C" uint64_t cmtts_launch_count(void) { return g_cmtts_launches; }
 
 namespace {
 

@@ -249,13 +249,13 @@ class PackedHifiGan:
             raise ValueError("conv_pre.weight shape does not match the HiFi-GAN config")
         t.add(conv_w(sd["conv_pre.weight"])); t.add(sd["conv_pre.bias"])
         taps, shift0 = [], []
+        nk = len(hspec.resblock_kernel_sizes)
+        nd = len(hspec.resblock_dilation_sizes[0])
+        # table order = consumption order in cmtts_hifigan_forward: per level {up, its MRF resblocks}
         for i, (u, k) in enumerate(zip(hspec.upsample_rates, hspec.upsample_kernel_sizes)):
             w, b, d0 = pack_conv_transpose(sd[f"ups.{i}.weight"], sd[f"ups.{i}.bias"], u, (k - u) // 2)
             t.add(w); t.add(b)
             taps.append(w.shape[0]); shift0.append(d0)
-        nk = len(hspec.resblock_kernel_sizes)
-        nd = len(hspec.resblock_dilation_sizes[0])
-        for i in range(len(hspec.upsample_rates)):
             for j in range(nk):
                 r = i * nk + j
                 for m in range(nd):

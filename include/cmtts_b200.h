@@ -34,6 +34,8 @@ extern "C" {
 
 int cmtts_abi_version(void);
 const char* cmtts_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+uint64_t cmtts_launch_count(void);
 
 /* ---- model dimensions shared by the acoustic entry points ---- */
 typedef struct cmtts_dims {
@@ -86,8 +88,9 @@ enum { CMTTS_DN_IN_W = 0, CMTTS_DN_IN_B, CMTTS_DN_FREQ, CMTTS_DN_MLP0, CMTTS_DN_
 
 /* hifigan config: ints {n_levels, C0, n_kernels, n_dil, pre_k, post_k, rates[n_levels],
  *                       up_taps[n_levels], up_shift0[n_levels], ksize[n_kernels], dil[n_kernels*n_dil]} */
-/* hifigan weights: pre_w[k][80][C0], pre_b, per level {up_w[taps][Cin][s*Cout], up_b[s*Cout]},
- *                  per resblock r, per m {c1_w, c1_b, c2_w, c2_b}, post_w[k][C], post_b */
+/* hifigan weights: pre_w[k][80][C0], pre_b, then per level { up_w[taps][Cin][s*Cout], up_b[s*Cout],
+ *                  per MRF resblock j of that level, per dilation m: {c1_w, c1_b, c2_w, c2_b} },
+ *                  post_w[k][C], post_b */
 
 /* ---- E1-E4: FastspeechEncoder.forward (model/modules.py:132-151, :80-105) ---- */
 size_t cmtts_encoder_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t T);

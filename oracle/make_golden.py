@@ -37,6 +37,32 @@ ACOUSTIC_CASES = [
 ]
 
 
+def cliff_margins(spec, ref):
+    """Distance of every quantiser input from its nearest decision boundary (the quantisers are
+    discontinuous: a value sitting on a boundary flips under 1-ulp differences, which says nothing
+    about either implementation).  Fixtures are drawn so that all margins are comfortably large."""
+    import numpy as np
+
+    bins = torch.linspace(spec.energy_min, spec.energy_max, spec.energy_bins - 1)
+    e = (ref["e_predictions"][..., None] - bins).abs().min(-1).values.min().item()
+    keep = ~ref["src_masks"]
+    dur_in = (torch.exp(ref["log_d_predictions"]) - 1)[keep]
+    d = ((dur_in - torch.floor(dur_in)) - 0.5).abs().min().item()
+    f0 = ref["p_predictions"]["f0_denorm"]
+    mel = 1127 * (1 + f0 / 700).log()
+    mn, mx = 1127 * np.log(1 + 50.0 / 700), 1127 * np.log(1 + 1100.0 / 700)
+    mel = torch.where(mel > 0, (mel - mn) * 254 / (mx - mn) + 1, mel)
+    mel = mel.clamp(1, 255) + 0.5
+    pm = mel[f0 > 0]
+    p = (pm - torch.round(pm)).abs().min().item() if pm.numel() else 1.0
+    uv = ref["p_predictions"]["cwt"][..., -1].abs().min().item() if spec.use_uv else 1.0
+    return {"energy": e, "duration": d, "pitch_bins": p, "uv_logit": uv}
+
+
+def margins_ok(m):
+    return m["energy"] > 2e-4 and m["duration"] > 2e-3 and m["pitch_bins"] > 2e-3 and m["uv_logit"] > 2e-4
+
+
 def acoustic_case(ds, B, lo, hi, wseed, bseed, nseed):
     from model.cm_tool.karras_diffusion import karras_sample_tts
 
@@ -45,10 +71,21 @@ def acoustic_case(ds, B, lo, hi, wseed, bseed, nseed):
     model, diffusion, _ = ref_shim.build_reference_model(ds, spec.energy_min, spec.energy_max)
     model.load_state_dict(sd)
     model.eval()
-    batch = synthetic.make_batch(spec, B, lo, hi, seed=bseed)
-    if lo == 1:
-        batch["src_lens"][1] = 1
-        batch["texts"][1, 1:] = 0
+    dp0, _ = model.get_segmentation_model()
+    for bseed in range(bseed, bseed + 50):
+        batch = synthetic.make_batch(spec, B, lo, hi, seed=bseed)
+        if lo == 1:
+            batch["src_lens"][1] = 1
+            batch["texts"][1, 1:] = 0
+        with torch.no_grad():
+            probe = dp0(speakers=batch["speakers"], texts=batch["texts"], src_lens=batch["src_lens"],
+                        spker_embeds=batch["spker_embeds"])
+        margins = cliff_margins(spec, probe)
+        if margins_ok(margins):
+            break
+        print(f"  batch seed {bseed}: quantiser input on a decision boundary {margins}, drawing another batch")
+    else:
+        raise RuntimeError("no cliff-free batch found")
     kw = dict(speakers=batch["speakers"], texts=batch["texts"], src_lens=batch["src_lens"],
               spker_embeds=batch["spker_embeds"])
     cap = {}
@@ -61,7 +98,8 @@ def acoustic_case(ds, B, lo, hi, wseed, bseed, nseed):
     out = {
         "meta": dict(dataset=ds, batch=B, src_lo=lo, src_hi=hi, weight_seed=wseed, batch_seed=bseed,
                      noise_seed=nseed, digest=synthetic.state_dict_digest(sd),
-                     torch=str(torch.__version__), single_phoneme_row=(1 if lo == 1 else -1)),
+                     torch=str(torch.__version__), single_phoneme_row=(1 if lo == 1 else -1),
+                     quantiser_margins=margins),
         "texts": batch["texts"], "src_lens": batch["src_lens"], "spker_embeds": batch["spker_embeds"],
         "enc": cap["enc"], "log_d": ref["log_d_predictions"], "e_pred": ref["e_predictions"],
         "d_rounded": ref["d_rounded"], "mel_lens": ref["mel_lens"], "cond": ref["cond"],

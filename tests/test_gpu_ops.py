@@ -37,7 +37,9 @@ def test_conv1d_matches_torch(B, L, Cin, Cout, k, dil):
     x = torch.randn(B, L, Cin, generator=g).to(DEV)
     w = (torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5).to(DEV)
     b = torch.randn(Cout, generator=g).to(DEV)
-    ref = F.conv1d(F.leaky_relu(x, 0.1).transpose(1, 2), w, b, dilation=dil, padding=(k - 1) // 2 * dil).transpose(1, 2)
+    # reference on the CPU: cuDNN on the device may silently use TF32
+    ref = F.conv1d(F.leaky_relu(x.cpu(), 0.1).transpose(1, 2), w.cpu(), b.cpu(), dilation=dil,
+                   padding=(k - 1) // 2 * dil).transpose(1, 2).to(DEV)
     shifts = [(i - (k - 1) // 2) * dil for i in range(k)]
     out = conv1d_cl(x, w.permute(2, 1, 0).contiguous(), b, shifts, pre_slope=0.1)
     torch.cuda.synchronize()
@@ -53,7 +55,7 @@ def test_conv1d_epilogues():
     res = torch.randn(B, L, N, generator=g).to(DEV)
     vec = torch.randn(B, N, generator=g).to(DEV)
     lens = torch.tensor([70, 33], device=DEV)
-    base = x @ w[0]
+    base = (x.cpu() @ w[0].cpu()).to(DEV)   # CPU fp32 reference
     # gelu((acc + b) * beta)
     out = conv1d_cl(x, w, b, act=2, beta=1 / 3)
     assert (out - F.gelu((base + b) / 3)).abs().max() <= 1e-5
@@ -90,10 +92,11 @@ def test_layernorm_and_attention():
     q, k, v = qkv.chunk(3, -1)
     d = Cc // H
     def heads(t): return t.view(B, T, H, d).transpose(1, 2)
+    q, k, v = q.cpu(), k.cpu(), v.cpu()
     sc = (heads(q) * d ** -0.5) @ heads(k).transpose(-1, -2)
-    mask = torch.arange(T, device=DEV)[None, :] >= lens[:, None]
+    mask = torch.arange(T)[None, :] >= lens.cpu()[:, None]
     sc = sc.masked_fill(mask[:, None, None, :], float("-inf"))
-    ref = (torch.softmax(sc, -1) @ heads(v)).transpose(1, 2).reshape(B, T, Cc)
+    ref = (torch.softmax(sc, -1) @ heads(v)).transpose(1, 2).reshape(B, T, Cc).to(DEV)
     torch.cuda.synchronize()
     assert (att - ref).abs().max() <= 1e-5
 

@@ -22,7 +22,7 @@ def err(a, b):
 
 
 def main():
-    for ds, B, lo, hi in [("LJSpeech", 3, 9, 14), ("VCTK", 4, 10, 40)]:
+    for ds, B, lo, hi in [("LibriTTS", 2, 10, 12), ("VCTK", 4, 10, 40)]:
         spec = ModelSpec.preset(ds)
         sd = synthetic.make_acoustic_state_dict(spec, 0)
         batch = synthetic.make_batch(spec, B, lo, hi, seed=1234)
