@@ -45,6 +45,18 @@ class ConvDesc(C.Structure):
     ]
 
 
+class UmmaDesc(C.Structure):
+    """struct cmtts_umma_desc."""
+    _fields_ = [
+        ("B", C.c_int32), ("M", C.c_int32), ("Lin", C.c_int32), ("N", C.c_int32), ("Cin", C.c_int32),
+        ("taps", C.c_int32), ("shift", C.c_int32 * 16), ("split", C.c_int32), ("epi", C.c_int32),
+        ("a_ld", C.c_int32), ("res_ld", C.c_int32), ("out_ld", C.c_int32), ("x_ld", C.c_int32),
+        ("a_bstride", i64), ("res_bstride", i64), ("out_bstride", i64), ("x_bstride", i64), ("addvec_bstride", i64),
+        ("alpha", f32), ("res_inv_slope", f32), ("out_slope", f32), ("out_scale", f32),
+        ("skip_accumulate", C.c_int32),
+    ]
+
+
 PD = C.POINTER(Dims)
 PV = C.POINTER(vp)
 PI32 = C.POINTER(C.c_int32)
@@ -74,6 +86,12 @@ PROTOTYPES = {
     "cmtts_attention": (C.c_int, [vp, vp, vp, i64, i64, i64, i64, vp]),
     "cmtts_length_regulate": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, i64, i64, vp]),
     "cmtts_round_durations": (C.c_int, [vp, f32, vp, vp, vp, vp, i64, i64, vp]),
+    "cmtts_umma_conv1d": (C.c_int, [C.POINTER(UmmaDesc)] + [vp] * 13),
+    "cmtts_f32_to_f16": (C.c_int, [vp, vp, vp, i64, i64, i64, f32, vp]),
+    "cmtts_denoiser_tc_workspace_bytes": (szt, [PD, i64, i64]),
+    "cmtts_denoiser_forward_tc": (C.c_int, [PD, PV, PV, vp, vp, vp, vp, vp, f32, f32, f32, i64, i64, vp, vp, vp, szt, vp]),
+    "cmtts_hifigan_tc_workspace_bytes": (szt, [PI32, i64, i64]),
+    "cmtts_hifigan_forward_tc": (C.c_int, [PI32, PV, vp, i64, i64, vp, vp, f32, vp, szt, vp]),
 }
 
 _lib: Optional[C.CDLL] = None

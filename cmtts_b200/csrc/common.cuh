@@ -1,6 +1,7 @@
 // Shared declarations for the cmtts_b200 CUDA library (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #define CMTTS_OK 0
@@ -56,11 +57,13 @@ struct ConvParams {
     float out_scale;
     const long long* lens;
     int accumulate;
+    // optional fp16 copy of the result with leaky-ReLU applied (operand of a following tensor-core conv)
+    __half* out_h; float out_h_slope;
 };
 
 static inline ConvParams conv_params_default() {
     ConvParams p{};
-    p.alpha = 1.f; p.beta = 1.f; p.res1_scale = 1.f; p.out_scale = 1.f; p.act = ACT_NONE;
+    p.alpha = 1.f; p.beta = 1.f; p.res1_scale = 1.f; p.out_scale = 1.f; p.act = ACT_NONE; p.out_h_slope = 1.f;
     return p;
 }
 

@@ -198,6 +198,14 @@ __global__ void __launch_bounds__(2 * BN) conv1d_simt_kernel(const ConvParams p)
                 r[0] += a.x; r[1] += a.y; r[2] += a.z; r[3] += a.w;
             }
             *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+            if (p.out_h) {
+                __half2 h01 = __floats2half2_rn(r[0] > 0.f ? r[0] : r[0] * p.out_h_slope, r[1] > 0.f ? r[1] : r[1] * p.out_h_slope);
+                __half2 h23 = __floats2half2_rn(r[2] > 0.f ? r[2] : r[2] * p.out_h_slope, r[3] > 0.f ? r[3] : r[3] * p.out_h_slope);
+                uint2 u;
+                u.x = *reinterpret_cast<uint32_t*>(&h01);
+                u.y = *reinterpret_cast<uint32_t*>(&h23);
+                *reinterpret_cast<uint2*>(p.out_h + (long long)b * p.out_bstride + (long long)t * p.out_ld + n) = u;
+            }
         }
     }
 }

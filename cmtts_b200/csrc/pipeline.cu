@@ -2,6 +2,7 @@
 // reference's hot path (see include/cmtts_b200.h for the seam -> reference file:line map).
 #include "../../include/cmtts_b200.h"
 #include "common.cuh"
+#include "umma_conv.cuh"
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -496,4 +497,203 @@ extern "C" int cmtts_round_durations(const float* log_d, float d_control, const 
                                      int64_t* cumsum, int64_t* mel_lens, int64_t B, int64_t T, void* stream) {
     return launch_round_durations(log_d, d_control, (const long long*)src_lens, d_rounded, (long long*)cumsum,
                                   (long long*)mel_lens, (int)B, (int)T, (cudaStream_t)stream);
+}
+
+
+// ============================================================================================
+// tensor-core (tcgen05) path
+// ============================================================================================
+extern "C" int cmtts_umma_conv1d(const cmtts_umma_desc* c, const void* a_hi, const void* a_lo, const void* w_hi,
+                                 const void* w_lo, const float* bias, const void* res_h, const void* sum_h,
+                                 void* out_h, void* out_lo, const float* addvec, float* x_f32, float* skip_f32,
+                                 void* stream) {
+    UmmaConvParams p = umma_params_default();
+    p.B = c->B; p.M = c->M; p.Lin = c->Lin; p.N = c->N; p.Cin = c->Cin; p.taps = c->taps;
+    CMTTS_REQUIRE(c->taps >= 1 && c->taps <= CMTTS_MAX_TAPS, "umma_conv1d: taps");
+    for (int i = 0; i < c->taps; ++i) p.shift[i] = c->shift[i];
+    p.split = c->split; p.epi = c->epi;
+    p.a_hi = (const __half*)a_hi; p.a_lo = (const __half*)a_lo; p.a_bstride = c->a_bstride; p.a_ld = c->a_ld;
+    p.w_hi = (const __half*)w_hi; p.w_lo = (const __half*)w_lo;
+    p.bias = bias; p.alpha = c->alpha;
+    p.res_h = (const __half*)res_h; p.res_bstride = c->res_bstride; p.res_ld = c->res_ld; p.res_inv_slope = c->res_inv_slope;
+    p.sum_h = (const __half*)sum_h;
+    p.out_h = (__half*)out_h; p.out_lo = (__half*)out_lo; p.out_bstride = c->out_bstride; p.out_ld = c->out_ld;
+    p.out_slope = c->out_slope;
+    p.addvec = addvec; p.addvec_bstride = c->addvec_bstride;
+    p.x_f32 = x_f32; p.x_bstride = c->x_bstride; p.x_ld = c->x_ld;
+    p.skip_f32 = skip_f32; p.skip_accumulate = c->skip_accumulate; p.out_scale = c->out_scale;
+    return launch_umma_conv(p, (cudaStream_t)stream);
+}
+
+extern "C" int cmtts_f32_to_f16(const float* x, void* hi, void* lo, int64_t rows, int64_t C, int64_t Cpad,
+                                float slope, void* stream) {
+    return launch_f32_to_f16(x, (__half*)hi, (__half*)lo, rows, (int)C, (int)Cpad, slope, (cudaStream_t)stream);
+}
+
+extern "C" size_t cmtts_denoiser_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t L) {
+    const size_t n = (size_t)B * L * d->res_channels;
+    return align_up(n * 4) * 3 + align_up(n * 2) * 4;
+}
+
+extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const* w, const void* const* w16,
+                                         const float* x_t, const void* cond_hi, const void* cond_lo,
+                                         const float* ds_all, const float* dsp_all, float c_in, float c_out,
+                                         float c_skip, int64_t B_, int64_t L_, float* out, float* model_out,
+                                         void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = (int)B_, L = (int)L_, C = d->res_channels, M = d->n_mels, H = d->hidden;
+    CMTTS_REQUIRE(ws_bytes >= cmtts_denoiser_tc_workspace_bytes(d, B_, L_), "denoiser_tc: workspace too small");
+    CMTTS_REQUIRE(C % 128 == 0 && H % 64 == 0, "denoiser_tc: channel counts must suit the 128x128x64 UMMA tiling");
+    if (B == 0 || L == 0) return CMTTS_OK;
+    Carver cv(ws, ws_bytes);
+    const size_t n = (size_t)B * L;
+    float* x = cv.take<float>(n * C);
+    float* skip = cv.take<float>(n * C);
+    float* v = cv.take<float>(n * C);
+    __half* y_hi = cv.take<__half>(n * C);
+    __half* y_lo = cv.take<__half>(n * C);
+    __half* g_hi = cv.take<__half>(n * C);
+    __half* g_lo = cv.take<__half>(n * C);
+    const long long NL = (long long)d->res_layers * C;
+    const long long bs = (long long)L * C;
+
+    // input projection on the fp32 path (K = 80): relu(W (c_in x_t) + b)
+    ConvParams p = conv_same(x_t, B, L, M, F(w, CMTTS_DN_IN_W), F(w, CMTTS_DN_IN_B), C, 1, 1, x);
+    p.alpha = c_in; p.act = ACT_RELU;
+    CMTTS_TRY(launch_conv1d_simt(p, s));
+    for (int l = 0; l < d->res_layers; ++l) {
+        const void* const* wl = w16 + l * 7;
+        const int o = CMTTS_DN_LAYER0 + l * CMTTS_DN_PER_LAYER;
+        UmmaConvParams u = umma_params_default();
+        // (a) y = Wc cond + bc + (step + speaker)[b] + x                    blocks.py:669-678
+        u.B = B; u.M = L; u.Lin = L; u.N = C; u.Cin = H; u.taps = 1; u.shift[0] = 0; u.split = 1; u.epi = UEPI_DN_COND;
+        u.a_hi = (const __half*)cond_hi; u.a_lo = (const __half*)cond_lo; u.a_bstride = (long long)L * H; u.a_ld = H;
+        u.w_hi = (const __half*)wl[0]; u.w_lo = (const __half*)wl[1];
+        u.bias = F(w, o + 1);
+        u.addvec = dsp_all + (long long)l * C; u.addvec_bstride = NL;
+        u.x_f32 = x; u.x_bstride = bs; u.x_ld = C;
+        u.out_h = y_hi; u.out_lo = y_lo; u.out_bstride = bs; u.out_ld = C;
+        CMTTS_TRY(launch_umma_conv(u, s));
+        // (b) g = sigmoid(gate) * tanh(filter) of the k=3 conv               blocks.py:677-681
+        u = umma_params_default();
+        u.B = B; u.M = L; u.Lin = L; u.N = 2 * C; u.Cin = C; u.taps = 3; u.shift[0] = -1; u.shift[1] = 0; u.shift[2] = 1;
+        u.split = 1; u.epi = UEPI_DN_GATE;
+        u.a_hi = y_hi; u.a_lo = y_lo; u.a_bstride = bs; u.a_ld = C;
+        u.w_hi = (const __half*)wl[2]; u.w_lo = (const __half*)wl[3];
+        u.bias = F(w, o + 3);
+        u.out_h = g_hi; u.out_lo = g_lo; u.out_bstride = bs; u.out_ld = C;
+        CMTTS_TRY(launch_umma_conv(u, s));
+        // (c) x = (Wo[:C] g + b + step[b] + x) / sqrt(2) ; skip (+)= Wo[C:] g + b     blocks.py:676, :683-686
+        u = umma_params_default();
+        u.B = B; u.M = L; u.Lin = L; u.N = 2 * C; u.Cin = C; u.taps = 1; u.shift[0] = 0; u.split = 1; u.epi = UEPI_DN_OUT;
+        u.a_hi = g_hi; u.a_lo = g_lo; u.a_bstride = bs; u.a_ld = C;
+        u.w_hi = (const __half*)wl[4]; u.w_lo = (const __half*)wl[5];
+        u.bias = (const float*)wl[6];
+        u.addvec = ds_all + (long long)l * C; u.addvec_bstride = NL;
+        u.x_f32 = x; u.x_bstride = bs; u.x_ld = C;
+        u.skip_f32 = skip; u.skip_accumulate = (l > 0);
+        u.out_scale = (float)(1.0 / sqrt(2.0));
+        CMTTS_TRY(launch_umma_conv(u, s));
+    }
+    const int o = CMTTS_DN_LAYER0 + d->res_layers * CMTTS_DN_PER_LAYER;
+    p = conv_same(skip, B, L, C, F(w, o + 0), F(w, o + 1), C, 1, 1, v);
+    p.alpha = (float)(1.0 / sqrt((double)d->res_layers)); p.act = ACT_RELU;
+    CMTTS_TRY(launch_conv1d_simt(p, s));
+    p = conv_same(v, B, L, C, F(w, o + 2), F(w, o + 3), M, 1, 1, out);
+    p.beta = c_out;
+    if (model_out) { p.aux_out = model_out; p.aux_bstride = (long long)L * M; p.aux_ld = M; }
+    if (c_skip != 0.f) { p.res1 = x_t; p.res1_bstride = (long long)L * M; p.res1_ld = M; p.res1_scale = c_skip; }
+    CMTTS_TRY(launch_conv1d_simt(p, s));
+    return CMTTS_OK;
+}
+
+extern "C" size_t cmtts_hifigan_tc_workspace_bytes(const int32_t* cfg, int64_t B, int64_t L) {
+    const HifiCfg c(cfg);
+    const size_t lvl = (size_t)B * L * c.max_level_elems_per_frame();
+    return align_up(lvl * 2) * 4 + align_up((size_t)B * L * c.C0 * 4);
+}
+
+extern "C" int cmtts_hifigan_forward_tc(const int32_t* cfg, const void* const* w, const float* mel, int64_t B_,
+                                        int64_t L_, float* wav, int16_t* wav_i16, float max_wav_value, void* ws,
+                                        size_t ws_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const HifiCfg c(cfg);
+    const int B = (int)B_, L = (int)L_;
+    CMTTS_REQUIRE(ws_bytes >= cmtts_hifigan_tc_workspace_bytes(cfg, B_, L_), "hifigan_tc: workspace too small");
+    CMTTS_REQUIRE((long long)L * c.hop() < (1ll << 31), "hifigan_tc: sequence too long");
+    if (B == 0 || L == 0) return CMTTS_OK;
+    Carver cv(ws, ws_bytes);
+    const size_t lvl = (size_t)B * L * c.max_level_elems_per_frame();
+    __half* up = cv.take<__half>(lvl);    // lrelu(x) of the level input (after the transposed conv)
+    __half* yb = cv.take<__half>(lvl);    // lrelu(running resblock state)
+    __half* tb = cv.take<__half>(lvl);    // lrelu(c1 output)
+    __half* xs = cv.take<__half>(lvl);    // MRF partial sums (raw), then lrelu(sum) for the next level
+    float* pre32 = cv.take<float>((size_t)B * L * c.C0);
+
+    int wi = 0;
+    // conv_pre on the fp32 path (K = 7 x 80, 0.1 % of the FLOPs) -> fp16 lrelu(x)
+    ConvParams p = conv_same(mel, B, L, 80, F(w, wi), F(w, wi + 1), c.C0, c.pre_k, 1, pre32);
+    p.out_h = xs; p.out_h_slope = 0.1f;
+    wi += 2;
+    CMTTS_TRY(launch_conv1d_simt(p, s));
+    int ch = c.C0, len = L;
+    const float inv_nk = 1.0f / (float)c.n_kernels;
+    for (int i = 0; i < c.n_levels; ++i) {
+        const int r = c.rates[i], cout = ch / 2;
+        const bool last_level = (i == c.n_levels - 1);
+        // ConvTranspose1d as a packed conv (N = r * cout) on lrelu(x); output stored as lrelu(up)
+        UmmaConvParams u = umma_params_default();
+        u.B = B; u.M = len; u.Lin = len; u.N = r * cout; u.Cin = ch; u.taps = c.up_taps[i];
+        for (int t = 0; t < u.taps; ++t) u.shift[t] = c.up_shift0[i] + t;
+        u.epi = UEPI_VOC;
+        u.a_hi = xs; u.a_bstride = (long long)len * ch; u.a_ld = ch;
+        u.w_hi = (const __half*)w[wi]; u.bias = F(w, wi + 1);
+        u.alpha = (i > 0) ? inv_nk : 1.f;
+        u.out_h = up; u.out_ld = r * cout; u.out_bstride = (long long)len * r * cout; u.out_slope = 0.1f;
+        wi += 2;
+        CMTTS_TRY(launch_umma_conv(u, s));
+        len *= r; ch = cout;
+        const long long bs = (long long)len * ch;
+        for (int j = 0; j < c.n_kernels; ++j) {
+            const int k = c.ksize[j];
+            const __half* yin = up;
+            for (int m = 0; m < c.n_dil; ++m) {
+                const int dl = c.dil[j * c.n_dil + m];
+                const bool last = (m == c.n_dil - 1);
+                // t = lrelu(c1(lrelu(y)) + b1)
+                u = umma_params_default();
+                u.B = B; u.M = len; u.Lin = len; u.N = ch; u.Cin = ch; u.taps = k;
+                for (int t = 0; t < k; ++t) u.shift[t] = (t - (k - 1) / 2) * dl;
+                u.epi = UEPI_VOC;
+                u.a_hi = yin; u.a_bstride = bs; u.a_ld = ch;
+                u.w_hi = (const __half*)w[wi]; u.bias = F(w, wi + 1);
+                u.out_h = tb; u.out_ld = ch; u.out_bstride = bs; u.out_slope = 0.1f;
+                CMTTS_TRY(launch_umma_conv(u, s));
+                // y' = c2(t) + b2 + y ; y recovered from its stored lrelu(y) (slope 0.1 -> x10 on negatives)
+                u = umma_params_default();
+                u.B = B; u.M = len; u.Lin = len; u.N = ch; u.Cin = ch; u.taps = k;
+                for (int t = 0; t < k; ++t) u.shift[t] = t - (k - 1) / 2;
+                u.epi = UEPI_VOC;
+                u.a_hi = tb; u.a_bstride = bs; u.a_ld = ch;
+                u.w_hi = (const __half*)w[wi + 2]; u.bias = F(w, wi + 3);
+                u.res_h = yin; u.res_bstride = bs; u.res_ld = ch; u.res_inv_slope = 10.f;
+                u.out_ld = ch; u.out_bstride = bs;
+                if (!last) {
+                    u.out_h = yb; u.out_slope = 0.1f;
+                } else {
+                    // MRF: xs = sum_j resblock_j(x); raw partial sums, activated on the last one for the
+                    // next level's conv (slope 0.01 before conv_post, models.py:161)
+                    u.out_h = xs;
+                    if (j > 0) u.sum_h = xs;
+                    u.out_slope = (j == c.n_kernels - 1) ? (last_level ? 0.01f : 0.1f) : 1.f;
+                }
+                CMTTS_TRY(launch_umma_conv(u, s));
+                yin = yb;
+                wi += 4;
+            }
+        }
+    }
+    CMTTS_TRY(launch_conv_post_f16(xs, F(w, wi), F(w, wi + 1), (float)c.n_kernels, wav, wav_i16, max_wav_value, B, len,
+                                   ch, c.post_k, s));
+    return CMTTS_OK;
 }

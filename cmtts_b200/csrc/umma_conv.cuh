@@ -1,0 +1,47 @@
+// tcgen05 implicit-GEMM conv1d (declarations).  See umma_conv.cu.
+#pragma once
+#include "common.cuh"
+#include <cuda_fp16.h>
+
+enum UmmaEpi {
+    UEPI_VOC = 0,      // fp16 "activated storage" epilogue (HiFi-GAN convs)
+    UEPI_DN_COND = 1,  // y = acc + bias + addvec[b] + x_f32            -> fp16 hi/lo
+    UEPI_DN_GATE = 2,  // sigmoid(gate + b) * tanh(filter + b)          -> fp16 hi/lo   (BN = 128: 64 gates | 64 filters)
+    UEPI_DN_OUT = 3,   // cols <  N/2: x = (acc + b + addvec[b] + x) * out_scale (fp32, in place)
+                       // cols >= N/2: skip (+)= acc + b                 (fp32)
+};
+
+struct UmmaConvParams {
+    // problem: out[b, t, n] = epi( sum_{tap, ci} A[b, t + shift[tap], ci] * W[tap][n][ci] )
+    int B, M, Lin, N, Cin, taps;
+    int shift[CMTTS_MAX_TAPS];
+    int split;            // 0: plain fp16 operands; 1: hi/lo operand pairs, 3 MMAs per K step (fp32-class)
+    int epi;
+    // operands (fp16, channels-last activations [B][Lin][Cin]; weights [taps*N][Cin])
+    const __half* a_hi; const __half* a_lo; long long a_bstride; int a_ld;
+    const __half* w_hi; const __half* w_lo;
+    // epilogue
+    const float* bias; float alpha;
+    // UEPI_VOC: v = acc*alpha + bias + inv_lrelu(res) + sum ; out = lrelu(v, out_slope) as fp16
+    const __half* res_h; long long res_bstride; int res_ld; float res_inv_slope;
+    const __half* sum_h;
+    __half* out_h; __half* out_lo; long long out_bstride; int out_ld; float out_slope;
+    // denoiser epilogues
+    const float* addvec; long long addvec_bstride;
+    float* x_f32; long long x_bstride; int x_ld;
+    float* skip_f32; int skip_accumulate; float out_scale;
+};
+
+static inline UmmaConvParams umma_params_default() {
+    UmmaConvParams p{};
+    p.alpha = 1.f; p.res_inv_slope = 1.f; p.out_slope = 1.f; p.out_scale = 1.f;
+    return p;
+}
+
+int launch_umma_conv(const UmmaConvParams& p, cudaStream_t s);
+
+// fp32 -> fp16 (optionally hi/lo pair, optional leaky-ReLU, optional channel zero-padding)
+int launch_f32_to_f16(const float* x, __half* hi, __half* lo, long long rows, int C, int Cpad, float slope, cudaStream_t s);
+// HiFi-GAN output stage on fp16 activated input
+int launch_conv_post_f16(const __half* x, const float* w, const float* bias, float pre_div, float* wav, short* wav_i16,
+                         float max_wav, int B, int L, int C, int K, cudaStream_t s);

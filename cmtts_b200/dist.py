@@ -101,7 +101,11 @@ class ShardedSynthesizer:
         return {n: v / reps for n, v in acc.items()}
 
     def dtype_label(self) -> str:
+        if self.pipe.precision == "tc":
+            return "f16 operands / f32 accumulate (tcgen05); denoiser f16 hi+lo pairs; encoder + variance adaptor f32"
         return "f32"
 
     def dominant_kernel(self) -> str:
+        if self.pipe.precision == "tc":
+            return "umma_conv_kernel (tcgen05 implicit-GEMM conv, TMA + TMEM)"
         return "conv1d_simt_kernel (fp32 FFMA implicit GEMM)"

@@ -60,17 +60,25 @@ class DurationPitchSpeakerNet:
 class CMTotalTTS:
     """B200-native stand-in for model/cm_tool/tts_net.py:CMTotalTTS (inference only)."""
 
+    #: "tc"   — residual stack on tcgen05 tensor cores with fp16 hi/lo operand pairs (fp32-class);
+    #: "fp32" — everything on the fp32 FFMA kernels (the device-side yardstick).
+    PRECISIONS = ("tc", "fp32")
+
     def __init__(self, use_fp16=False, args=None, preprocess_config=None, model_config=None,
-                 train_config=None, spec: Optional[ModelSpec] = None, **_ignored):
+                 train_config=None, spec: Optional[ModelSpec] = None, precision: str = "tc", **_ignored):
         if use_fp16:
             raise NotImplementedError("use_fp16 converts the torso for training; inference here is fp32-class")
         if spec is None:
             spec = ModelSpec.from_reference_configs(preprocess_config, model_config, train_config)
+        if precision not in self.PRECISIONS:
+            raise ValueError(f"precision must be one of {self.PRECISIONS}")
+        self.precision = precision
         self.spec = spec
         self.device = torch.device("cpu")
         self._sd: Optional[Dict[str, torch.Tensor]] = None
         self.packed: Optional[PackedAcoustic] = None
         self.training = False
+        self._cond_split_cache = None
         self.duration_pitch_energy_net = DurationPitchSpeakerNet(self)
         self._ws: Optional[_Workspace] = None
         self.lib = _lib.load()
@@ -239,14 +247,37 @@ class CMTotalTTS:
         out = torch.empty_like(x)
         mo = torch.empty_like(x) if want_model_out else None
         d = C.byref(self._dims)
-        ws = self._ws.get("dn", lib.cmtts_denoiser_workspace_bytes(d, B, L))
         with torch.cuda.device(dev):
-            _lib.check(lib.cmtts_denoiser_forward(d, self.packed.dn.ptrs, _lib.ptr(x), _lib.ptr(cond),
-                                                  _lib.ptr(steps[0]), _lib.ptr(steps[1]), c_in, c_out, c_skip, B, L,
-                                                  _lib.ptr(out), _lib.ptr(mo), _lib.ptr(ws), ws.numel(),
-                                                  _lib.stream_ptr(dev)), "denoiser_forward")
+            if self.precision == "tc":
+                c_hi, c_lo = self._cond_split(cond)
+                ws = self._ws.get("dn", lib.cmtts_denoiser_tc_workspace_bytes(d, B, L))
+                _lib.check(lib.cmtts_denoiser_forward_tc(d, self.packed.dn.ptrs, self.packed.dn16.ptrs, _lib.ptr(x),
+                                                         _lib.ptr(c_hi), _lib.ptr(c_lo), _lib.ptr(steps[0]),
+                                                         _lib.ptr(steps[1]), c_in, c_out, c_skip, B, L, _lib.ptr(out),
+                                                         _lib.ptr(mo), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+                           "denoiser_forward_tc")
+            else:
+                ws = self._ws.get("dn", lib.cmtts_denoiser_workspace_bytes(d, B, L))
+                _lib.check(lib.cmtts_denoiser_forward(d, self.packed.dn.ptrs, _lib.ptr(x), _lib.ptr(cond),
+                                                      _lib.ptr(steps[0]), _lib.ptr(steps[1]), c_in, c_out, c_skip, B, L,
+                                                      _lib.ptr(out), _lib.ptr(mo), _lib.ptr(ws), ws.numel(),
+                                                      _lib.stream_ptr(dev)), "denoiser_forward")
         out = out.view(shape)
         return (out, mo.view(shape)) if want_model_out else out
+
+    def _cond_split(self, cond: torch.Tensor):
+        """fp16 hi/lo operand pair of the conditioner, made once per conditioner tensor (it is the
+        same for every solver step)."""
+        key = (cond.data_ptr(), tuple(cond.shape), cond._version)
+        if self._cond_split_cache is not None and self._cond_split_cache[0] == key:
+            return self._cond_split_cache[1]
+        hi = torch.empty(cond.shape, dtype=torch.float16, device=cond.device)
+        lo = torch.empty_like(hi)
+        rows = cond.shape[0] * cond.shape[1]
+        _lib.check(self.lib.cmtts_f32_to_f16(_lib.ptr(cond), _lib.ptr(hi), _lib.ptr(lo), rows, cond.shape[2],
+                                             cond.shape[2], 1.0, _lib.stream_ptr(cond.device)), "f32_to_f16")
+        self._cond_split_cache = (key, (hi, lo), cond)   # keep `cond` alive so the pointer key stays valid
+        return hi, lo
 
     def get_segmentation_model(self):
         """tts_net.py:66-73 -> (dpen callable, denoise_fun(mel[B,1,L,80]... ) in the reference's

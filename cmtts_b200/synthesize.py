@@ -106,13 +106,14 @@ class Pipeline:
     HiFi-GAN on the whole padded batch, x32768 -> int16, crop to mel_len * hop)."""
 
     def __init__(self, spec: ModelSpec, acoustic_sd: Dict[str, torch.Tensor], hifigan_sd: Dict[str, torch.Tensor],
-                 device, distillation: bool = True):
+                 device, distillation: bool = True, precision: str = "tc"):
         self.spec = spec
+        self.precision = precision
         self.device = torch.device(device)
-        self.model = CMTotalTTS(spec=spec).load_state_dict(acoustic_sd).to(self.device)
+        self.model = CMTotalTTS(spec=spec, precision=precision).load_state_dict(acoustic_sd).to(self.device)
         self.diffusion = KarrasDenoiser(sigma_data=spec.sigma_data, sigma_max=spec.sigma_max,
                                         sigma_min=spec.sigma_min, rho=spec.rho, distillation=distillation)
-        self.vocoder = Generator(hspec=spec.hifigan).load_state_dict(hifigan_sd).to(self.device)
+        self.vocoder = Generator(hspec=spec.hifigan, precision=precision).load_state_dict(hifigan_sd).to(self.device)
 
     def acoustic(self, texts, src_lens, spker_embeds, T: int, generator=None, l_max_hook=None, trace=None):
         out = self.model.dpen(texts, src_lens, spker_embeds, None, l_max_hook=l_max_hook)

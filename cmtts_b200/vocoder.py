@@ -45,7 +45,13 @@ def hspec_from_config(h) -> HifiGanSpec:
 class Generator:
     """B200-native stand-in for hifigan.Generator (inference only)."""
 
-    def __init__(self, h=None, hspec: Optional[HifiGanSpec] = None):
+    #: "tc" — fp16 operands / fp32 accumulation on tcgen05 tensor cores; "fp32" — FFMA yardstick
+    PRECISIONS = ("tc", "fp32")
+
+    def __init__(self, h=None, hspec: Optional[HifiGanSpec] = None, precision: str = "tc"):
+        if precision not in self.PRECISIONS:
+            raise ValueError(f"precision must be one of {self.PRECISIONS}")
+        self.precision = precision
         self.hspec = hspec if hspec is not None else (hspec_from_config(h) if h is not None else HifiGanSpec())
         self.device = torch.device("cpu")
         self._sd: Optional[Dict[str, torch.Tensor]] = None
@@ -94,11 +100,17 @@ class Generator:
         n = L * self.packed.hop
         wav = torch.empty(B, n, dtype=torch.float32, device=dev) if want_float else None
         w16 = torch.empty(B, n, dtype=torch.int16, device=dev) if want_int16 else None
-        ws = self._ws.get("hifi", lib.cmtts_hifigan_workspace_bytes(self.packed.cfg, B, L))
         with torch.cuda.device(dev):
-            _lib.check(lib.cmtts_hifigan_forward(self.packed.cfg, self.packed.table.ptrs, _lib.ptr(mel), B, L,
-                                                 _lib.ptr(wav), _lib.ptr(w16), max_wav_value, _lib.ptr(ws), ws.numel(),
-                                                 _lib.stream_ptr(dev)), "hifigan_forward")
+            if self.precision == "tc":
+                ws = self._ws.get("hifi", lib.cmtts_hifigan_tc_workspace_bytes(self.packed.cfg, B, L))
+                _lib.check(lib.cmtts_hifigan_forward_tc(self.packed.cfg, self.packed.table16.ptrs, _lib.ptr(mel), B, L,
+                                                        _lib.ptr(wav), _lib.ptr(w16), max_wav_value, _lib.ptr(ws),
+                                                        ws.numel(), _lib.stream_ptr(dev)), "hifigan_forward_tc")
+            else:
+                ws = self._ws.get("hifi", lib.cmtts_hifigan_workspace_bytes(self.packed.cfg, B, L))
+                _lib.check(lib.cmtts_hifigan_forward(self.packed.cfg, self.packed.table.ptrs, _lib.ptr(mel), B, L,
+                                                     _lib.ptr(wav), _lib.ptr(w16), max_wav_value, _lib.ptr(ws), ws.numel(),
+                                                     _lib.stream_ptr(dev)), "hifigan_forward")
         return wav, w16
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -81,6 +81,18 @@ def pack_conv_transpose(w: torch.Tensor, bias: torch.Tensor, stride: int, paddin
     return out.contiguous(), bias.repeat(u).contiguous(), d0
 
 
+def conv_w_nk(w: torch.Tensor) -> torch.Tensor:
+    """(Cout, Cin, k) -> [k][Cout][Cin]: K-major B operand of the tcgen05 path (rows = tap*Cout + n)."""
+    return w.permute(2, 0, 1).contiguous()
+
+
+def split_f16(w: torch.Tensor):
+    """fp32 -> (hi, lo) fp16 with hi + lo == w to ~22 bits (hi = fp16(w), lo = fp16(w - hi))."""
+    hi = w.to(torch.float16)
+    lo = (w - hi.to(torch.float32)).to(torch.float16)
+    return hi, lo
+
+
 class _Table:
     """Keeps the device tensors alive next to the ctypes pointer array that references them."""
 
@@ -90,7 +102,9 @@ class _Table:
 
     def add(self, t: Optional[torch.Tensor]) -> int:
         if t is not None:
-            t = t.detach().to(torch.float32).contiguous().to(self.device)
+            if t.dtype != torch.float16:
+                t = t.to(torch.float32)
+            t = t.detach().contiguous().to(self.device)
             if t.data_ptr() % 16 != 0:
                 raise _lib.CmttsError("weight tensor not 16-byte aligned")
         self.tensors.append(t)
@@ -229,6 +243,18 @@ class PackedAcoustic:
         dn.add(conv_w(sd["net.output_projection.conv.weight"])); dn.add(sd["net.output_projection.conv.bias"])
         self.dn = dn.finish()
 
+        # tensor-core operands of the residual stack: fp16 hi/lo pairs, [tap][Cout][Cin] (K-major)
+        dn16 = _Table(dev)
+        for l in range(s.res_layers):
+            p = f"net.residual_layers.{l}."
+            for w in (conv_w_nk(sd[p + "conditioner_projection.conv.weight"]),
+                      conv_w_nk(sd[p + "conv_layer.conv.weight"][perm]),
+                      conv_w_nk(sd[p + "output_projection.conv.weight"])):
+                hi, lo = split_f16(w)
+                dn16.add(hi); dn16.add(lo)
+            dn16.add(sd[p + "output_projection.conv.bias"])
+        self.dn16 = dn16.finish()
+
     def ensure_pe_rows(self, n: int) -> None:
         """Sinusoid tables auto-grow like the reference's (model/blocks.py:65-72)."""
         if n + 2 > self.pe_rows:
@@ -265,6 +291,19 @@ class PackedHifiGan:
         t.add(wp[0].t().contiguous())          # [k][C]
         t.add(sd["conv_post.bias"].reshape(1).repeat(4))
         self.table = t.finish()
+        # tensor-core table: fp16 K-major weights, fp32 biases; conv_pre / conv_post stay fp32
+        t16 = _Table(self.device)
+        t16.add(conv_w(sd["conv_pre.weight"])); t16.add(sd["conv_pre.bias"])
+        for i, (u, k) in enumerate(zip(hspec.upsample_rates, hspec.upsample_kernel_sizes)):
+            w, b, d0 = pack_conv_transpose(sd[f"ups.{i}.weight"], sd[f"ups.{i}.bias"], u, (k - u) // 2)
+            t16.add(w.permute(0, 2, 1).contiguous().to(torch.float16)); t16.add(b)   # [taps][u*Cout][Cin]
+            for j in range(nk):
+                r = i * nk + j
+                for m in range(nd):
+                    t16.add(conv_w_nk(sd[f"resblocks.{r}.convs1.{m}.weight"]).to(torch.float16)); t16.add(sd[f"resblocks.{r}.convs1.{m}.bias"])
+                    t16.add(conv_w_nk(sd[f"resblocks.{r}.convs2.{m}.weight"]).to(torch.float16)); t16.add(sd[f"resblocks.{r}.convs2.{m}.bias"])
+        t16.add(wp[0].t().contiguous()); t16.add(sd["conv_post.bias"].reshape(1).repeat(4))
+        self.table16 = t16.finish()
         dil = [d for ds in hspec.resblock_dilation_sizes for d in ds]
         cfg = [len(hspec.upsample_rates), C0, nk, nd, 7, wp.shape[2]] + list(hspec.upsample_rates) + taps + shift0 \
             + list(hspec.resblock_kernel_sizes) + dil

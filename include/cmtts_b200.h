@@ -166,6 +166,46 @@ int cmtts_length_regulate(const float* x, const int64_t* cumsum, const int64_t* 
 int cmtts_round_durations(const float* log_d, float d_control, const int64_t* src_lens, float* d_rounded,
                           int64_t* cumsum, int64_t* mel_lens, int64_t B, int64_t T, void* stream);
 
+/* ==== tensor-core (tcgen05) path ================================================================
+ * fp16 operands in HBM, fp32 accumulation in TMEM.  The vocoder uses plain fp16 operands with
+ * "activated storage" (every tensor is stored as leaky_relu(x), the raw value is recovered exactly
+ * in the residual epilogue); the denoiser stack uses fp16 hi/lo operand pairs (3 MMAs per K step,
+ * fp32-class products).  Weight tables: see cmtts_b200/weights.py (PackedAcoustic.dn16,
+ * PackedHifiGan.table16). */
+typedef struct cmtts_umma_desc {
+    int32_t B, M, Lin, N, Cin, taps;
+    int32_t shift[16];
+    int32_t split, epi;                   /* epi: 0 VOC, 1 DN_COND, 2 DN_GATE, 3 DN_OUT */
+    int32_t a_ld, res_ld, out_ld, x_ld;
+    int64_t a_bstride, res_bstride, out_bstride, x_bstride, addvec_bstride;
+    float alpha, res_inv_slope, out_slope, out_scale;
+    int32_t skip_accumulate;
+} cmtts_umma_desc;
+int cmtts_umma_conv1d(const cmtts_umma_desc* c, const void* a_hi, const void* a_lo, const void* w_hi,
+                      const void* w_lo, const float* bias, const void* res_h, const void* sum_h,
+                      void* out_h, void* out_lo, const float* addvec, float* x_f32, float* skip_f32,
+                      void* stream);
+/* fp32 (rows, C) -> fp16 (rows, Cpad) hi [+ lo], optional leaky-ReLU slope (1.0 = none) */
+int cmtts_f32_to_f16(const float* x, void* hi, void* lo, int64_t rows, int64_t C, int64_t Cpad,
+                     float slope, void* stream);
+
+/* D1/D3 + S4 on tensor cores: same contract as cmtts_denoiser_forward; `w16` holds per layer
+ * {cond_w hi, lo [C][H]; k3_w hi, lo [3*2C][C] (gate/filter interleaved per 64); out_w hi, lo [2C][C];
+ *  out_b fp32 [2C]}; cond_hi/cond_lo are the fp16 split of the conditioner (cmtts_f32_to_f16). */
+size_t cmtts_denoiser_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t L);
+int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const* w, const void* const* w16,
+                              const float* x_t, const void* cond_hi, const void* cond_lo,
+                              const float* ds_all, const float* dsp_all, float c_in, float c_out,
+                              float c_skip, int64_t B, int64_t L, float* out, float* model_out,
+                              void* ws, size_t ws_bytes, void* stream);
+
+/* H1-H3 on tensor cores: `w16` = {pre_w fp32 [k][80][C0], pre_b, per level {up_w fp16 [taps*s*Cout][Cin],
+ * up_b fp32, per resblock conv {w fp16 [k*C][C], b fp32}}, post_w fp32 [k][C], post_b}. */
+size_t cmtts_hifigan_tc_workspace_bytes(const int32_t* cfg, int64_t B, int64_t L);
+int cmtts_hifigan_forward_tc(const int32_t* cfg, const void* const* w16, const float* mel /* (B,L,80) */,
+                             int64_t B, int64_t L, float* wav, int16_t* wav_i16, float max_wav_value,
+                             void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,11 +26,20 @@ def load_golden(path):
 _MODELS = {}
 
 
-def gpu_model(spec, sd, key):
+def gpu_model(spec, sd, key, precision="tc"):
     from cmtts_b200.model import CMTotalTTS
+    key = (key, precision)
     if key not in _MODELS:
-        _MODELS[key] = CMTotalTTS(spec=spec).load_state_dict(sd).to(DEV)
+        _MODELS[key] = CMTotalTTS(spec=spec, precision=precision).load_state_dict(sd).to(DEV)
     return _MODELS[key]
+
+
+# mel tolerances: north_star demands 1e-3 max-abs; the fp32 FFMA path differs from torch-CPU only by
+# summation order; the tensor-core path multiplies fp16 hi/lo pairs (22-bit operands)
+MEL_TOL = {"fp32": 1e-4, "tc": 3e-4}
+MODEL_OUT_TOL = {"fp32": 2e-4, "tc": 6e-4}
+# HiFi-GAN: fp32 path ~1e-6; tensor-core path stores fp16 activations (SNR >= 50 dB vs the reference)
+WAV_TOL = {"fp32": 2e-5, "tc": 4e-3}
 
 
 class Replay:

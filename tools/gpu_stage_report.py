@@ -22,14 +22,16 @@ def err(a, b):
 
 
 def main():
-    for ds, B, lo, hi in [("LibriTTS", 2, 10, 12), ("VCTK", 4, 10, 40)]:
+    prec = sys.argv[1] if len(sys.argv) > 1 else "tc"
+    print("precision", prec)
+    for ds, B, lo, hi in [("LJSpeech", 3, 20, 45), ("VCTK", 4, 10, 40)]:
         spec = ModelSpec.preset(ds)
         sd = synthetic.make_acoustic_state_dict(spec, 0)
         batch = synthetic.make_batch(spec, B, lo, hi, seed=1234)
         W = O.Weights(sd)
         with torch.no_grad():
             ref = O.dpen(W, spec, **batch)
-        m = CMTotalTTS(spec=spec).load_state_dict(sd).to(DEV)
+        m = CMTotalTTS(spec=spec, precision=prec).load_state_dict(sd).to(DEV)
         out = m.dpen(batch["texts"], batch["src_lens"], batch["spker_embeds"])
         torch.cuda.synchronize()
         print(f"== {ds} B={B} L={ref['cond'].shape[1]}")
@@ -67,13 +69,33 @@ def main():
             print(f"  T={T} model_out0 {err(tr2['model_output'][0], tr['model_output'][0]):.3e}  mel {err(mel, rm):.3e}  |mel|max {float(rm.abs().max()):.2f}")
     ck = synthetic.make_hifigan_checkpoint(HifiGanSpec(), seed=7)
     Wf = O.Weights(synthetic.fold_weight_norm(ck["generator"]))
-    voc = Generator(hspec=HifiGanSpec()).load_state_dict(ck["generator"]).to(DEV)
-    mel = synthetic.make_mels(2, 80, 24, seed=99)
-    with torch.no_grad():
-        ref = O.hifigan(Wf, HifiGanSpec(), mel)
-    wav = voc(mel.to(DEV))
-    torch.cuda.synchronize()
-    print(f"== hifigan synthetic: wav err {err(wav, ref):.3e} |wav|max {float(ref.abs().max()):.3f}")
+    voc = Generator(hspec=HifiGanSpec(), precision=prec).load_state_dict(ck["generator"]).to(DEV)
+    for (B, L) in [(2, 24), (2, 150)]:
+        mel = synthetic.make_mels(B, 80, L, seed=99)
+        with torch.no_grad():
+            ref = O.hifigan(Wf, HifiGanSpec(), mel)
+        wav = voc(mel.to(DEV))
+        torch.cuda.synchronize()
+        d = (wav.cpu() - ref)
+        snr = 10 * torch.log10(ref.pow(2).mean() / d.pow(2).mean())
+        print(f"== hifigan synthetic (B={B}, L={L}): wav max err {err(wav, ref):.3e} rms err {float(d.pow(2).mean().sqrt()):.3e} "
+              f"|wav|max {float(ref.abs().max()):.3f} SNR {float(snr):.1f} dB")
+    import os
+    real = os.path.join(ROOT, "oracle", "_ref", "hifigan", "generator_universal.pth.tar")
+    if os.path.isfile(real):
+        sd = torch.load(real, map_location="cpu", weights_only=True)["generator"]
+        Wr = O.Weights(synthetic.fold_weight_norm(sd))
+        voc = Generator(hspec=HifiGanSpec(), precision=prec).load_state_dict(sd).to(DEV)
+        mel = synthetic.make_mels(1, 80, 100, seed=3)
+        with torch.no_grad():
+            ref = O.hifigan(Wr, HifiGanSpec(), mel)
+        wav = voc(mel.to(DEV))
+        torch.cuda.synchronize()
+        d = (wav.cpu() - ref)
+        snr = 10 * torch.log10(ref.pow(2).mean() / d.pow(2).mean())
+        i16 = (wav.cpu() * 32768).to(torch.int32) - (ref * 32768).to(torch.int32)
+        print(f"== hifigan REAL universal weights: wav max err {err(wav, ref):.3e} rms {float(d.pow(2).mean().sqrt()):.3e} "
+              f"|wav|max {float(ref.abs().max()):.3f} SNR {float(snr):.1f} dB int16 maxdiff {int(i16.abs().max())}")
 
 
 if __name__ == "__main__":
