@@ -7,8 +7,9 @@
 //   row (t0 + shift[s]); rows outside [0, L) of an utterance are zero-filled by the TMA unit (3-D
 //   tensor map {C, L, B}), which is exactly the conv's zero padding and keeps utterances apart;
 // * warp-specialised persistent CTA (one per SM): warp 0 = TMA producer, warp 1 = single-thread
-//   tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue (one thread per accumulator
-//   row / TMEM lane).  mbarrier ring between producer and MMA, double-buffered TMEM accumulator
+//   tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4-11 = epilogue (one thread per accumulator
+//   row / TMEM lane and column half; global operands of the epilogue are prefetched into registers
+//   before the accumulator wait).  mbarrier ring between producer and MMA, double-buffered TMEM accumulator
 //   between MMA and epilogue so tile i+1's MMAs overlap tile i's epilogue;
 // * 128B- (BK=64) or 64B- (BK=32, for the 32-channel level) swizzled K-major operand tiles, shared
 //   by the TMA tensor maps and the UMMA shared-memory descriptors;
@@ -18,152 +19,18 @@
 //   1e-3 mel tolerance through 20 residual layers;
 // * fused epilogues (bias, conditioner/step/speaker adds, gated activation, residual, skip / MRF
 //   accumulation, leaky-ReLU for the next conv's operand) — see UmmaEpi in umma_conv.cuh.
-#include "umma_conv.cuh"
-#include <cuda.h>
-#include <cudaTypedefs.h>
-#include <math.h>
+#include "umma_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
-// ------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start >> 4 | [16,30) LBO >> 4 (=1, unused for swizzled K-major) | [32,46) SBO >> 4 (8 rows)
-//   [46,48) version = 1 | [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
-template <int BK>
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    constexpr uint64_t row_bytes = BK * 2;                    // 128 or 64
-    constexpr uint64_t sbo = (8 * row_bytes) >> 4;            // 8-row core-matrix group stride
-    constexpr uint64_t layout = (BK == 64) ? 2ull : 4ull;
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
-// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, K-major both
-__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
-    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
-
-struct H8 { __half2 a, b, c, d; };  // 16 bytes
-
-__device__ __forceinline__ void load16h(const __half* p, float (&f)[16]) {
-    const uint4 u0 = *reinterpret_cast<const uint4*>(p);
-    const uint4 u1 = *reinterpret_cast<const uint4*>(p + 8);
-    const __half2* h0 = reinterpret_cast<const __half2*>(&u0);
-    const __half2* h1 = reinterpret_cast<const __half2*>(&u1);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float2 a = __half22float2(h0[i]), b = __half22float2(h1[i]);
-        f[2 * i] = a.x; f[2 * i + 1] = a.y; f[8 + 2 * i] = b.x; f[8 + 2 * i + 1] = b.y;
-    }
-}
-__device__ __forceinline__ void store16h(__half* p, const float (&f)[16]) {
-    uint4 u0, u1;
-    __half2* h0 = reinterpret_cast<__half2*>(&u0);
-    __half2* h1 = reinterpret_cast<__half2*>(&u1);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        h0[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-        h1[i] = __floats2half2_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
-    }
-    *reinterpret_cast<uint4*>(p) = u0;
-    *reinterpret_cast<uint4*>(p + 8) = u1;
-}
-// v = hi + lo with hi = fp16(v), lo = fp16(v - hi)
-__device__ __forceinline__ void store16_hilo(__half* hi, __half* lo, const float (&f)[16]) {
-    float h[16], l[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const __half hh = __float2half_rn(f[i]);
-        h[i] = __half2float(hh);
-        l[i] = f[i] - h[i];
-    }
-    store16h(hi, h);
-    store16h(lo, l);
-}
-__device__ __forceinline__ void load16f(const float* p, float (&f)[16]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float4 v = *reinterpret_cast<const float4*>(p + 4 * i);
-        f[4 * i] = v.x; f[4 * i + 1] = v.y; f[4 * i + 2] = v.z; f[4 * i + 3] = v.w;
-    }
-}
-__device__ __forceinline__ void store16f(float* p, const float (&f)[16]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<float4*>(p + 4 * i) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-}
-
-constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+using namespace umma;
 
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
 template <int BN, int BK, int SPLIT, int STAGES>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                  const UmmaConvParams p) {
@@ -190,7 +57,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -261,7 +128,12 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
     } else if (warp >= 4) {
         // ================================ epilogue ================================
-        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        // 8 warps: warp w reads TMEM lane quarter (w & 3) and column half (w - 4) >> 2.  Everything the
+        // epilogue needs from global memory (residual / x / skip row segment) is fetched into registers
+        // BEFORE the accumulator wait, so that latency overlaps the tile's MMAs.
+        constexpr int BNH = BN / 2;
+        const int q = warp & 3;
+        const int h = (warp - 4) >> 2;
         const int row = q * 32 + lane;
         int abuf = 0; uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -269,21 +141,47 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int mt = rest % m_tiles; const int b = rest / m_tiles;
             const int t = mt * BM + row;
             const bool valid = t < p.M;
+            const int n0 = nt * BN + h * BNH;                 // first output column of this thread
+            uint4 pre[16];
+            bool have_pre = false;
+            if constexpr (SPLIT) {
+                const float* src = nullptr;
+                if (p.epi == UEPI_DN_COND) src = p.x_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + n0;
+                else if (p.epi == UEPI_DN_OUT) {
+                    const int half_n = p.N >> 1;
+                    if (n0 < half_n) src = p.x_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + n0;
+                    else if (p.skip_accumulate) src = p.skip_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + (n0 - half_n);
+                }
+                if (src && valid) {
+                    have_pre = true;
+#pragma unroll
+                    for (int i = 0; i < BNH / 4; ++i) pre[i] = reinterpret_cast<const uint4*>(src)[i];
+                }
+            } else {
+                if (p.res_h && valid) {
+                    have_pre = true;
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.res_h + (long long)b * p.res_bstride + (long long)t * p.res_ld + n0);
+#pragma unroll
+                    for (int i = 0; i < BNH / 8; ++i) pre[i] = rp[i];
+                }
+            }
             mbar_wait(&tfull[abuf], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(abuf * BN) + ((uint32_t)(q * 32) << 16);
 
-            if (p.epi == UEPI_DN_GATE) {
+            if (SPLIT && p.epi == UEPI_DN_GATE) {
                 // tile columns [0, BN/2) are gates, [BN/2, BN) the matching filters (weights.py gate_permutation)
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                constexpr int GH = BN / 4;                        // gate columns per column-half
+#pragma unroll
+                for (int c = 0; c < GH / 16; ++c) {
                     uint32_t rg[16], rf[16];
-                    tmem_ld16(taddr + c * 16, rg);
-                    tmem_ld16(taddr + BN / 2 + c * 16, rf);
+                    const int g0 = h * GH + c * 16;
+                    tmem_ld16(taddr + g0, rg);
+                    tmem_ld16(taddr + BN / 2 + g0, rf);
                     tmem_ld_wait();
                     if (valid) {
-                        const int ng = nt * BN + c * 16, nf = ng + BN / 2;
-                        const int ch = nt * (BN / 2) + c * 16;
+                        const int ng = nt * BN + g0, nf = ng + BN / 2;
+                        const int ch = nt * (BN / 2) + g0;
                         float v[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
@@ -296,23 +194,27 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     }
                 }
             } else {
-#pragma unroll 1
-                for (int c = 0; c < BN / 16; ++c) {
+#pragma unroll
+                for (int c = 0; c < BNH / 16; ++c) {
                     uint32_t r[16];
-                    tmem_ld16(taddr + c * 16, r);
+                    tmem_ld16(taddr + h * BNH + c * 16, r);
                     tmem_ld_wait();
                     if (!valid) continue;
-                    const int n = nt * BN + c * 16;
+                    const int n = n0 + c * 16;
                     float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, p.bias ? p.bias[n + j] : 0.f);
-                    if (p.epi == UEPI_VOC) {
+                    if constexpr (!SPLIT) {   // UEPI_VOC
                         const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
-                        if (p.res_h) {
-                            float rr[16];
-                            load16h(p.res_h + (long long)b * p.res_bstride + (long long)t * p.res_ld + n, rr);
+                        if (have_pre) {
+                            const __half2* h0 = reinterpret_cast<const __half2*>(&pre[2 * c]);
+                            const __half2* h1 = reinterpret_cast<const __half2*>(&pre[2 * c + 1]);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] += lrelu(rr[j], p.res_inv_slope);
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 a = __half22float2(h0[i]), bb = __half22float2(h1[i]);
+                                v[2 * i] += lrelu(a.x, p.res_inv_slope); v[2 * i + 1] += lrelu(a.y, p.res_inv_slope);
+                                v[8 + 2 * i] += lrelu(bb.x, p.res_inv_slope); v[8 + 2 * i + 1] += lrelu(bb.y, p.res_inv_slope);
+                            }
                         }
                         if (p.sum_h) {
                             float ss[16];
@@ -323,33 +225,34 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = lrelu(v[j], p.out_slope);
                         store16h(p.out_h + o, v);
-                    } else if (p.epi == UEPI_DN_COND) {
-                        float a[16], x[16];
-                        load16f(p.addvec + (long long)b * p.addvec_bstride + n, a);
-                        load16f(p.x_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + n, x);
+                    } else {
+                        float x[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] += a[j] + x[j];
-                        const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
-                        store16_hilo(p.out_h + o, p.out_lo + o, v);
-                    } else {  // UEPI_DN_OUT
-                        const int half_n = p.N >> 1;
-                        if (n < half_n) {
-                            float a[16], x[16];
-                            float* xp = p.x_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + n;
+                        for (int i = 0; i < 4; ++i) {
+                            const uint4 u = have_pre ? pre[4 * c + i] : make_uint4(0u, 0u, 0u, 0u);
+                            x[4 * i] = __uint_as_float(u.x); x[4 * i + 1] = __uint_as_float(u.y);
+                            x[4 * i + 2] = __uint_as_float(u.z); x[4 * i + 3] = __uint_as_float(u.w);
+                        }
+                        if (p.epi == UEPI_DN_COND) {
+                            float a[16];
                             load16f(p.addvec + (long long)b * p.addvec_bstride + n, a);
-                            load16f(xp, x);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = (v[j] + a[j] + x[j]) * p.out_scale;
-                            store16f(xp, v);
-                        } else {
-                            float* sp = p.skip_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + (n - half_n);
-                            if (p.skip_accumulate) {
-                                float s[16];
-                                load16f(sp, s);
+                            for (int j = 0; j < 16; ++j) v[j] += a[j] + x[j];
+                            const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
+                            store16_hilo(p.out_h + o, p.out_lo + o, v);
+                        } else {  // UEPI_DN_OUT
+                            const int half_n = p.N >> 1;
+                            if (n < half_n) {
+                                float a[16];
+                                load16f(p.addvec + (long long)b * p.addvec_bstride + n, a);
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) v[j] += s[j];
+                                for (int j = 0; j < 16; ++j) v[j] = (v[j] + a[j] + x[j]) * p.out_scale;
+                                store16f(p.x_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + n, v);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] += x[j];     // x[] holds the old skip (or zeros)
+                                store16f(p.skip_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + (n - half_n), v);
                             }
-                            store16f(sp, v);
                         }
                     }
                 }
@@ -372,46 +275,6 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 // ------------------------------------------------------------------------------------------
 // host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------
-PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
-    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-    if (!fn) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
-    }
-    return fn;
-}
-
-// activations [B][L][C] fp16 (row stride ld, batch stride bstride): box {BK channels, 128 rows, 1}
-bool make_act_map(CUtensorMap* m, const __half* base, int C, int L, int B, int ld, long long bstride, int BK) {
-    auto enc = get_encode_fn();
-    if (!enc) return false;
-    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B};
-    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)bstride * 2};
-    cuuint32_t box[3] = {(cuuint32_t)BK, 128u, 1u};
-    cuuint32_t es[3] = {1, 1, 1};
-    const CUtensorMapSwizzle sw = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, es,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-// weights [taps*N][Cin] fp16: box {BK, BN}
-bool make_w_map(CUtensorMap* m, const __half* base, int Cin, int rows, int BK, int BN) {
-    auto enc = get_encode_fn();
-    if (!enc) return false;
-    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
-    cuuint32_t es[2] = {1, 1};
-    const CUtensorMapSwizzle sw = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, es,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-int g_num_sms = 0;
 
 template <int BN, int BK, int SPLIT>
 int launch_cfg(const UmmaConvParams& p, cudaStream_t s) {
@@ -444,21 +307,20 @@ int launch_cfg(const UmmaConvParams& p, cudaStream_t s) {
             return CMTTS_ERR_CUDA;
         }
     }
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
     const int tiles = p.B * ((p.M + 127) / 128) * (p.N / BN);
-    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    kern<<<grid, 256, SMEM, s>>>(a0, a1, b0, b1, p);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, 384, SMEM, s>>>(a0, a1, b0, b1, p);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }
 
 }  // namespace
 
-int launch_umma_conv(const UmmaConvParams& p, cudaStream_t s) {
+int launch_umma_conv(const UmmaConvParams& p_in, cudaStream_t s) {
+    static int dbg_env = -1;
+    if (dbg_env < 0) { const char* e = getenv("CMTTS_UMMA_DBG"); dbg_env = e ? atoi(e) : 0; }
+    UmmaConvParams p = p_in;
+    p.dbg = dbg_env;
     CMTTS_REQUIRE(p.a_hi && p.w_hi, "umma_conv: null operand");
     CMTTS_REQUIRE(p.taps >= 1 && p.taps <= CMTTS_MAX_TAPS, "umma_conv: taps out of range");
     CMTTS_REQUIRE(p.Cin % 32 == 0, "umma_conv: Cin must be a multiple of 32");
@@ -472,6 +334,10 @@ int launch_umma_conv(const UmmaConvParams& p, cudaStream_t s) {
         return launch_cfg<128, 64, 1>(p, s);
     }
     CMTTS_REQUIRE(p.epi == UEPI_VOC, "umma_conv: denoiser epilogues need split mode");
+    if (!(p.dbg & 2)) {
+        const int rc = launch_umma_halo(p, s);
+        if (rc != CMTTS_ERR_UNSUPPORTED) return rc;
+    }
     if (bk == 64) {
         if (p.N % 256 == 0) return launch_cfg<256, 64, 0>(p, s);
         if (p.N % 128 == 0) return launch_cfg<128, 64, 0>(p, s);

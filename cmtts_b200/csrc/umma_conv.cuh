@@ -30,6 +30,7 @@ struct UmmaConvParams {
     const float* addvec; long long addvec_bstride;
     float* x_f32; long long x_bstride; int x_ld;
     float* skip_f32; int skip_accumulate; float out_scale;
+    int dbg;              // experiment bits (CMTTS_UMMA_DBG): 1 = descriptor base_offset, 2 = disable the halo kernel
 };
 
 static inline UmmaConvParams umma_params_default() {
@@ -39,6 +40,8 @@ static inline UmmaConvParams umma_params_default() {
 }
 
 int launch_umma_conv(const UmmaConvParams& p, cudaStream_t s);
+// halo-tile / resident-weight variant for Cin == N in {32, 64, 128}; CMTTS_ERR_UNSUPPORTED if not applicable
+int launch_umma_halo(const UmmaConvParams& p, cudaStream_t s);
 
 // fp32 -> fp16 (optionally hi/lo pair, optional leaky-ReLU, optional channel zero-padding)
 int launch_f32_to_f16(const float* x, __half* hi, __half* lo, long long rows, int C, int Cpad, float slope, cudaStream_t s);

@@ -15,10 +15,11 @@ lib = _lib.load()
 
 
 def umma(a_hi, w_hi, bias, shifts, N, *, a_lo=None, w_lo=None, epi=0, alpha=1.0, res=None, res_inv=1.0, sum_h=None,
-         out_slope=1.0, out_lo=False, addvec=None, x_f32=None, skip=None, skip_acc=0, out_scale=1.0, out_ch=None):
+         out_slope=1.0, out_lo=False, addvec=None, x_f32=None, skip=None, skip_acc=0, out_scale=1.0, out_ch=None,
+         sync=True, out_buf=None):
     B, L, Cin = a_hi.shape
     out_ch = out_ch or N
-    out_h = torch.empty(B, L, out_ch, dtype=torch.float16, device=DEV) if epi != 3 else None
+    out_h = out_buf if out_buf is not None else (torch.empty(B, L, out_ch, dtype=torch.float16, device=DEV) if epi != 3 else None)
     o_lo = torch.empty(B, L, out_ch, dtype=torch.float16, device=DEV) if out_lo else None
     d = _lib.UmmaDesc(B=B, M=L, Lin=L, N=N, Cin=Cin, taps=len(shifts), split=int(a_lo is not None), epi=epi,
                       a_ld=Cin, res_ld=out_ch, out_ld=out_ch, x_ld=(x_f32.shape[-1] if x_f32 is not None else 0),
@@ -31,7 +32,8 @@ def umma(a_hi, w_hi, bias, shifts, N, *, a_lo=None, w_lo=None, epi=0, alpha=1.0,
     p = _lib.ptr
     _lib.check(lib.cmtts_umma_conv1d(C.byref(d), p(a_hi), p(a_lo), p(w_hi), p(w_lo), p(bias), p(res), p(sum_h), p(out_h),
                                      p(o_lo), p(addvec), p(x_f32), p(skip), _lib.stream_ptr()), "umma_conv1d")
-    torch.cuda.synchronize()
+    if sync:
+        torch.cuda.synchronize()
     return out_h, o_lo
 
 
@@ -131,6 +133,26 @@ def case_split2():
     print(f"split DN_OUT: x err {(xd.cpu() - ref_x).abs().max().item():.3e} skip err {(sd.cpu() - ref_s).abs().max().item():.3e}", flush=True)
 
 
+def case_time(B, L, Cc, k, dil, res=False, reps=20):
+    g = torch.Generator().manual_seed(1)
+    a = (torch.randn(B, L, Cc, generator=g)).half().to(DEV)
+    w = (torch.randn(k * Cc, Cc, generator=g) / (Cc * k) ** 0.5).half().to(DEV)
+    bias = torch.randn(Cc, generator=g).to(DEV)
+    r = a.clone() if res else None
+    shifts = [(i - (k - 1) // 2) * dil for i in range(k)]
+    ob = torch.empty(B, L, Cc, dtype=torch.float16, device=DEV)
+    umma(a, w, bias, shifts, Cc, res=r, res_inv=10.0, out_buf=ob)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        umma(a, w, bias, shifts, Cc, res=r, res_inv=10.0, sync=False, out_buf=ob)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * B * L * Cc * Cc * k
+    byts = B * L * Cc * 2 * (3 if res else 2)
+    print(f"time B={B} L={L} C={Cc} k={k} dil={dil} res={res}: {ms*1e3:8.1f} us  {flops/ms/1e9:7.1f} TFLOP/s  {byts/ms/1e6:7.1f} GB/s (algorithmic)", flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "plain"):
@@ -142,7 +164,19 @@ if __name__ == "__main__":
         case_plain(2, 700, 32, 32, 11, 5)
         case_plain(2, 90, 512, 2048, 3, 1)
         case_plain(1, 40000, 64, 64, 7, 1)
+        case_plain(2, 333, 128, 128, 3, 1)
+        case_plain(2, 1000, 128, 128, 11, 5)
     if which in ("all", "epi"):
         case_voc_epilogue()
+    if which in ("time",):
+        for res in (False, True):
+            case_time(32, 204800, 32, 3, 1, res)
+            case_time(32, 204800, 32, 11, 5, res)
+            case_time(32, 102400, 64, 3, 1, res)
+            case_time(32, 102400, 64, 7, 3, res)
+            case_time(32, 51200, 128, 3, 1, res)
+            case_time(32, 51200, 128, 7, 1, res)
+            case_time(32, 51200, 128, 11, 5, res)
+            case_time(32, 6400, 256, 7, 1, res)
     if which in ("all", "split"):
         case_split2()
