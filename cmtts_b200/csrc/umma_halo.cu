@@ -34,13 +34,17 @@ struct HaloCfg {
 template <int BN, int BK, int CB, int TAPS>
 __global__ void __launch_bounds__(256, 1)
 umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                 const __grid_constant__ CUtensorMap tmR, const UmmaConvParams p, const HaloCfg cfg) {
+                 const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
+                 const UmmaConvParams p, const HaloCfg cfg) {
     constexpr int BM = 128;
     constexpr int ROW_BYTES = BK * 2;
     constexpr int W_BLK = BN * ROW_BYTES;
     constexpr int R_BLK = BM * ROW_BYTES;          // one channel block of the residual tile
     constexpr int R_STAGE = CB * R_BLK;
+    constexpr int O_SLAB = 32 * ROW_BYTES;         // one epilogue warp's 32 output rows of one channel block
+    constexpr int O_BYTES = 4 * CB * O_SLAB;       // whole 128 x BN fp16 output tile
     constexpr int TMEM_COLS = pow2_cols(2 * BN);
+    constexpr bool TMA_STORE = BN >= 64;           // C = 32: a warp's 32 rows are one contiguous 2 KB run, direct stores win
 
     const int a_alloc = cfg.rows_alloc * ROW_BYTES;
     const int a_stage = CB * a_alloc;
@@ -51,7 +55,8 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smA = smem;
     uint8_t* smR = smA + cfg.a_stages * a_stage;
-    uint8_t* smW = smR + cfg.r_stages * R_STAGE;
+    uint8_t* smO = smR + cfg.r_stages * R_STAGE;
+    uint8_t* smW = smO + O_BYTES;
     const int w_blocks = wres ? p.taps * CB : cfg.w_stages;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smW + (size_t)w_blocks * W_BLK);
     uint64_t* a_empty = a_full + MAX_STAGES;
@@ -199,6 +204,7 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // 16-byte chunk swizzle of the TMA-written residual tile (same pattern as the operands)
         const int swz = (BK == 64) ? (row & 7) : ((row >> 1) & 3);
         constexpr int CHUNKS = ROW_BYTES / 16;     // 16-byte chunks per channel-block row: 8 or 4
+        const int swz_o = (BK == 64) ? (lane & 7) : ((lane >> 1) & 3);   // same pattern, row index inside the warp slab
         int abuf = 0; uint32_t aphase = 0;
         int rs = 0; uint32_t rphase = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -221,43 +227,71 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&tfull[abuf], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(abuf * BN) + ((uint32_t)(q * 32) << 16);
+            // the previous tile's TMA store must have finished READING this warp's staging slab
+            if (TMA_STORE) {
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+            }
+            uint8_t* slab = smO + q * (CB * O_SLAB) + lane * ROW_BYTES;     // this thread's row inside the warp slab
 #pragma unroll
             for (int c = 0; c < BN / 16; ++c) {
                 uint32_t r[16];
                 tmem_ld16(taddr + c * 16, r);
                 tmem_ld_wait();
-                if (valid) {
-                    const int n = c * 16;
-                    float v[16];
+                const int n = c * 16;
+                float v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, p.bias[n + j]);
-                    const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
-                    if (has_res) {
-                        const __half2* h0 = reinterpret_cast<const __half2*>(&rres[2 * c]);
-                        const __half2* h1 = reinterpret_cast<const __half2*>(&rres[2 * c + 1]);
+                for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, p.bias[n + j]);
+                if (has_res) {
+                    const __half2* h0 = reinterpret_cast<const __half2*>(&rres[2 * c]);
+                    const __half2* h1 = reinterpret_cast<const __half2*>(&rres[2 * c + 1]);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float2 a = __half22float2(h0[i]), bb = __half22float2(h1[i]);
-                            v[2 * i] += lrelu(a.x, p.res_inv_slope); v[2 * i + 1] += lrelu(a.y, p.res_inv_slope);
-                            v[8 + 2 * i] += lrelu(bb.x, p.res_inv_slope); v[8 + 2 * i + 1] += lrelu(bb.y, p.res_inv_slope);
-                        }
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 a = __half22float2(h0[i]), bb = __half22float2(h1[i]);
+                        v[2 * i] += lrelu(a.x, p.res_inv_slope); v[2 * i + 1] += lrelu(a.y, p.res_inv_slope);
+                        v[8 + 2 * i] += lrelu(bb.x, p.res_inv_slope); v[8 + 2 * i + 1] += lrelu(bb.y, p.res_inv_slope);
                     }
-                    if (p.sum_h) {
-                        float ss[16];
-                        load16h(p.sum_h + o, ss);
+                }
+                if (p.sum_h && valid) {
+                    float ss[16];
+                    load16h(p.sum_h + (long long)b * p.out_bstride + (long long)t * p.out_ld + n, ss);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] += ss[j];
-                    }
+                    for (int j = 0; j < 16; ++j) v[j] += ss[j];
+                }
+                // stage as fp16 in the TMA box layout: 16-byte chunk j of a row lives at chunk (j ^ swz)
+                uint4 u0, u1;
+                __half2* p0 = reinterpret_cast<__half2*>(&u0);
+                __half2* p1 = reinterpret_cast<__half2*>(&u1);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = lrelu(v[j], p.out_slope);
-                    store16h(p.out_h + o, v);
+                for (int i = 0; i < 4; ++i) {
+                    p0[i] = __floats2half2_rn(lrelu(v[2 * i], p.out_slope), lrelu(v[2 * i + 1], p.out_slope));
+                    p1[i] = __floats2half2_rn(lrelu(v[8 + 2 * i], p.out_slope), lrelu(v[8 + 2 * i + 1], p.out_slope));
+                }
+                if (TMA_STORE) {
+                    const int cb = (2 * c) / CHUNKS, j0 = (2 * c) % CHUNKS;
+                    *reinterpret_cast<uint4*>(slab + cb * O_SLAB + ((j0 ^ swz_o) << 4)) = u0;
+                    *reinterpret_cast<uint4*>(slab + cb * O_SLAB + (((j0 + 1) ^ swz_o) << 4)) = u1;
+                } else if (valid) {
+                    __half* op = p.out_h + (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
+                    *reinterpret_cast<uint4*>(op) = u0;
+                    *reinterpret_cast<uint4*>(op + 8) = u1;
                 }
             }
             tc_fence_before();
+            if (TMA_STORE) fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[abuf]);
+            if (lane == 0) {
+                mbar_arrive(&tempty[abuf]);
+                if (TMA_STORE) {
+#pragma unroll
+                    for (int cb = 0; cb < CB; ++cb)
+                        tma_store_3d(&tmO, smO + q * (CB * O_SLAB) + cb * O_SLAB, cb * BK, mt * BM + q * 32, b);
+                    tma_store_commit();
+                }
+            }
             abuf ^= 1; if (abuf == 0) aphase ^= 1;
         }
+        if (TMA_STORE && lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -275,7 +309,8 @@ int launch_halo_cfg(const UmmaConvParams& p, cudaStream_t s) {
     constexpr int R_STAGE = CB * 128 * ROW_BYTES;
     constexpr int ROW_ALIGN = 1024 / ROW_BYTES;        // rows per 1024-byte swizzle-aligned unit
     constexpr size_t LIMIT = 227 * 1024;
-    constexpr size_t FIXED = (6 * MAX_STAGES + 4) * 8 + 16 + 1024;
+    constexpr size_t O_BYTES = (size_t)4 * CB * 32 * ROW_BYTES;
+    constexpr size_t FIXED = (6 * MAX_STAGES + 4) * 8 + 16 + 1024 + O_BYTES;
 
     HaloCfg cfg{};
     const int span = p.shift[p.taps - 1] - p.shift[0];
@@ -313,7 +348,7 @@ int launch_halo_cfg(const UmmaConvParams& p, cudaStream_t s) {
         }
         attr_done = true;
     }
-    CUtensorMap a_map, w_map, r_map;
+    CUtensorMap a_map, w_map, r_map, o_map;
     if (!make_act_map(&a_map, p.a_hi, p.Cin, p.Lin, p.B, p.a_ld, p.a_bstride, BK, cfg.box_rows) ||
         !make_w_map(&w_map, p.w_hi, p.Cin, p.taps * p.N, BK, BN)) {
         cmtts_set_error("umma_halo: cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
@@ -324,9 +359,13 @@ int launch_halo_cfg(const UmmaConvParams& p, cudaStream_t s) {
         cmtts_set_error("umma_halo: cuTensorMapEncodeTiled failed (residual)", __FILE__, __LINE__);
         return CMTTS_ERR_CUDA;
     }
+    if (!make_act_map(&o_map, p.out_h, p.N, p.M, p.B, p.out_ld, p.out_bstride, BK, 32)) {
+        cmtts_set_error("umma_halo: cuTensorMapEncodeTiled failed (output)", __FILE__, __LINE__);
+        return CMTTS_ERR_CUDA;
+    }
     const int tiles = p.B * ((p.M + 127) / 128);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, 256, smem, s>>>(a_map, w_map, r_map, p, cfg);
+    kern<<<grid, 256, smem, s>>>(a_map, w_map, r_map, o_map, p, cfg);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }
@@ -340,6 +379,7 @@ int launch_umma_halo(const UmmaConvParams& p, cudaStream_t s) {
     for (int i = 1; i < p.taps; ++i)
         if (p.shift[i] <= p.shift[i - 1]) return CMTTS_ERR_UNSUPPORTED;
     if (p.shift[p.taps - 1] - p.shift[0] > 96) return CMTTS_ERR_UNSUPPORTED;
+    if (p.out_ld % 8 != 0 || p.out_bstride % 8 != 0 || ((uintptr_t)p.out_h % 16) != 0) return CMTTS_ERR_UNSUPPORTED;
     if (p.res_h && (p.res_ld % 8 != 0 || p.res_bstride % 8 != 0 || ((uintptr_t)p.res_h % 16) != 0)) return CMTTS_ERR_UNSUPPORTED;
     if (p.B == 0 || p.M == 0) return CMTTS_OK;
     for (int i = 2; i < p.taps; ++i)   // uniform tap spacing (dilation)
