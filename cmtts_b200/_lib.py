@@ -90,6 +90,13 @@ PROTOTYPES = {
     "cmtts_f32_to_f16": (C.c_int, [vp, vp, vp, i64, i64, i64, f32, vp]),
     "cmtts_denoiser_tc_workspace_bytes": (szt, [PD, i64, i64]),
     "cmtts_denoiser_forward_tc": (C.c_int, [PD, PV, PV, vp, vp, vp, vp, vp, f32, f32, f32, i64, i64, vp, vp, vp, szt, vp]),
+    "cmtts_encoder_tc_workspace_bytes": (szt, [PD, i64, i64]),
+    "cmtts_encoder_forward_tc": (C.c_int, [PD, PV, PV, vp, vp, i64, i64, vp, vp, szt, vp]),
+    "cmtts_variance_token_tc_workspace_bytes": (szt, [PD, i64, i64]),
+    "cmtts_variance_token_tc": (C.c_int, [PD, PV, PV, vp, vp, vp, f32, f32, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                          vp, szt, vp]),
+    "cmtts_variance_frame_tc_workspace_bytes": (szt, [PD, i64, i64]),
+    "cmtts_variance_frame_tc": (C.c_int, [PD, PV, PV, vp, vp, vp, vp, f32, i64, i64, i64, vp, vp, vp, vp, vp, vp, szt, vp]),
     "cmtts_hifigan_tc_workspace_bytes": (szt, [PI32, i64, i64]),
     "cmtts_hifigan_forward_tc": (C.c_int, [PI32, PV, vp, i64, i64, vp, vp, f32, vp, szt, vp]),
 }

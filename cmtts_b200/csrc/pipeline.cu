@@ -503,6 +503,33 @@ extern "C" int cmtts_round_durations(const float* log_d, float d_control, const 
 // ============================================================================================
 // tensor-core (tcgen05) path
 // ============================================================================================
+namespace {
+
+struct HL { __half* hi; __half* lo; };
+
+// hi/lo weight pairs are stored pre-scaled by this power of two (cmtts_b200/weights.py: TC_W_SCALE)
+constexpr float TC_W_SCALE_INV = 1.0f / 1024.0f;
+
+// "same" conv on fp16 hi/lo operands: A (B, M, Cin), W [k][N][Cin]; generic fp32 epilogue
+UmmaConvParams tc_same(HL a, int B, int M, int Cin, const void* w_hi, const void* w_lo, const float* bias, int N,
+                       int k, int dil) {
+    UmmaConvParams u = umma_params_default();
+    u.B = B; u.M = M; u.Lin = M; u.N = N; u.Cin = Cin; u.taps = k;
+    for (int i = 0; i < k; ++i) u.shift[i] = (i - (k - 1) / 2) * dil;
+    u.split = 1; u.epi = UEPI_F32;
+    u.a_hi = a.hi; u.a_lo = a.lo; u.a_bstride = (long long)M * Cin; u.a_ld = Cin;
+    u.w_hi = (const __half*)w_hi; u.w_lo = (const __half*)w_lo;
+    u.bias = bias; u.n_valid = N; u.act = ACT_NONE;
+    u.alpha = TC_W_SCALE_INV;
+    return u;
+}
+void tc_out32(UmmaConvParams& u, float* out, int M, int ld) { u.out_f32 = out; u.out32_bstride = (long long)M * ld; u.out32_ld = ld; }
+void tc_out16(UmmaConvParams& u, HL o, int M, int ld) { u.out_h = o.hi; u.out_lo = o.lo; u.out_bstride = (long long)M * ld; u.out_ld = ld; }
+void tc_res(UmmaConvParams& u, float* r, int M, int ld, float scale = 1.f) { u.x_f32 = r; u.x_bstride = (long long)M * ld; u.x_ld = ld; u.res_scale = scale; }
+int to_hl(const float* x, HL o, long long rows, int C, cudaStream_t s) { return launch_f32_to_f16(x, o.hi, o.lo, rows, C, C, 1.f, s); }
+
+}  // namespace
+
 extern "C" int cmtts_umma_conv1d(const cmtts_umma_desc* c, const void* a_hi, const void* a_lo, const void* w_hi,
                                  const void* w_lo, const float* bias, const void* res_h, const void* sum_h,
                                  void* out_h, void* out_lo, const float* addvec, float* x_f32, float* skip_f32,
@@ -532,7 +559,7 @@ extern "C" int cmtts_f32_to_f16(const float* x, void* hi, void* lo, int64_t rows
 
 extern "C" size_t cmtts_denoiser_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t L) {
     const size_t n = (size_t)B * L * d->res_channels;
-    return align_up(n * 4) * 3 + align_up(n * 2) * 4;
+    return align_up(n * 4) * 3 + align_up(n * 2) * 4 + align_up((size_t)B * L * 128 * 2) * 2;
 }
 
 extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const* w, const void* const* w16,
@@ -554,19 +581,29 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
     __half* y_lo = cv.take<__half>(n * C);
     __half* g_hi = cv.take<__half>(n * C);
     __half* g_lo = cv.take<__half>(n * C);
+    __half* xt_hi = cv.take<__half>(n * 128);
+    __half* xt_lo = cv.take<__half>(n * 128);
     const long long NL = (long long)d->res_layers * C;
     const long long bs = (long long)L * C;
+    const void* const* wx = w16 + d->res_layers * 7;   // {in_w hi, lo [C][128]; skip_w hi, lo [C][C]}
+    CMTTS_REQUIRE(M <= 128, "denoiser_tc: n_mels must be <= 128");
 
-    // input projection on the fp32 path (K = 80): relu(W (c_in x_t) + b)
-    ConvParams p = conv_same(x_t, B, L, M, F(w, CMTTS_DN_IN_W), F(w, CMTTS_DN_IN_B), C, 1, 1, x);
-    p.alpha = c_in; p.act = ACT_RELU;
-    CMTTS_TRY(launch_conv1d_simt(p, s));
+    // input projection: relu(W (c_in x_t) + b), x_t zero-padded to 128 channels as an fp16 hi/lo pair
+    CMTTS_TRY(launch_f32_to_f16(x_t, xt_hi, xt_lo, (long long)n, M, 128, 1.f, s));
+    {
+        UmmaConvParams u = tc_same(HL{xt_hi, xt_lo}, B, L, 128, wx[0], wx[1], F(w, CMTTS_DN_IN_B), C, 1, 1);
+        u.alpha = c_in * TC_W_SCALE_INV; u.act = ACT_RELU;
+        tc_out32(u, x, L, C);
+        CMTTS_TRY(launch_umma_conv(u, s));
+    }
+    ConvParams p;
     for (int l = 0; l < d->res_layers; ++l) {
         const void* const* wl = w16 + l * 7;
         const int o = CMTTS_DN_LAYER0 + l * CMTTS_DN_PER_LAYER;
         UmmaConvParams u = umma_params_default();
         // (a) y = Wc cond + bc + (step + speaker)[b] + x                    blocks.py:669-678
         u.B = B; u.M = L; u.Lin = L; u.N = C; u.Cin = H; u.taps = 1; u.shift[0] = 0; u.split = 1; u.epi = UEPI_DN_COND;
+        u.alpha = TC_W_SCALE_INV;
         u.a_hi = (const __half*)cond_hi; u.a_lo = (const __half*)cond_lo; u.a_bstride = (long long)L * H; u.a_ld = H;
         u.w_hi = (const __half*)wl[0]; u.w_lo = (const __half*)wl[1];
         u.bias = F(w, o + 1);
@@ -577,7 +614,7 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
         // (b) g = sigmoid(gate) * tanh(filter) of the k=3 conv               blocks.py:677-681
         u = umma_params_default();
         u.B = B; u.M = L; u.Lin = L; u.N = 2 * C; u.Cin = C; u.taps = 3; u.shift[0] = -1; u.shift[1] = 0; u.shift[2] = 1;
-        u.split = 1; u.epi = UEPI_DN_GATE;
+        u.split = 1; u.epi = UEPI_DN_GATE; u.alpha = TC_W_SCALE_INV;
         u.a_hi = y_hi; u.a_lo = y_lo; u.a_bstride = bs; u.a_ld = C;
         u.w_hi = (const __half*)wl[2]; u.w_lo = (const __half*)wl[3];
         u.bias = F(w, o + 3);
@@ -586,6 +623,7 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
         // (c) x = (Wo[:C] g + b + step[b] + x) / sqrt(2) ; skip (+)= Wo[C:] g + b     blocks.py:676, :683-686
         u = umma_params_default();
         u.B = B; u.M = L; u.Lin = L; u.N = 2 * C; u.Cin = C; u.taps = 1; u.shift[0] = 0; u.split = 1; u.epi = UEPI_DN_OUT;
+        u.alpha = TC_W_SCALE_INV;
         u.a_hi = g_hi; u.a_lo = g_lo; u.a_bstride = bs; u.a_ld = C;
         u.w_hi = (const __half*)wl[4]; u.w_lo = (const __half*)wl[5];
         u.bias = (const float*)wl[6];
@@ -596,9 +634,15 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
         CMTTS_TRY(launch_umma_conv(u, s));
     }
     const int o = CMTTS_DN_LAYER0 + d->res_layers * CMTTS_DN_PER_LAYER;
-    p = conv_same(skip, B, L, C, F(w, o + 0), F(w, o + 1), C, 1, 1, v);
-    p.alpha = (float)(1.0 / sqrt((double)d->res_layers)); p.act = ACT_RELU;
-    CMTTS_TRY(launch_conv1d_simt(p, s));
+    // skip projection: relu(W (sum skip / sqrt(n_layers)) + b) on the hi/lo kernel (y/g buffers are free now)
+    CMTTS_TRY(to_hl(skip, HL{y_hi, y_lo}, (long long)n, C, s));
+    {
+        UmmaConvParams u = tc_same(HL{y_hi, y_lo}, B, L, C, wx[2], wx[3], F(w, o + 1), C, 1, 1);
+        u.alpha = (float)(1.0 / sqrt((double)d->res_layers)) * TC_W_SCALE_INV; u.act = ACT_RELU;
+        tc_out32(u, v, L, C);
+        CMTTS_TRY(launch_umma_conv(u, s));
+    }
+    // output projection (N = 80) + Karras combination stay on the fp32 kernel
     p = conv_same(v, B, L, C, F(w, o + 2), F(w, o + 3), M, 1, 1, out);
     p.beta = c_out;
     if (model_out) { p.aux_out = model_out; p.aux_bstride = (long long)L * M; p.aux_ld = M; }
@@ -695,5 +739,202 @@ extern "C" int cmtts_hifigan_forward_tc(const int32_t* cfg, const void* const* w
     }
     CMTTS_TRY(launch_conv_post_f16(xs, F(w, wi), F(w, wi + 1), (float)c.n_kernels, wav, wav_i16, max_wav_value, B, len,
                                    ch, c.post_k, s));
+    return CMTTS_OK;
+}
+
+
+// ============================================================================================
+// encoder / variance adaptor / projections on the hi/lo tensor-core kernel (fp32-class products)
+// ============================================================================================
+
+extern "C" size_t cmtts_encoder_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t T) {
+    const size_t n = (size_t)B * T, C = d->hidden;
+    return cmtts_encoder_workspace_bytes(d, B, T) + align_up(n * C * 2) * 2 + align_up(n * 4 * C * 2) * 2;
+}
+
+// w16: per layer {in_proj hi, lo [3C][C]; out_proj hi, lo [C][C]; ffn1 hi, lo [k*4C][C]; ffn2 hi, lo [C][4C]}
+extern "C" int cmtts_encoder_forward_tc(const cmtts_dims* d, const void* const* w, const void* const* w16,
+                                        const int64_t* tokens, const int64_t* src_lens, int64_t B_, int64_t T_,
+                                        float* enc_out, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = (int)B_, T = (int)T_, C = d->hidden;
+    CMTTS_REQUIRE(ws_bytes >= cmtts_encoder_tc_workspace_bytes(d, B_, T_), "encoder_tc: workspace too small");
+    CMTTS_REQUIRE(C % 128 == 0, "encoder_tc: hidden size must be a multiple of 128");
+    if (B == 0 || T == 0) return CMTTS_OK;
+    Carver cv(ws, ws_bytes);
+    const size_t n = (size_t)B * T;
+    float* x = cv.take<float>(n * C);
+    float* h = cv.take<float>(n * C);
+    float* att = cv.take<float>(n * C);
+    float* qkv = cv.take<float>(n * 3 * C);
+    cv.take<float>(n * 4 * C);   // (fp32 path's FFN buffer, unused here; keeps the carve order of the fp32 workspace)
+    HL h16{cv.take<__half>(n * C), cv.take<__half>(n * C)};
+    HL ff16{cv.take<__half>(n * 4 * C), cv.take<__half>(n * 4 * C)};
+    const long long* lens = (const long long*)src_lens;
+
+    CMTTS_TRY(launch_embed_tokens((const long long*)tokens, F(w, CMTTS_ENC_EMB), F(w, CMTTS_ENC_PE), d->pe_rows,
+                                  sqrtf((float)C), x, B, T, C, lens, s));
+    for (int l = 0; l < d->enc_layers; ++l) {
+        const int o = CMTTS_ENC_LAYER0 + l * CMTTS_ENC_PER_LAYER;
+        const void* const* wl = w16 + l * 8;
+        CMTTS_TRY(launch_layernorm(x, F(w, o + 0), F(w, o + 1), 1e-12f, h, B, T, C, nullptr, s));
+        CMTTS_TRY(to_hl(h, h16, (long long)n, C, s));
+        UmmaConvParams u = tc_same(h16, B, T, C, wl[0], wl[1], nullptr, 3 * C, 1, 1);
+        tc_out32(u, qkv, T, 3 * C);
+        CMTTS_TRY(launch_umma_conv(u, s));
+        CMTTS_TRY(launch_attention(qkv, lens, att, B, T, C, d->enc_heads, s));
+        CMTTS_TRY(to_hl(att, h16, (long long)n, C, s));
+        u = tc_same(h16, B, T, C, wl[2], wl[3], nullptr, C, 1, 1);       // x = (x + attn W_o) * nonpad
+        tc_res(u, x, T, C); tc_out32(u, x, T, C); u.lens = lens;
+        CMTTS_TRY(launch_umma_conv(u, s));
+        CMTTS_TRY(launch_layernorm(x, F(w, o + 4), F(w, o + 5), 1e-12f, h, B, T, C, nullptr, s));
+        CMTTS_TRY(to_hl(h, h16, (long long)n, C, s));
+        u = tc_same(h16, B, T, C, wl[4], wl[5], F(w, o + 7), 4 * C, d->ffn_kernel, 1);
+        u.beta = (float)pow((double)d->ffn_kernel, -0.5); u.act = d->ffn_act;
+        tc_out16(u, ff16, T, 4 * C);
+        CMTTS_TRY(launch_umma_conv(u, s));
+        u = tc_same(ff16, B, T, 4 * C, wl[6], wl[7], F(w, o + 9), C, 1, 1);
+        tc_res(u, x, T, C); tc_out32(u, x, T, C); u.lens = lens;
+        CMTTS_TRY(launch_umma_conv(u, s));
+    }
+    const int o = CMTTS_ENC_LAYER0 + d->enc_layers * CMTTS_ENC_PER_LAYER;
+    CMTTS_TRY(launch_layernorm(x, F(w, o), F(w, o + 1), 1e-5f, enc_out, B, T, C, lens, s));
+    return CMTTS_OK;
+}
+
+namespace {
+// predictor stack on tensor cores: conv -> ReLU (epilogue) -> LayerNorm (fp32 row kernel) -> hi/lo -> conv ... -> LN + head
+int predictor_stack_tc(const cmtts_dims* d, const void* const* w, const void* const* w16, int conv0, int head,
+                       int n_layers, int k, HL x16, int Cin, int B, int T, const long long* lens, int odim, float scale,
+                       float* bufa, float* bufb, HL tmp16, float* out, cudaStream_t s) {
+    const int Fc = d->filter;
+    HL cur = x16;
+    int cin = Cin;
+    for (int i = 0; i < n_layers; ++i) {
+        UmmaConvParams u = tc_same(cur, B, T, cin, w16[2 * i], w16[2 * i + 1], F(w, conv0 + 4 * i + 1), Fc, k, 1);
+        u.act = ACT_RELU;
+        tc_out32(u, bufa, T, Fc);
+        CMTTS_TRY(launch_umma_conv(u, s));
+        if (i + 1 < n_layers) {
+            CMTTS_TRY(launch_layernorm(bufa, F(w, conv0 + 4 * i + 2), F(w, conv0 + 4 * i + 3), 1e-12f, bufb, B, T, Fc, lens, s));
+            CMTTS_TRY(to_hl(bufb, tmp16, (long long)B * T, Fc, s));
+            cur = tmp16; cin = Fc;
+        } else {
+            CMTTS_TRY(launch_ln_head(bufa, F(w, conv0 + 4 * i + 2), F(w, conv0 + 4 * i + 3), 1e-12f, F(w, head),
+                                     F(w, head + 1), odim, scale, out, B, T, Fc, lens, s));
+        }
+    }
+    return CMTTS_OK;
+}
+}  // namespace
+
+extern "C" size_t cmtts_variance_token_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t T) {
+    const size_t n = (size_t)B * T;
+    const size_t big = d->hidden > d->filter ? d->hidden : d->filter;
+    return cmtts_variance_token_workspace_bytes(d, B, T) + align_up(n * big * 2) * 4;
+}
+
+// w16: {dur conv_i hi, lo} x dur_layers, {energy conv_i hi, lo} x pred_layers, cwt_in hi, lo, {cwt conv_i hi, lo} x pred_layers
+extern "C" int cmtts_variance_token_tc(const cmtts_dims* d, const void* const* w, const void* const* w16,
+                                       const float* enc, const int64_t* src_lens, const float* spker_embeds,
+                                       float e_control, float d_control, int64_t B_, int64_t T_, float* out1,
+                                       float* log_d, float* d_rounded, float* e_pred, int64_t* e_idx, int64_t* cumsum,
+                                       int64_t* mel_lens, float* spk_emb, float* f0_stats, void* ws, size_t ws_bytes,
+                                       void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = (int)B_, T = (int)T_, C = d->hidden, Fc = d->filter;
+    CMTTS_REQUIRE(ws_bytes >= cmtts_variance_token_tc_workspace_bytes(d, B_, T_), "variance_token_tc: workspace too small");
+    CMTTS_REQUIRE(C % 64 == 0 && Fc % 128 == 0, "variance_token_tc: channel counts must suit the UMMA tiling");
+    if (B == 0 || T == 0) return CMTTS_OK;
+    const VaIdx ix(d);
+    Carver cv(ws, ws_bytes);
+    const size_t n = (size_t)B * T;
+    const size_t big = C > Fc ? C : Fc;
+    float* x = cv.take<float>(n * big);
+    float* xp = cv.take<float>(n * big);
+    float* bufa = cv.take<float>(n * big);
+    float* bufb = cv.take<float>(n * big);
+    float* st1 = cv.take<float>((size_t)B * d->cwt_hidden);
+    float* st2 = cv.take<float>((size_t)B * d->cwt_hidden);
+    float* e_raw = cv.take<float>(n);
+    HL x16{cv.take<__half>(n * big), cv.take<__half>(n * big)};
+    HL t16{cv.take<__half>(n * big), cv.take<__half>(n * big)};
+    const long long* lens = (const long long*)src_lens;
+
+    cudaMemcpyAsync(x, enc, n * C * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    if (d->multi_speaker) {
+        CMTTS_REQUIRE(spker_embeds != nullptr && spk_emb != nullptr, "Speaker embedding should not be None");
+        ConvParams p = conv_same(spker_embeds, 1, B, d->spk_dim, F(w, ix.spk_w), F(w, ix.spk_b), C, 1, 1, spk_emb);
+        CMTTS_TRY(launch_conv1d_simt(p, s));
+        CMTTS_TRY(launch_add_rowvec(x, spk_emb, B, T, C, s));
+    }
+    CMTTS_TRY(to_hl(x, x16, (long long)n, C, s));
+    CMTTS_TRY(predictor_stack_tc(d, w, w16, ix.dur0, ix.dur_head, d->dur_layers, d->dur_kernel, x16, C, B, T, lens, 1, 1.f,
+                                 bufa, bufb, t16, log_d, s));
+    CMTTS_TRY(launch_add_positional(x, F(w, ix.pe_c), d->pe_rows, F(w, ix.en_alpha), xp, B, T, C, s));
+    CMTTS_TRY(to_hl(xp, x16, (long long)n, C, s));
+    CMTTS_TRY(predictor_stack_tc(d, w, w16 + 2 * d->dur_layers, ix.en0, ix.en_head, d->pred_layers, d->pred_kernel, x16, C,
+                                 B, T, nullptr, 1, 1.f, bufa, bufb, t16, e_raw, s));
+    CMTTS_TRY(launch_energy_embed(x, e_raw, e_control, F(w, ix.en_bins), d->energy_bins - 1, F(w, ix.en_emb), out1,
+                                  (long long*)e_idx, e_pred, B, T, C, s));
+    CMTTS_TRY(launch_round_durations(log_d, d_control, lens, d_rounded, (long long*)cumsum, (long long*)mel_lens, B, T, s));
+    {
+        const int h = d->cwt_hidden;
+        ConvParams p = conv_same(out1, 1, B, C, F(w, ix.st0), F(w, ix.st0 + 1), h, 1, 1, st1);
+        p.x_ld = T * C; p.act = ACT_RELU;
+        CMTTS_TRY(launch_conv1d_simt(p, s));
+        p = conv_same(st1, 1, B, h, F(w, ix.st0 + 2), F(w, ix.st0 + 3), h, 1, 1, st2);
+        p.act = ACT_RELU;
+        CMTTS_TRY(launch_conv1d_simt(p, s));
+        p = conv_same(st2, 1, B, h, F(w, ix.st0 + 4), F(w, ix.st0 + 5), 4, 1, 1, f0_stats);
+        CMTTS_TRY(launch_conv1d_simt(p, s));
+    }
+    return CMTTS_OK;
+}
+
+extern "C" size_t cmtts_variance_frame_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t L) {
+    const size_t n = (size_t)B * L;
+    const size_t big = d->hidden > d->filter ? d->hidden : d->filter;
+    return cmtts_variance_frame_workspace_bytes(d, B, L) + align_up(n * big * 2) * 4;
+}
+
+extern "C" int cmtts_variance_frame_tc(const cmtts_dims* d, const void* const* w, const void* const* w16,
+                                       const float* out1, const int64_t* cumsum, const int64_t* mel_lens,
+                                       const float* f0_stats, float p_control, int64_t B_, int64_t T_, int64_t L_,
+                                       float* cond, int64_t* mel2ph, float* cwt, float* f0_denorm, int64_t* pitch_idx,
+                                       void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = (int)B_, T = (int)T_, L = (int)L_, C = d->hidden, h = d->cwt_hidden, Fc = d->filter;
+    CMTTS_REQUIRE(ws_bytes >= cmtts_variance_frame_tc_workspace_bytes(d, B_, L_), "variance_frame_tc: workspace too small");
+    CMTTS_REQUIRE(h % 128 == 0 && C % 64 == 0, "variance_frame_tc: channel counts must suit the UMMA tiling");
+    if (B == 0 || L == 0) return CMTTS_OK;
+    const VaIdx ix(d);
+    Carver cv(ws, ws_bytes);
+    const size_t n = (size_t)B * L;
+    const size_t big = C > Fc ? C : Fc;
+    float* xf = cv.take<float>(n * C);
+    float* hin = cv.take<float>(n * h);
+    float* hp = cv.take<float>(n * h);
+    float* bufa = cv.take<float>(n * Fc);
+    float* bufb = cv.take<float>(n * Fc);
+    float* rec = cv.take<float>(n);
+    float* stat = cv.take<float>((size_t)B * 2);
+    HL x16{cv.take<__half>(n * big), cv.take<__half>(n * big)};
+    HL t16{cv.take<__half>(n * big), cv.take<__half>(n * big)};
+    const void* const* wc = w16 + 2 * d->dur_layers + 2 * d->pred_layers;
+
+    CMTTS_TRY(launch_length_regulate(out1, (const long long*)cumsum, (const long long*)mel_lens, xf,
+                                     (long long*)mel2ph, B, T, L, C, s));
+    CMTTS_TRY(to_hl(xf, x16, (long long)n, C, s));
+    UmmaConvParams u = tc_same(x16, B, L, C, wc[0], wc[1], F(w, ix.cwt_in + 1), h, 1, 1);
+    tc_out32(u, hin, L, h);
+    CMTTS_TRY(launch_umma_conv(u, s));
+    CMTTS_TRY(launch_add_positional(hin, F(w, ix.pe_h), d->pe_rows, F(w, ix.cwt_alpha), hp, B, L, h, s));
+    CMTTS_TRY(to_hl(hp, x16, (long long)n, h, s));
+    CMTTS_TRY(predictor_stack_tc(d, w, wc + 2, ix.cwt0, ix.cwt_head, d->pred_layers, d->pred_kernel, x16, h, B, L, nullptr,
+                                 d->cwt_out, p_control, bufa, bufb, t16, cwt, s));
+    CMTTS_TRY(cmtts_cwt_pitch_impl(cwt, d->cwt_out, F(w, ix.cwt_b), f0_stats, 4, d->cwt_std_scale, d->pitch_eps,
+                                   d->use_uv, d->f0_mel_min, d->f0_mel_span, xf, F(w, ix.pitch_emb), d->pitch_bins,
+                                   cond, f0_denorm, (long long*)pitch_idx, rec, stat, B, L, C, s));
     return CMTTS_OK;
 }

@@ -146,7 +146,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             bool have_pre = false;
             if constexpr (SPLIT) {
                 const float* src = nullptr;
-                if (p.epi == UEPI_DN_COND) src = p.x_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + n0;
+                if (p.epi == UEPI_DN_COND || (p.epi == UEPI_F32 && p.x_f32 != nullptr && n0 < p.n_valid))
+                    src = p.x_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + n0;
                 else if (p.epi == UEPI_DN_OUT) {
                     const int half_n = p.N >> 1;
                     if (n0 < half_n) src = p.x_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + n0;
@@ -185,8 +186,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         float v[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const float g = __uint_as_float(rg[j]) + p.bias[ng + j];
-                            const float f = __uint_as_float(rf[j]) + p.bias[nf + j];
+                            const float g = fmaf(__uint_as_float(rg[j]), p.alpha, p.bias[ng + j]);
+                            const float f = fmaf(__uint_as_float(rf[j]), p.alpha, p.bias[nf + j]);
                             v[j] = (1.f / (1.f + expf(-g))) * tanhf(f);
                         }
                         const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + ch;
@@ -233,7 +234,32 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             x[4 * i] = __uint_as_float(u.x); x[4 * i + 1] = __uint_as_float(u.y);
                             x[4 * i + 2] = __uint_as_float(u.z); x[4 * i + 3] = __uint_as_float(u.w);
                         }
-                        if (p.epi == UEPI_DN_COND) {
+                        if (p.epi == UEPI_F32) {
+                            if (n >= p.n_valid) continue;
+                            const bool keep = p.lens == nullptr || (long long)t < p.lens[b];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                float u = v[j] * p.beta;
+                                if (p.act == ACT_RELU) u = fmaxf(u, 0.f);
+                                else if (p.act == ACT_GELU) u = 0.5f * u * (1.f + erff(u * 0.70710678118654752440f));
+                                else if (p.act == ACT_SWISH) u = u / (1.f + expf(-u));
+                                else if (p.act == ACT_LRELU) u = u > 0.f ? u : u * p.out_slope;
+                                v[j] = u;
+                            }
+                            if (p.addvec) {
+                                float a[16];
+                                load16f(p.addvec + (long long)b * p.addvec_bstride + n, a);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] += a[j];
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = keep ? fmaf(x[j], p.res_scale, v[j]) * p.out_scale : 0.f;
+                            if (p.out_f32) store16f(p.out_f32 + (long long)b * p.out32_bstride + (long long)t * p.out32_ld + n, v);
+                            if (p.out_h) {
+                                const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
+                                store16_hilo(p.out_h + o, p.out_lo + o, v);
+                            }
+                        } else if (p.epi == UEPI_DN_COND) {
                             float a[16];
                             load16f(p.addvec + (long long)b * p.addvec_bstride + n, a);
 #pragma unroll

@@ -9,6 +9,8 @@ enum UmmaEpi {
     UEPI_DN_GATE = 2,  // sigmoid(gate + b) * tanh(filter + b)          -> fp16 hi/lo   (BN = 128: 64 gates | 64 filters)
     UEPI_DN_OUT = 3,   // cols <  N/2: x = (acc + b + addvec[b] + x) * out_scale (fp32, in place)
                        // cols >= N/2: skip (+)= acc + b                 (fp32)
+    UEPI_F32 = 4,      // generic: v = act((acc*alpha + bias) * beta) + addvec[b] + res*res_scale ; v *= out_scale ;
+                       // rows >= lens[b] -> 0 ; written as fp32 (out_f32) and/or fp16 hi/lo ; cols >= n_valid dropped
 };
 
 struct UmmaConvParams {
@@ -30,12 +32,14 @@ struct UmmaConvParams {
     const float* addvec; long long addvec_bstride;
     float* x_f32; long long x_bstride; int x_ld;
     float* skip_f32; int skip_accumulate; float out_scale;
+    // UEPI_F32 extras (res = x_f32 with x_bstride / x_ld)
+    int act; float beta; float res_scale; const long long* lens; float* out_f32; long long out32_bstride; int out32_ld; int n_valid;
     int dbg;              // experiment bits (CMTTS_UMMA_DBG): 1 = descriptor base_offset, 2 = disable the halo kernel
 };
 
 static inline UmmaConvParams umma_params_default() {
     UmmaConvParams p{};
-    p.alpha = 1.f; p.res_inv_slope = 1.f; p.out_slope = 1.f; p.out_scale = 1.f;
+    p.alpha = 1.f; p.res_inv_slope = 1.f; p.out_slope = 1.f; p.out_scale = 1.f; p.beta = 1.f; p.res_scale = 1.f;
     return p;
 }
 

@@ -73,6 +73,11 @@ class CMTotalTTS:
         if precision not in self.PRECISIONS:
             raise ValueError(f"precision must be one of {self.PRECISIONS}")
         self.precision = precision
+        # Encoder + variance-adaptor GEMMs can also run on the hi/lo tensor-core kernel (1.6 ms faster per
+        # C2 batch), but tcgen05's fp32 accumulation is not IEEE round-to-nearest: over K = 2304 the
+        # encoder output differs from the reference by ~1e-5 instead of ~2e-6 (FFMA), which makes a
+        # duration / energy / pitch quantiser flip ~5x more likely.  Parity first: off by default.
+        self.tc_frontend = False
         self.spec = spec
         self.device = torch.device("cpu")
         self._sd: Optional[Dict[str, torch.Tensor]] = None
@@ -153,9 +158,16 @@ class CMTotalTTS:
         H = s.hidden
         with torch.cuda.device(dev):
             enc = torch.empty(B, T, H, **f32)
-            ws = self._ws.get("enc", lib.cmtts_encoder_workspace_bytes(d, B, T))
-            _lib.check(lib.cmtts_encoder_forward(d, self.packed.enc.ptrs, _lib.ptr(texts), _lib.ptr(src_lens), B, T,
-                                                 _lib.ptr(enc), _lib.ptr(ws), ws.numel(), st), "encoder_forward")
+            tc = self.precision == "tc" and self.tc_frontend
+            if tc:
+                ws = self._ws.get("enc", lib.cmtts_encoder_tc_workspace_bytes(d, B, T))
+                _lib.check(lib.cmtts_encoder_forward_tc(d, self.packed.enc.ptrs, self.packed.enc16.ptrs, _lib.ptr(texts),
+                                                        _lib.ptr(src_lens), B, T, _lib.ptr(enc), _lib.ptr(ws), ws.numel(), st),
+                           "encoder_forward_tc")
+            else:
+                ws = self._ws.get("enc", lib.cmtts_encoder_workspace_bytes(d, B, T))
+                _lib.check(lib.cmtts_encoder_forward(d, self.packed.enc.ptrs, _lib.ptr(texts), _lib.ptr(src_lens), B, T,
+                                                     _lib.ptr(enc), _lib.ptr(ws), ws.numel(), st), "encoder_forward")
             out1 = torch.empty(B, T, H, **f32)
             log_d = torch.empty(B, T, **f32)
             d_rounded = torch.empty(B, T, **f32)
@@ -165,12 +177,17 @@ class CMTotalTTS:
             mel_lens = torch.empty(B, **i64)
             spk = torch.empty(B, H, **f32) if s.multi_speaker else None
             f0_stats = torch.empty(B, 4, **f32)
-            ws = self._ws.get("vat", lib.cmtts_variance_token_workspace_bytes(d, B, T))
-            _lib.check(lib.cmtts_variance_token(
-                d, self.packed.va.ptrs, _lib.ptr(enc), _lib.ptr(src_lens), _lib.ptr(spk_in), e_control, d_control,
-                B, T, _lib.ptr(out1), _lib.ptr(log_d), _lib.ptr(d_rounded), _lib.ptr(e_pred), _lib.ptr(e_idx),
-                _lib.ptr(cumsum), _lib.ptr(mel_lens), _lib.ptr(spk), _lib.ptr(f0_stats), _lib.ptr(ws), ws.numel(), st),
-                "variance_token")
+            vt_args = (_lib.ptr(enc), _lib.ptr(src_lens), _lib.ptr(spk_in), e_control, d_control,
+                       B, T, _lib.ptr(out1), _lib.ptr(log_d), _lib.ptr(d_rounded), _lib.ptr(e_pred), _lib.ptr(e_idx),
+                       _lib.ptr(cumsum), _lib.ptr(mel_lens), _lib.ptr(spk), _lib.ptr(f0_stats))
+            if tc:
+                ws = self._ws.get("vat", lib.cmtts_variance_token_tc_workspace_bytes(d, B, T))
+                _lib.check(lib.cmtts_variance_token_tc(d, self.packed.va.ptrs, self.packed.va16.ptrs, *vt_args,
+                                                       _lib.ptr(ws), ws.numel(), st), "variance_token_tc")
+            else:
+                ws = self._ws.get("vat", lib.cmtts_variance_token_workspace_bytes(d, B, T))
+                _lib.check(lib.cmtts_variance_token(d, self.packed.va.ptrs, *vt_args, _lib.ptr(ws), ws.numel(), st),
+                           "variance_token")
             # the one host round trip of the path: output length is data dependent
             local_max = int(mel_lens.max().item()) if B > 0 else 0
             if l_max_hook is not None:
@@ -184,11 +201,17 @@ class CMTotalTTS:
             pitch_idx = torch.empty(B, L, **i64)
             if L > 0:
                 d = C.byref(self._dims)
-                ws = self._ws.get("vaf", lib.cmtts_variance_frame_workspace_bytes(d, B, L))
-                _lib.check(lib.cmtts_variance_frame(
-                    d, self.packed.va.ptrs, _lib.ptr(out1), _lib.ptr(cumsum), _lib.ptr(mel_lens), _lib.ptr(f0_stats),
-                    p_control, B, T, L, _lib.ptr(cond), _lib.ptr(mel2ph), _lib.ptr(cwt), _lib.ptr(f0_denorm),
-                    _lib.ptr(pitch_idx), _lib.ptr(ws), ws.numel(), st), "variance_frame")
+                vf_args = (_lib.ptr(out1), _lib.ptr(cumsum), _lib.ptr(mel_lens), _lib.ptr(f0_stats),
+                           p_control, B, T, L, _lib.ptr(cond), _lib.ptr(mel2ph), _lib.ptr(cwt), _lib.ptr(f0_denorm),
+                           _lib.ptr(pitch_idx))
+                if tc:
+                    ws = self._ws.get("vaf", lib.cmtts_variance_frame_tc_workspace_bytes(d, B, L))
+                    _lib.check(lib.cmtts_variance_frame_tc(d, self.packed.va.ptrs, self.packed.va16.ptrs, *vf_args,
+                                                           _lib.ptr(ws), ws.numel(), st), "variance_frame_tc")
+                else:
+                    ws = self._ws.get("vaf", lib.cmtts_variance_frame_workspace_bytes(d, B, L))
+                    _lib.check(lib.cmtts_variance_frame(d, self.packed.va.ptrs, *vf_args, _lib.ptr(ws), ws.numel(), st),
+                               "variance_frame")
         ar_t = torch.arange(T, device=dev)
         ar_l = torch.arange(local_max, device=dev)
         return {

@@ -106,11 +106,12 @@ class Pipeline:
     HiFi-GAN on the whole padded batch, x32768 -> int16, crop to mel_len * hop)."""
 
     def __init__(self, spec: ModelSpec, acoustic_sd: Dict[str, torch.Tensor], hifigan_sd: Dict[str, torch.Tensor],
-                 device, distillation: bool = True, precision: str = "tc"):
+                 device, distillation: bool = True, precision: str = "tc", tc_frontend: bool = False):
         self.spec = spec
         self.precision = precision
         self.device = torch.device(device)
         self.model = CMTotalTTS(spec=spec, precision=precision).load_state_dict(acoustic_sd).to(self.device)
+        self.model.tc_frontend = bool(tc_frontend)
         self.diffusion = KarrasDenoiser(sigma_data=spec.sigma_data, sigma_max=spec.sigma_max,
                                         sigma_min=spec.sigma_min, rho=spec.rho, distillation=distillation)
         self.vocoder = Generator(hspec=spec.hifigan, precision=precision).load_state_dict(hifigan_sd).to(self.device)

@@ -86,10 +86,19 @@ def conv_w_nk(w: torch.Tensor) -> torch.Tensor:
     return w.permute(2, 0, 1).contiguous()
 
 
-def split_f16(w: torch.Tensor):
-    """fp32 -> (hi, lo) fp16 with hi + lo == w to ~22 bits (hi = fp16(w), lo = fp16(w - hi))."""
-    hi = w.to(torch.float16)
-    lo = (w - hi.to(torch.float32)).to(torch.float16)
+#: power-of-two pre-scale of hi/lo weight pairs: keeps the `lo` halves (|lo| ~ 2^-11 |w|) out of the fp16
+#: subnormal range, where their absolute spacing (6e-8) would cap the pair at ~18 bits for |w| ~ 0.01.
+#: The kernels multiply the accumulator by 1 / TC_W_SCALE (csrc/pipeline.cu: TC_W_SCALE).
+TC_W_SCALE = 1024.0
+
+
+def split_f16(w: torch.Tensor, scale: float = TC_W_SCALE):
+    """fp32 -> (hi, lo) fp16 with (hi + lo) / scale == w to ~22 bits (hi = fp16(w s), lo = fp16(w s - hi))."""
+    ws = w.to(torch.float32) * scale
+    if float(ws.abs().max()) >= 60000.0:
+        raise ValueError("weight too large for the fp16 hi/lo split")
+    hi = ws.to(torch.float16)
+    lo = (ws - hi.to(torch.float32)).to(torch.float16)
     return hi, lo
 
 
@@ -253,7 +262,38 @@ class PackedAcoustic:
                 hi, lo = split_f16(w)
                 dn16.add(hi); dn16.add(lo)
             dn16.add(sd[p + "output_projection.conv.bias"])
+        # projections around the stack: input (K = n_mels zero-padded to 128) and skip
+        w_in = torch.zeros(C, 128)
+        w_in[:, :s.n_mels] = sd["net.input_projection.0.conv.weight"][:, :, 0]
+        for w in (w_in, sd["net.skip_projection.conv.weight"][:, :, 0].contiguous()):
+            hi, lo = split_f16(w)
+            dn16.add(hi); dn16.add(lo)
         self.dn16 = dn16.finish()
+
+        def add_pair(tab, w):
+            hi, lo = split_f16(w)
+            tab.add(hi); tab.add(lo)
+
+        # encoder GEMMs on the hi/lo tensor-core kernel: per layer in_proj, out_proj, ffn1, ffn2
+        enc16 = _Table(dev)
+        for l in range(s.enc_layers):
+            p = f"{TE}layers.{l}.op."
+            add_pair(enc16, sd[p + "self_attn.in_proj_weight"].contiguous())              # [3C][C]
+            add_pair(enc16, sd[p + "self_attn.out_proj.weight"].contiguous())             # [C][C]
+            add_pair(enc16, conv_w_nk(sd[p + "ffn.ffn_1.weight"]))                        # [k][4C][C]
+            add_pair(enc16, sd[p + "ffn.ffn_2.weight"].contiguous())                      # [C][4C]
+        self.enc16 = enc16.finish()
+
+        # variance-adaptor convs: duration, energy, cwt_in, cwt predictor
+        va16 = _Table(dev)
+        for i in range(s.dur_layers):
+            add_pair(va16, conv_w_nk(sd[f"{VA}duration_predictor.conv.{i}.1.weight"]))
+        for i in range(s.pred_layers):
+            add_pair(va16, conv_w_nk(sd[f"{VA}energy_predictor.conv.{i}.1.weight"]))
+        add_pair(va16, sd[VA + "cwt_predictor.0.weight"].contiguous())                    # [h][C]
+        for i in range(s.pred_layers):
+            add_pair(va16, conv_w_nk(sd[f"{VA}cwt_predictor.1.conv.{i}.1.weight"]))
+        self.va16 = va16.finish()
 
     def ensure_pe_rows(self, n: int) -> None:
         """Sinusoid tables auto-grow like the reference's (model/blocks.py:65-72)."""

@@ -191,13 +191,34 @@ int cmtts_f32_to_f16(const float* x, void* hi, void* lo, int64_t rows, int64_t C
 
 /* D1/D3 + S4 on tensor cores: same contract as cmtts_denoiser_forward; `w16` holds per layer
  * {cond_w hi, lo [C][H]; k3_w hi, lo [3*2C][C] (gate/filter interleaved per 64); out_w hi, lo [2C][C];
- *  out_b fp32 [2C]}; cond_hi/cond_lo are the fp16 split of the conditioner (cmtts_f32_to_f16). */
+ *  out_b fp32 [2C]}, then {in_w hi, lo [C][128] (K zero-padded); skip_w hi, lo [C][C]};
+ * cond_hi/cond_lo are the fp16 split of the conditioner (cmtts_f32_to_f16). */
 size_t cmtts_denoiser_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t L);
 int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const* w, const void* const* w16,
                               const float* x_t, const void* cond_hi, const void* cond_lo,
                               const float* ds_all, const float* dsp_all, float c_in, float c_out,
                               float c_skip, int64_t B, int64_t L, float* out, float* model_out,
                               void* ws, size_t ws_bytes, void* stream);
+
+/* E1-E4 / V1-V5 with their GEMMs on the hi/lo tensor-core kernel (same contracts as the fp32 entry
+ * points; `w16` = fp16 hi/lo weight pairs, see PackedAcoustic.enc16 / va16 in cmtts_b200/weights.py) */
+size_t cmtts_encoder_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t T);
+int cmtts_encoder_forward_tc(const cmtts_dims* d, const void* const* w, const void* const* w16,
+                             const int64_t* tokens, const int64_t* src_lens, int64_t B, int64_t T,
+                             float* enc_out, void* ws, size_t ws_bytes, void* stream);
+size_t cmtts_variance_token_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t T);
+int cmtts_variance_token_tc(const cmtts_dims* d, const void* const* w, const void* const* w16, const float* enc,
+                            const int64_t* src_lens, const float* spker_embeds, float e_control,
+                            float d_control, int64_t B, int64_t T, float* out1, float* log_d,
+                            float* d_rounded, float* e_pred, int64_t* e_idx, int64_t* cumsum,
+                            int64_t* mel_lens, float* spk_emb, float* f0_stats, void* ws, size_t ws_bytes,
+                            void* stream);
+size_t cmtts_variance_frame_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t L);
+int cmtts_variance_frame_tc(const cmtts_dims* d, const void* const* w, const void* const* w16, const float* out1,
+                            const int64_t* cumsum, const int64_t* mel_lens, const float* f0_stats,
+                            float p_control, int64_t B, int64_t T, int64_t L, float* cond, int64_t* mel2ph,
+                            float* cwt, float* f0_denorm, int64_t* pitch_idx, void* ws, size_t ws_bytes,
+                            void* stream);
 
 /* H1-H3 on tensor cores: `w16` = {pre_w fp32 [k][80][C0], pre_b, per level {up_w fp16 [taps*s*Cout][Cin],
  * up_b fp32, per resblock conv {w fp16 [k*C][C], b fp32}}, post_w fp32 [k][C], post_b}. */

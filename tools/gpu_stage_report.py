@@ -24,7 +24,7 @@ def err(a, b):
 def main():
     prec = sys.argv[1] if len(sys.argv) > 1 else "tc"
     print("precision", prec)
-    for ds, B, lo, hi in [("LJSpeech", 3, 20, 45), ("VCTK", 4, 10, 40)]:
+    for ds, B, lo, hi in [("LJSpeech", 3, 20, 45), ("VCTK", 4, 10, 40), ("LibriTTS", 8, 60, 115)]:
         spec = ModelSpec.preset(ds)
         sd = synthetic.make_acoustic_state_dict(spec, 0)
         batch = synthetic.make_batch(spec, B, lo, hi, seed=1234)

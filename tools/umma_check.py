@@ -89,6 +89,14 @@ def split(x):
     return hi, (x - hi.float()).half()
 
 
+def wsplit(w):
+    from cmtts_b200.weights import split_f16
+    return split_f16(w)
+
+
+W_INV = 1.0 / 1024.0
+
+
 def case_split2():
     g = torch.Generator().manual_seed(8)
     B, L, Cc = 2, 200, 256
@@ -101,9 +109,9 @@ def case_split2():
     w = torch.randn(1, Cc, Cc, generator=g) / 16
     b = torch.randn(Cc, generator=g)
     ref = ref_conv(cond, w, b, [0]) + vec[:, None] + x
-    ch, cl = split(cond); wh, wl = split(w.reshape(Cc, Cc))
+    ch, cl = split(cond); wh, wl = wsplit(w.reshape(Cc, Cc))
     yh_, yl_ = umma(ch.to(DEV), wh.to(DEV), b.to(DEV), [0], Cc, a_lo=cl.to(DEV), w_lo=wl.to(DEV), epi=1, out_lo=True,
-                    addvec=vec.to(DEV), x_f32=x.to(DEV))
+                    addvec=vec.to(DEV), x_f32=x.to(DEV), alpha=W_INV)
     got = yh_.float().cpu() + yl_.float().cpu()
     print(f"split DN_COND: max err {(got - ref).abs().max().item():.3e}", flush=True)
     # DN_GATE: k3 conv 256 -> 512, gate/filter pairs
@@ -113,9 +121,9 @@ def case_split2():
     ref = torch.sigmoid(conv[..., :Cc]) * torch.tanh(conv[..., Cc:])
     perm = gate_permutation(Cc)
     wp, bp = w[:, perm], b[perm]
-    yh, yl = split(y); wh, wl = split(wp.reshape(3 * 2 * Cc, Cc))
+    yh, yl = split(y); wh, wl = wsplit(wp.reshape(3 * 2 * Cc, Cc))
     gh, gl = umma(yh.to(DEV), wh.to(DEV), bp.to(DEV), [-1, 0, 1], 2 * Cc, a_lo=yl.to(DEV), w_lo=wl.to(DEV), epi=2,
-                  out_lo=True, out_ch=Cc)
+                  out_lo=True, out_ch=Cc, alpha=W_INV)
     got = gh.float().cpu() + gl.float().cpu()
     print(f"split DN_GATE: max err {(got - ref).abs().max().item():.3e}", flush=True)
     # DN_OUT
@@ -126,10 +134,10 @@ def case_split2():
     ref_x = (conv[..., :Cc] + vec[:, None] + x) * 0.70710678
     skip0 = torch.randn(B, L, Cc, generator=g)
     ref_s = skip0 + conv[..., Cc:]
-    ah, al = split(gact); wh, wl = split(w.reshape(2 * Cc, Cc))
+    ah, al = split(gact); wh, wl = wsplit(w.reshape(2 * Cc, Cc))
     xd = x.to(DEV).clone(); sd = skip0.to(DEV).clone()
     umma(ah.to(DEV), wh.to(DEV), b.to(DEV), [0], 2 * Cc, a_lo=al.to(DEV), w_lo=wl.to(DEV), epi=3, addvec=vec.to(DEV),
-         x_f32=xd, skip=sd, skip_acc=1, out_scale=0.70710678, out_ch=Cc)
+         x_f32=xd, skip=sd, skip_acc=1, out_scale=0.70710678, out_ch=Cc, alpha=W_INV)
     print(f"split DN_OUT: x err {(xd.cpu() - ref_x).abs().max().item():.3e} skip err {(sd.cpu() - ref_s).abs().max().item():.3e}", flush=True)
 
 
