@@ -5,6 +5,7 @@
 #include "umma_conv.cuh"
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 // implemented in rowops.cu
@@ -682,6 +683,9 @@ extern "C" int cmtts_hifigan_forward_tc(const int32_t* cfg, const void* const* w
     CMTTS_TRY(launch_conv1d_simt(p, s));
     int ch = c.C0, len = L;
     const float inv_nk = 1.0f / (float)c.n_kernels;
+    static int fuse_env = -1;
+    if (fuse_env < 0) { const char* e = getenv("CMTTS_UMMA_DBG"); fuse_env = e ? atoi(e) : 0; }
+    const bool fuse_off = (fuse_env & 4) != 0;
     for (int i = 0; i < c.n_levels; ++i) {
         const int r = c.rates[i], cout = ch / 2;
         const bool last_level = (i == c.n_levels - 1);
@@ -700,39 +704,50 @@ extern "C" int cmtts_hifigan_forward_tc(const int32_t* cfg, const void* const* w
         const long long bs = (long long)len * ch;
         for (int j = 0; j < c.n_kernels; ++j) {
             const int k = c.ksize[j];
-            const __half* yin = up;
+            const __half* cur = up;                 // lrelu(running resblock state)
             for (int m = 0; m < c.n_dil; ++m) {
                 const int dl = c.dil[j * c.n_dil + m];
                 const bool last = (m == c.n_dil - 1);
+                // MRF (models.py:155-160): the last iteration of resblock j adds into xs — raw partial sums,
+                // activated on the last resblock for the next level's conv (slope 0.01 before conv_post, :161)
+                const __half* sum = (last && j > 0) ? xs : nullptr;
+                const float oslope = !last ? 0.1f : ((j == c.n_kernels - 1) ? (last_level ? 0.01f : 0.1f) : 1.f);
+                // fused iteration (both convs, t tile kept in shared memory) for the HBM-bound levels;
+                // it cannot run in place (tiles read halo rows of their neighbours), so it ping-pongs yb / tb
+                if (!fuse_off) {
+                    __half* fdst = last ? xs : ((cur == yb) ? tb : yb);
+                    UmmaResblockParams rb{};
+                    rb.B = B; rb.L = len; rb.C = ch; rb.taps = k; rb.dil = dl;
+                    rb.a = cur; rb.w1 = (const __half*)w[wi]; rb.b1 = F(w, wi + 1); rb.t_slope = 0.1f;
+                    rb.w2 = (const __half*)w[wi + 2]; rb.b2 = F(w, wi + 3); rb.alpha2 = 1.f;
+                    rb.res_inv_slope = 10.f; rb.sum_h = sum; rb.out_h = fdst; rb.out_slope = oslope;
+                    const int rc = launch_umma_resblock(rb, s);
+                    if (rc == CMTTS_OK) { if (!last) cur = fdst; wi += 4; continue; }
+                    if (rc != CMTTS_ERR_UNSUPPORTED) return rc;
+                }
+                __half* tbuf = (cur == tb) ? yb : tb;
+                __half* odst = last ? xs : ((cur == up) ? (tbuf == tb ? yb : tb) : const_cast<__half*>(cur));
                 // t = lrelu(c1(lrelu(y)) + b1)
                 u = umma_params_default();
                 u.B = B; u.M = len; u.Lin = len; u.N = ch; u.Cin = ch; u.taps = k;
                 for (int t = 0; t < k; ++t) u.shift[t] = (t - (k - 1) / 2) * dl;
                 u.epi = UEPI_VOC;
-                u.a_hi = yin; u.a_bstride = bs; u.a_ld = ch;
+                u.a_hi = cur; u.a_bstride = bs; u.a_ld = ch;
                 u.w_hi = (const __half*)w[wi]; u.bias = F(w, wi + 1);
-                u.out_h = tb; u.out_ld = ch; u.out_bstride = bs; u.out_slope = 0.1f;
+                u.out_h = tbuf; u.out_ld = ch; u.out_bstride = bs; u.out_slope = 0.1f;
                 CMTTS_TRY(launch_umma_conv(u, s));
                 // y' = c2(t) + b2 + y ; y recovered from its stored lrelu(y) (slope 0.1 -> x10 on negatives)
                 u = umma_params_default();
                 u.B = B; u.M = len; u.Lin = len; u.N = ch; u.Cin = ch; u.taps = k;
                 for (int t = 0; t < k; ++t) u.shift[t] = t - (k - 1) / 2;
                 u.epi = UEPI_VOC;
-                u.a_hi = tb; u.a_bstride = bs; u.a_ld = ch;
+                u.a_hi = tbuf; u.a_bstride = bs; u.a_ld = ch;
                 u.w_hi = (const __half*)w[wi + 2]; u.bias = F(w, wi + 3);
-                u.res_h = yin; u.res_bstride = bs; u.res_ld = ch; u.res_inv_slope = 10.f;
+                u.res_h = cur; u.res_bstride = bs; u.res_ld = ch; u.res_inv_slope = 10.f;
                 u.out_ld = ch; u.out_bstride = bs;
-                if (!last) {
-                    u.out_h = yb; u.out_slope = 0.1f;
-                } else {
-                    // MRF: xs = sum_j resblock_j(x); raw partial sums, activated on the last one for the
-                    // next level's conv (slope 0.01 before conv_post, models.py:161)
-                    u.out_h = xs;
-                    if (j > 0) u.sum_h = xs;
-                    u.out_slope = (j == c.n_kernels - 1) ? (last_level ? 0.01f : 0.1f) : 1.f;
-                }
+                u.out_h = odst; u.sum_h = sum; u.out_slope = oslope;
                 CMTTS_TRY(launch_umma_conv(u, s));
-                yin = yb;
+                if (!last) cur = odst;
                 wi += 4;
             }
         }

@@ -47,6 +47,20 @@ int launch_umma_conv(const UmmaConvParams& p, cudaStream_t s);
 // halo-tile / resident-weight variant for Cin == N in {32, 64, 128}; CMTTS_ERR_UNSUPPORTED if not applicable
 int launch_umma_halo(const UmmaConvParams& p, cudaStream_t s);
 
+// Fused ResBlock iteration y' = c2(lrelu(c1(a) + b1)) + b2 + inv_lrelu(a) on fp16 activated storage
+// (all tensors [B][L][C] contiguous; weights [k][C][C] fp16); see umma_resblock.cu
+struct UmmaResblockParams {
+    int B, L, C, taps, dil;
+    const __half* a;                       // lrelu(y)
+    const __half* w1; const float* b1; float t_slope;
+    const __half* w2; const float* b2; float alpha2;
+    float res_inv_slope;
+    const __half* sum_h;                   // optional raw partial sum added before the output activation
+    __half* out_h; float out_slope;
+};
+// CMTTS_ERR_UNSUPPORTED when the shape is not covered (C not in {32, 64}, weights do not fit, ...)
+int launch_umma_resblock(const UmmaResblockParams& p, cudaStream_t s);
+
 // fp32 -> fp16 (optionally hi/lo pair, optional leaky-ReLU, optional channel zero-padding)
 int launch_f32_to_f16(const float* x, __half* hi, __half* lo, long long rows, int C, int Cpad, float slope, cudaStream_t s);
 // HiFi-GAN output stage on fp16 activated input
