@@ -71,7 +71,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
+        // (whole warp, convergent; single-lane instructions are elected inside the PTX wrappers)
+        {
             prefetch_tmap(&tmA0); prefetch_tmap(&tmB0);
             if (SPLIT) { prefetch_tmap(&tmA1); prefetch_tmap(&tmB1); }
             int stage = 0; uint32_t phase = 0;
@@ -81,28 +82,29 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 for (int kb = 0; kb < kblocks; ++kb) {
                     const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * BK;
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    mbar_expect_tx_elect(&full[stage], STAGE_BYTES);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     const int row = mt * BM + p.shift[tap];
-                    tma_load_3d(sa, &tmA0, &full[stage], c0, row, b);
-                    if (SPLIT) tma_load_3d(sa + A_BYTES, &tmA1, &full[stage], c0, row, b);
+                    tma_load_3d_elect(sa, &tmA0, &full[stage], c0, row, b);
+                    if (SPLIT) tma_load_3d_elect(sa + A_BYTES, &tmA1, &full[stage], c0, row, b);
                     uint8_t* sb = sa + NOP * A_BYTES;
-                    tma_load_2d(sb, &tmB0, &full[stage], c0, tap * p.N + nt * BN);
-                    if (SPLIT) tma_load_2d(sb + B_BYTES, &tmB1, &full[stage], c0, tap * p.N + nt * BN);
+                    tma_load_2d_elect(sb, &tmB0, &full[stage], c0, tap * p.N + nt * BN);
+                    if (SPLIT) tma_load_2d_elect(sb + B_BYTES, &tmB1, &full[stage], c0, tap * p.N + nt * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
+        {
+            const uint32_t tmem_u = make_uniform(tmem_base);
             const uint32_t idesc = make_idesc(BM, BN);
             int stage = 0; uint32_t phase = 0;
             int abuf = 0; uint32_t aphase = 0;
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
                 mbar_wait(&tempty[abuf], aphase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(abuf * BN);
+                const uint32_t d_tmem = tmem_u + (uint32_t)(abuf * BN);
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
@@ -113,16 +115,16 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 x 16B units along K
-                        umma_f16(d_tmem, a0 + adv, b0 + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_f16_pred(d_tmem, a0 + adv, b0 + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u, 0u);
                         if (SPLIT) {
-                            umma_f16(d_tmem, a0 + adv, b1 + adv, idesc, 1u);
-                            umma_f16(d_tmem, a1 + adv, b0 + adv, idesc, 1u);
+                            umma_f16_pred(d_tmem, a0 + adv, b1 + adv, idesc, 1u, 0u);
+                            umma_f16_pred(d_tmem, a1 + adv, b0 + adv, idesc, 1u, 0u);
                         }
                     }
-                    umma_commit(&empty[stage]);   // frees the smem slot once these MMAs have read it
+                    umma_commit_pred(&empty[stage], 0u);   // frees the smem slot once these MMAs have read it
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull[abuf]);        // accumulator complete -> epilogue
+                umma_commit_pred(&tfull[abuf], 0u);        // accumulator complete -> epilogue
                 abuf ^= 1; if (abuf == 0) aphase ^= 1;
             }
         }

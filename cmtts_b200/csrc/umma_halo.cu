@@ -93,28 +93,28 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (warp == 0) {
         // ======================= activation producer (+ resident weights) =======================
-        if (lane == 0) {
+        {
             prefetch_tmap(&tmA); prefetch_tmap(&tmW);
             if (wres) {
-                mbar_expect_tx(&w_full[0], (uint32_t)(p.taps * CB * W_BLK));
+                mbar_expect_tx_elect(&w_full[0], (uint32_t)(p.taps * CB * W_BLK));
                 for (int tap = 0; tap < p.taps; ++tap)
                     for (int cb = 0; cb < CB; ++cb)
-                        tma_load_2d(smW + (size_t)(tap * CB + cb) * W_BLK, &tmW, &w_full[0], cb * BK, tap * p.N);
+                        tma_load_2d_elect(smW + (size_t)(tap * CB + cb) * W_BLK, &tmW, &w_full[0], cb * BK, tap * p.N);
             }
             int stage = 0; uint32_t phase = 0;
             const uint32_t bytes = (uint32_t)(CB * cfg.box_rows * ROW_BYTES);
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
                 const int mt = tile % m_tiles, b = tile / m_tiles;
                 mbar_wait(&a_empty[stage], phase ^ 1);
-                mbar_expect_tx(&a_full[stage], bytes);
+                mbar_expect_tx_elect(&a_full[stage], bytes);
                 for (int cb = 0; cb < CB; ++cb)
-                    tma_load_3d(smA + stage * a_stage + cb * a_alloc, &tmA, &a_full[stage], cb * BK, mt * BM + shift0, b);
+                    tma_load_3d_elect(smA + stage * a_stage + cb * a_alloc, &tmA, &a_full[stage], cb * BK, mt * BM + shift0, b);
                 if (++stage == cfg.a_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 3) {
         // ======================= residual + streamed-weight producer =======================
-        if (lane == 0 && (has_res || !wres)) {
+        if (has_res || !wres) {
             if (has_res) prefetch_tmap(&tmR);
             int ws = 0; uint32_t wphase = 0;
             int rs = 0; uint32_t rphase = 0;
@@ -122,17 +122,17 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int mt = tile % m_tiles, b = tile / m_tiles;
                 if (has_res) {
                     mbar_wait(&r_empty[rs], rphase ^ 1);
-                    mbar_expect_tx(&r_full[rs], R_STAGE);
+                    mbar_expect_tx_elect(&r_full[rs], R_STAGE);
                     for (int cb = 0; cb < CB; ++cb)
-                        tma_load_3d(smR + rs * R_STAGE + cb * R_BLK, &tmR, &r_full[rs], cb * BK, mt * BM, b);
+                        tma_load_3d_elect(smR + rs * R_STAGE + cb * R_BLK, &tmR, &r_full[rs], cb * BK, mt * BM, b);
                     if (++rs == cfg.r_stages) { rs = 0; rphase ^= 1; }
                 }
                 if (!wres) {
                     for (int tap = 0; tap < p.taps; ++tap)
                         for (int cb = 0; cb < CB; ++cb) {
                             mbar_wait(&w_empty[ws], wphase ^ 1);
-                            mbar_expect_tx(&w_full[ws], W_BLK);
-                            tma_load_2d(smW + ws * W_BLK, &tmW, &w_full[ws], cb * BK, tap * p.N);
+                            mbar_expect_tx_elect(&w_full[ws], W_BLK);
+                            tma_load_2d_elect(smW + ws * W_BLK, &tmW, &w_full[ws], cb * BK, tap * p.N);
                             if (++ws == cfg.w_stages) { ws = 0; wphase ^= 1; }
                         }
                 }
@@ -140,7 +140,8 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ======================= MMA issuer =======================
-        if (lane == 0) {
+        {
+            const uint32_t tmem_u = make_uniform(tmem_base);
             // The issuing thread is a single lane: every integer instruction on its path delays the next
             // tcgen05.mma.  With the tap count a template parameter the loops unroll completely, all
             // descriptor offsets fold into immediates / one IADD each, and the tensor pipe stays fed.
@@ -158,7 +159,7 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&tempty[abuf], aphase ^ 1);
                 mbar_wait(&a_full[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(abuf * BN);
+                const uint32_t d_tmem = tmem_u + (uint32_t)(abuf * BN);
                 const uint32_t a_lo0 = ((smem_u32(smA + stage * a_stage) >> 4) & 0x3FFF) | (1u << 16);
                 if (wres) {
 #pragma unroll
@@ -169,8 +170,8 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             const uint32_t w_lo = w_lo0 + (uint32_t)(((tap * CB + cb) * W_BLK) >> 4);
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k)
-                                umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | (a_lo + 2 * k), ((uint64_t)DESC_HI << 32) | (w_lo + 2 * k),
-                                         idesc, (tap | cb | k) ? 1u : 0u);
+                                umma_f16_pred(d_tmem, ((uint64_t)DESC_HI << 32) | (a_lo + 2 * k), ((uint64_t)DESC_HI << 32) | (w_lo + 2 * k),
+                                         idesc, (tap | cb | k) ? 1u : 0u, 0u);
                         }
                     }
                 } else {
@@ -184,15 +185,15 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             const uint32_t w_lo = w_lo0 + (uint32_t)((ws * W_BLK) >> 4);
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k)
-                                umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | (a_lo + 2 * k), ((uint64_t)DESC_HI << 32) | (w_lo + 2 * k),
-                                         idesc, (tap | cb | k) ? 1u : 0u);
-                            umma_commit(&w_empty[ws]);
+                                umma_f16_pred(d_tmem, ((uint64_t)DESC_HI << 32) | (a_lo + 2 * k), ((uint64_t)DESC_HI << 32) | (w_lo + 2 * k),
+                                         idesc, (tap | cb | k) ? 1u : 0u, 0u);
+                            umma_commit_pred(&w_empty[ws], 0u);
                             if (++ws == cfg.w_stages) { ws = 0; wphase ^= 1; }
                         }
                     }
                 }
-                umma_commit(&a_empty[stage]);
-                umma_commit(&tfull[abuf]);
+                umma_commit_pred(&a_empty[stage], 0u);
+                umma_commit_pred(&tfull[abuf], 0u);
                 if (++stage == cfg.a_stages) { stage = 0; phase ^= 1; }
                 abuf ^= 1; if (abuf == 0) aphase ^= 1;
             }

@@ -14,8 +14,9 @@
 //     inverted exactly in the epilogue), the output is staged in the TMA box layout and TMA-stored.
 // HBM traffic per iteration: read y once (+halo), write y' once.
 //
-// Pipelining: the single MMA-issuing lane alternates conv1(i+1) / conv2(i); the epilogue warps
-// alternate epilogue1(i+1) / epilogue2(i); accumulators and the t tile are double-buffered.
+// Pipelining: the MMA-issuing warp alternates conv1(i+1) / conv2(i); epilogue 1 (TMEM -> t tile) and
+// epilogue 2 (output) run on separate warp quartets concurrently; accumulators and the t tile are
+// double-buffered.
 // Both weight sets stay resident in shared memory for the whole persistent loop.
 #include "umma_common.cuh"
 
@@ -31,7 +32,7 @@ struct RbCfg {
 };
 
 template <int C, int TAPS>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                      const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmO,
                      const __grid_constant__ CUtensorMap tmOtail, const UmmaResblockParams p, const RbCfg cfg) {
@@ -92,12 +93,12 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
     if (warp == 0) {
         // ======================= producer: resident weights, then one halo tile per output tile =======
-        if (lane == 0) {
+        {
             prefetch_tmap(&tmA); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2);
-            mbar_expect_tx(&w_full[0], (uint32_t)(2 * TAPS * W_BLK));
+            mbar_expect_tx_elect(&w_full[0], (uint32_t)(2 * TAPS * W_BLK));
             for (int tap = 0; tap < TAPS; ++tap) {
-                tma_load_2d(smW1 + tap * W_BLK, &tmW1, &w_full[0], 0, tap * C);
-                tma_load_2d(smW2 + tap * W_BLK, &tmW2, &w_full[0], 0, tap * C);
+                tma_load_2d_elect(smW1 + tap * W_BLK, &tmW1, &w_full[0], 0, tap * C);
+                tma_load_2d_elect(smW2 + tap * W_BLK, &tmW2, &w_full[0], 0, tap * C);
             }
             int stage = 0; uint32_t phase = 0;
             const uint32_t bytes = (uint32_t)(cfg.box_rows * ROW_BYTES);
@@ -105,14 +106,17 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const int mt = tile % cfg.m_tiles, b = tile / cfg.m_tiles;
                 const int row0 = mt * cfg.valid - P2 - p1d;          // first input row of the halo tile
                 mbar_wait(&a_empty[stage], phase ^ 1);
-                mbar_expect_tx(&a_full[stage], bytes);
-                tma_load_3d(smA + stage * a_alloc, &tmA, &a_full[stage], 0, row0, b);
+                mbar_expect_tx_elect(&a_full[stage], bytes);
+                tma_load_3d_elect(smA + stage * a_alloc, &tmA, &a_full[stage], 0, row0, b);
                 if (++stage == cfg.a_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ======================= MMA issuer =======================
-        if (lane == 0) {
+        {
+            // the whole warp runs this loop convergently; one lane's tcgen05 instructions are predicated on
+            const uint32_t issue = 0;
+            const uint32_t tmem_u = make_uniform(tmem_base);
             const uint32_t idesc = make_idesc(BM, C);
             const uint32_t tap_step1 = (uint32_t)((p.dil * ROW_BYTES) >> 4);
             constexpr uint32_t tap_step2 = (uint32_t)(ROW_BYTES >> 4);
@@ -127,35 +131,35 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 mbar_wait(&t_full[bb], ph);
                 mbar_wait(&acc2_empty[bb], ph ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(2 * C + bb * C);
+                const uint32_t d_tmem = tmem_u + (uint32_t)(2 * C + bb * C);
                 const uint32_t t_lo = ((smem_u32(smT + bb * T_ALLOC) >> 4) & 0x3FFF) | (1u << 16);
 #pragma unroll
                 for (int tap = 0; tap < TAPS; ++tap) {
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | (t_lo + tap * tap_step2 + 2 * k),
+                        umma_f16_pred(d_tmem, ((uint64_t)DESC_HI << 32) | (t_lo + tap * tap_step2 + 2 * k),
                                  ((uint64_t)DESC_HI << 32) | (w2_lo + (uint32_t)((tap * W_BLK) >> 4) + 2 * k), idesc,
-                                 (tap | k) ? 1u : 0u);
+                                 (tap | k) ? 1u : 0u, issue);
                 }
-                umma_commit(&t_empty[bb]);
-                umma_commit(&acc2_full[bb]);
+                umma_commit_pred(&t_empty[bb], issue);
+                umma_commit_pred(&acc2_full[bb], issue);
             };
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
                 const int bb = it & 1; const uint32_t ph = (uint32_t)((it >> 1) & 1);
                 mbar_wait(&acc1_empty[bb], ph ^ 1);
                 mbar_wait(&a_full[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(bb * C);
+                const uint32_t d_tmem = tmem_u + (uint32_t)(bb * C);
                 const uint32_t a_lo = ((smem_u32(smA + stage * a_alloc) >> 4) & 0x3FFF) | (1u << 16);
 #pragma unroll
                 for (int tap = 0; tap < TAPS; ++tap) {
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | (a_lo + tap * tap_step1 + 2 * k),
+                        umma_f16_pred(d_tmem, ((uint64_t)DESC_HI << 32) | (a_lo + tap * tap_step1 + 2 * k),
                                  ((uint64_t)DESC_HI << 32) | (w1_lo + (uint32_t)((tap * W_BLK) >> 4) + 2 * k), idesc,
-                                 (tap | k) ? 1u : 0u);
+                                 (tap | k) ? 1u : 0u, issue);
                 }
-                umma_commit(&acc1_full[bb]);
+                umma_commit_pred(&acc1_full[bb], issue);
                 if (++stage == cfg.a_stages) { stage = 0; phase ^= 1; }
                 if (it > 0) conv2(it - 1);
             }
@@ -169,12 +173,15 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
         int it = 0;
         int e2_stage = 0;                                                   // A stage of the tile epilogue2 handles next
-        int prev_mt = 0, prev_b = 0;
 
         auto epilogue2 = [&](int j, int mt, int b) {
             const int bb = j & 1; const uint32_t ph = (uint32_t)((j >> 1) & 1);
             const int o = mt * cfg.valid + row;                             // output row of this thread
             const bool valid = row < cfg.valid && o < p.L;
+            // conv2(j) complete  =>  conv1(j) complete  =>  this tile's input stage is loaded and no longer
+            // needed by the tensor core; only now may it be read (residual) and handed back to the producer
+            mbar_wait(&acc2_full[bb], ph);
+            tc_fence_after();
             // residual: lrelu(y) sits in the input halo tile at row (row + P2 + p1d)
             uint4 rres[C / 8];
             {
@@ -185,10 +192,8 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 for (int i = 0; i < C / 8; ++i) rres[i] = *reinterpret_cast<const uint4*>(rb + ((i ^ swa) << 4));
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&a_empty[e2_stage]);                 // (conv1 of this tile finished long ago)
+            if (lane == 0) mbar_arrive(&a_empty[e2_stage]);
             if (++e2_stage == cfg.a_stages) e2_stage = 0;
-            mbar_wait(&acc2_full[bb], ph);
-            tc_fence_after();
             if (lane == 0) tma_store_wait_read();
             __syncwarp();
             const uint32_t taddr = tmem_base + (uint32_t)(2 * C + bb * C) + lane_addr;
@@ -241,10 +246,11 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
         };
 
+        const bool is_e1 = warp < 8;      // warps 4-7: epilogue 1 (conv1 -> t tile); warps 8-11: epilogue 2 (output)
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
             const int mt = tile % cfg.m_tiles, b = tile / cfg.m_tiles;
             // ---- epilogue 1: t = lrelu(c1 + b1) -> fp16 swizzled smem tile (zeros outside the utterance)
-            {
+            if (is_e1) {
                 const int bb = it & 1; const uint32_t ph = (uint32_t)((it >> 1) & 1);
                 mbar_wait(&acc1_full[bb], ph);
                 mbar_wait(&t_empty[bb], ph ^ 1);
@@ -279,12 +285,10 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&acc1_empty[bb]); mbar_arrive(&t_full[bb]); }
             }
-            // ---- epilogue 2 of the previous tile
-            if (it > 0) epilogue2(it - 1, prev_mt, prev_b);
-            prev_mt = mt; prev_b = b;
+            // ---- epilogue 2 (its own warps, running concurrently with epilogue 1 of later tiles)
+            if (!is_e1) epilogue2(it, mt, b);
         }
-        if (it > 0) epilogue2(it - 1, prev_mt, prev_b);
-        if (lane == 0) tma_store_wait_all();
+        if (!is_e1 && lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -340,7 +344,7 @@ int launch_rb_cfg(const UmmaResblockParams& p, cudaStream_t s) {
     }
     const int tiles = p.B * cfg.m_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, 256, smem, s>>>(a_map, w1_map, w2_map, o_map, ot_map, p, cfg);
+    kern<<<grid, 384, smem, s>>>(a_map, w1_map, w2_map, o_map, ot_map, p, cfg);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }
