@@ -41,9 +41,9 @@ def parse():
     ap.add_argument("--src-hi", type=int, default=115)
     ap.add_argument("--cpu-sample", type=int, default=6, help="utterances in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tc-frontend", action="store_true",
-                    help="also run the encoder / variance-adaptor GEMMs on the hi/lo tensor-core kernel (off by default: "
-                         "their outputs feed the duration / energy / pitch quantisers)")
+    ap.add_argument("--ffma-frontend", action="store_true",
+                    help="run the encoder / variance-adaptor GEMMs on the fp32 FFMA kernels instead of the hi/lo "
+                         "tensor-core kernel")
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
                     help="tc: tcgen05 tensor cores (fp16 operands, fp32 accumulate; hi/lo pairs in the denoiser); fp32: FFMA yardstick")
     return ap.parse_args()
@@ -206,7 +206,7 @@ def main():
     from cmtts_b200.synthesize import Pipeline
 
     lib = _lib.load()
-    pipe = Pipeline(spec, sd, hifigan_sd, dev, precision=args.precision, tc_frontend=args.tc_frontend)
+    pipe = Pipeline(spec, sd, hifigan_sd, dev, precision=args.precision, tc_frontend=not args.ffma_frontend)
     synth = ShardedSynthesizer(pipe, dist if world > 1 else None)
     # per-rank shard of the global synthetic batch (weak scaling: args.batch utterances per GPU)
     gb = synthetic.make_batch(spec, args.batch * world, args.src_lo, args.src_hi, seed=1234)

@@ -38,7 +38,13 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     constexpr int NOP = SPLIT ? 2 : 1;
     constexpr int STAGE_BYTES = NOP * (A_BYTES + B_BYTES);
-    constexpr int TMEM_COLS = pow2_cols(2 * BN);
+    // SPLIT: the two small cross terms (A_hi W_lo + A_lo W_hi, ~2^-11 of the main term) get their OWN
+    // accumulator.  tcgen05 accumulates in fp32 with truncation, an error of ~1 ulp of the running sum per
+    // MMA that grows linearly with the number of accumulation steps (measured: 5.7e-6 / 1.5e-5 / 4.5e-5 for
+    // K = 256 / 768 / 2304 with all three products in one accumulator); keeping the cross terms out of the
+    // main chain cuts the steps on the full-magnitude sum by 3x.
+    constexpr int ACC_COLS = SPLIT ? 2 * BN : BN;     // TMEM columns per accumulator buffer
+    constexpr int TMEM_COLS = pow2_cols(2 * ACC_COLS);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -104,7 +110,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
                 mbar_wait(&tempty[abuf], aphase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_u + (uint32_t)(abuf * BN);
+                const uint32_t d_tmem = tmem_u + (uint32_t)(abuf * ACC_COLS);
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
@@ -117,8 +123,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 x 16B units along K
                         umma_f16_pred(d_tmem, a0 + adv, b0 + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u, 0u);
                         if (SPLIT) {
-                            umma_f16_pred(d_tmem, a0 + adv, b1 + adv, idesc, 1u, 0u);
-                            umma_f16_pred(d_tmem, a1 + adv, b0 + adv, idesc, 1u, 0u);
+                            umma_f16_pred(d_tmem + BN, a0 + adv, b1 + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u, 0u);
+                            umma_f16_pred(d_tmem + BN, a1 + adv, b0 + adv, idesc, 1u, 0u);
                         }
                     }
                     umma_commit_pred(&empty[stage], 0u);   // frees the smem slot once these MMAs have read it
@@ -170,18 +176,25 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
             mbar_wait(&tfull[abuf], aphase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (uint32_t)(abuf * BN) + ((uint32_t)(q * 32) << 16);
+            const uint32_t taddr = tmem_base + (uint32_t)(abuf * ACC_COLS) + ((uint32_t)(q * 32) << 16);
 
             if (SPLIT && p.epi == UEPI_DN_GATE) {
                 // tile columns [0, BN/2) are gates, [BN/2, BN) the matching filters (weights.py gate_permutation)
                 constexpr int GH = BN / 4;                        // gate columns per column-half
 #pragma unroll
                 for (int c = 0; c < GH / 16; ++c) {
-                    uint32_t rg[16], rf[16];
+                    uint32_t rg[16], rf[16], rg2[16], rf2[16];
                     const int g0 = h * GH + c * 16;
                     tmem_ld16(taddr + g0, rg);
                     tmem_ld16(taddr + BN / 2 + g0, rf);
+                    tmem_ld16(taddr + BN + g0, rg2);               // cross-term accumulator
+                    tmem_ld16(taddr + BN + BN / 2 + g0, rf2);
                     tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        rg[j] = __float_as_uint(__uint_as_float(rg[j]) + __uint_as_float(rg2[j]));
+                        rf[j] = __float_as_uint(__uint_as_float(rf[j]) + __uint_as_float(rf2[j]));
+                    }
                     if (valid) {
                         const int ng = nt * BN + g0, nf = ng + BN / 2;
                         const int ch = nt * (BN / 2) + g0;
@@ -201,7 +214,15 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 for (int c = 0; c < BNH / 16; ++c) {
                     uint32_t r[16];
                     tmem_ld16(taddr + h * BNH + c * 16, r);
-                    tmem_ld_wait();
+                    if constexpr (SPLIT) {
+                        uint32_t r2[16];
+                        tmem_ld16(taddr + BN + h * BNH + c * 16, r2);   // cross-term accumulator
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+                    } else {
+                        tmem_ld_wait();
+                    }
                     if (!valid) continue;
                     const int n = n0 + c * 16;
                     float v[16];

@@ -73,11 +73,13 @@ class CMTotalTTS:
         if precision not in self.PRECISIONS:
             raise ValueError(f"precision must be one of {self.PRECISIONS}")
         self.precision = precision
-        # Encoder + variance-adaptor GEMMs can also run on the hi/lo tensor-core kernel (1.6 ms faster per
-        # C2 batch), but tcgen05's fp32 accumulation is not IEEE round-to-nearest: over K = 2304 the
-        # encoder output differs from the reference by ~1e-5 instead of ~2e-6 (FFMA), which makes a
-        # duration / energy / pitch quantiser flip ~5x more likely.  Parity first: off by default.
-        self.tc_frontend = False
+        # Encoder + variance-adaptor GEMMs on the hi/lo tensor-core kernel when precision == "tc".  These
+        # stages feed the duration / energy / pitch quantisers, so accuracy matters: tcgen05 accumulates
+        # in fp32 with truncation (error grows with the number of accumulation steps), which is why the
+        # kernel keeps the hi/lo cross terms in their own accumulator.  Measured against the reference:
+        # log_d 1.4-1.9e-6 (FFMA 1.1-1.2e-6), energy 1.0e-5 (6e-6), cwt 6.9e-6 (5.2e-6).  Set False to
+        # run them on the fp32 FFMA kernels (4 ms slower per C2 batch).
+        self.tc_frontend = True
         self.spec = spec
         self.device = torch.device("cpu")
         self._sd: Optional[Dict[str, torch.Tensor]] = None

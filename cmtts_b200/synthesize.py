@@ -106,7 +106,7 @@ class Pipeline:
     HiFi-GAN on the whole padded batch, x32768 -> int16, crop to mel_len * hop)."""
 
     def __init__(self, spec: ModelSpec, acoustic_sd: Dict[str, torch.Tensor], hifigan_sd: Dict[str, torch.Tensor],
-                 device, distillation: bool = True, precision: str = "tc", tc_frontend: bool = False):
+                 device, distillation: bool = True, precision: str = "tc", tc_frontend: bool = True):
         self.spec = spec
         self.precision = precision
         self.device = torch.device(device)

@@ -32,6 +32,7 @@ def main():
         with torch.no_grad():
             ref = O.dpen(W, spec, **batch)
         m = CMTotalTTS(spec=spec, precision=prec).load_state_dict(sd).to(DEV)
+        m.tc_frontend = os.environ.get("CMTTS_TC_FRONTEND", "0") == "1"
         out = m.dpen(batch["texts"], batch["src_lens"], batch["spker_embeds"])
         torch.cuda.synchronize()
         print(f"== {ds} B={B} L={ref['cond'].shape[1]}")
@@ -80,7 +81,7 @@ def main():
         snr = 10 * torch.log10(ref.pow(2).mean() / d.pow(2).mean())
         print(f"== hifigan synthetic (B={B}, L={L}): wav max err {err(wav, ref):.3e} rms err {float(d.pow(2).mean().sqrt()):.3e} "
               f"|wav|max {float(ref.abs().max()):.3f} SNR {float(snr):.1f} dB")
-    import os
+    pass
     real = os.path.join(ROOT, "oracle", "_ref", "hifigan", "generator_universal.pth.tar")
     if os.path.isfile(real):
         sd = torch.load(real, map_location="cpu", weights_only=True)["generator"]

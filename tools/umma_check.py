@@ -161,6 +161,31 @@ def case_time(B, L, Cc, k, dil, res=False, reps=20):
     print(f"time B={B} L={L} C={Cc} k={k} dil={dil} res={res}: {ms*1e3:8.1f} us  {flops/ms/1e9:7.1f} TFLOP/s  {byts/ms/1e6:7.1f} GB/s (algorithmic)", flush=True)
 
 
+def case_accum():
+    """How accurate is the hi/lo tensor-core GEMM over a long K (tcgen05 fp32 accumulation) vs fp32 FFMA?"""
+    import ctypes as C
+    g = torch.Generator().manual_seed(11)
+    for taps in (1, 3, 9):
+        B, L, Cc, N = 2, 256, 256, 256
+        a = torch.randn(B, L, Cc, generator=g)
+        w = torch.randn(taps, N, Cc, generator=g) / (Cc * taps) ** 0.5
+        bias = torch.zeros(N)
+        shifts = [i - (taps - 1) // 2 for i in range(taps)]
+        ref = ref_conv(a.double(), w.double(), bias.double(), shifts)
+        ah, al = split(a); wh, wl = wsplit(w.reshape(taps * N, Cc))
+        # generic fp32 epilogue (epi 4) is not exposed through umma(); use DN_COND with zero x / addvec
+        zx = torch.zeros(B, L, N, device=DEV); zv = torch.zeros(B, N, device=DEV)
+        yh, yl = umma(ah.to(DEV), wh.to(DEV), bias.to(DEV), shifts, N, a_lo=al.to(DEV), w_lo=wl.to(DEV), epi=1, out_lo=True,
+                      addvec=zv, x_f32=zx, alpha=W_INV)
+        got = yh.double().cpu() + yl.double().cpu()
+        # exact product of the rounded operands (isolates accumulation error from operand rounding)
+        a_r = ah.double() + al.double(); w_r = (wh.double() + wl.double()).reshape(taps, N, Cc) / 1024.0
+        ref_r = ref_conv(a_r, w_r, bias.double(), shifts)
+        ref32 = ref_conv(a, w, bias, shifts)
+        print(f"accum taps={taps} K={taps*Cc}: tc vs fp64 {(got-ref).abs().max():.3e} | tc vs exact-of-rounded-operands {(got-ref_r).abs().max():.3e}"
+              f" | operand rounding alone {(ref_r-ref).abs().max():.3e} | torch fp32 vs fp64 {(ref32.double()-ref).abs().max():.3e} | hi/lo output quantisation ~{float(ref.abs().max())*2**-22:.1e}", flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "plain"):
@@ -188,3 +213,5 @@ if __name__ == "__main__":
             case_time(32, 6400, 256, 7, 1, res)
     if which in ("all", "split"):
         case_split2()
+    if which in ("accum",):
+        case_accum()
