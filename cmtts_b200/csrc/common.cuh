@@ -94,6 +94,8 @@ int launch_length_regulate(const float* x, const long long* cumsum, const long l
 int launch_attention(const float* qkv, const long long* src_lens, float* out, int B, int T, int C,
                      int heads, cudaStream_t s);
 int launch_mish(float* x, long long n, cudaStream_t s);
+int launch_dn_fuse_steps(const float* ds_all, const float* dsp_all, float* yc, int B, int layers, int C, float r,
+                         cudaStream_t s);
 int launch_renoise(const float* x0, const float* noise, float s1, float s2, float* out, long long n,
                    cudaStream_t s);
 int launch_scale(const float* x, float a, float* out, long long n, cudaStream_t s);

@@ -560,16 +560,24 @@ extern "C" int cmtts_f32_to_f16(const float* x, void* hi, void* lo, int64_t rows
 
 extern "C" size_t cmtts_denoiser_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t L) {
     const size_t n = (size_t)B * L * d->res_channels;
-    return align_up(n * 4) * 3 + align_up(n * 2) * 4 + align_up((size_t)B * L * 128 * 2) * 2;
+    return align_up(n * 4) * 3 + align_up(n * 2) * 4 + align_up((size_t)B * L * 128 * 2) * 2 +
+           align_up((size_t)B * d->res_layers * d->res_channels * 4);
 }
 
+// The residual stack as a recurrence in y_l = x_l + c_l, with c_l = Wc_l cond + bc_l + step_l[b] + spk_l[b]
+// (what the k=3 conv consumes, blocks.py:669-678).  With r = 1/sqrt(2) and x_{l+1} = r (Wo_l[:C] g_l + bo_l +
+// step_l[b] + x_l) (blocks.py:676, :683-686):
+//     y_{l+1} = [r Wo_l[:C] | Wc_{l+1} - r Wc_l] [g_l ; cond]  +  r y_l  +  const_l[b]
+// — ONE GEMM per layer (K = C + H, the "fused" weights of weights.py) instead of the output projection, a
+// separate conditioner projection and two passes over x.  x_l itself is never needed: the stack's result is
+// the skip sum (modules.py:629-637).  Same algebra as the reference, different rounding order (fp32-class).
 extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const* w, const void* const* w16,
                                          const float* x_t, const void* cond_hi, const void* cond_lo,
                                          const float* ds_all, const float* dsp_all, float c_in, float c_out,
                                          float c_skip, int64_t B_, int64_t L_, float* out, float* model_out,
                                          void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    const int B = (int)B_, L = (int)L_, C = d->res_channels, M = d->n_mels, H = d->hidden;
+    const int B = (int)B_, L = (int)L_, C = d->res_channels, M = d->n_mels, H = d->hidden, NLY = d->res_layers;
     CMTTS_REQUIRE(ws_bytes >= cmtts_denoiser_tc_workspace_bytes(d, B_, L_), "denoiser_tc: workspace too small");
     CMTTS_REQUIRE(C % 128 == 0 && H % 64 == 0, "denoiser_tc: channel counts must suit the 128x128x64 UMMA tiling");
     if (B == 0 || L == 0) return CMTTS_OK;
@@ -584,11 +592,15 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
     __half* g_lo = cv.take<__half>(n * C);
     __half* xt_hi = cv.take<__half>(n * 128);
     __half* xt_lo = cv.take<__half>(n * 128);
-    const long long NL = (long long)d->res_layers * C;
+    float* yc = cv.take<float>((size_t)B * NLY * C);
+    const long long NL = (long long)NLY * C;
     const long long bs = (long long)L * C;
-    const void* const* wx = w16 + d->res_layers * 7;   // {in_w hi, lo [C][128]; skip_w hi, lo [C][C]}
+    const void* const* wx = w16 + NLY * 7;              // {in_w hi, lo [C][128]; skip_w hi, lo [C][C]}
+    const void* const* wf = wx + 4;                     // per layer l < NLY-1: {fused_w hi, lo [2C][C+H]; fused_b [2C]}
+    const float r = (float)(1.0 / sqrt(2.0));
     CMTTS_REQUIRE(M <= 128, "denoiser_tc: n_mels must be <= 128");
 
+    CMTTS_TRY(launch_dn_fuse_steps(ds_all, dsp_all, yc, B, NLY, C, r, s));
     // input projection: relu(W (c_in x_t) + b), x_t zero-padded to 128 channels as an fp16 hi/lo pair
     CMTTS_TRY(launch_f32_to_f16(x_t, xt_hi, xt_lo, (long long)n, M, 128, 1.f, s));
     {
@@ -597,23 +609,25 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
         tc_out32(u, x, L, C);
         CMTTS_TRY(launch_umma_conv(u, s));
     }
-    ConvParams p;
-    for (int l = 0; l < d->res_layers; ++l) {
-        const void* const* wl = w16 + l * 7;
-        const int o = CMTTS_DN_LAYER0 + l * CMTTS_DN_PER_LAYER;
+    {
+        // y_0 = Wc_0 cond + bc_0 + (step + speaker)_0[b] + x_0                blocks.py:669-678
         UmmaConvParams u = umma_params_default();
-        // (a) y = Wc cond + bc + (step + speaker)[b] + x                    blocks.py:669-678
         u.B = B; u.M = L; u.Lin = L; u.N = C; u.Cin = H; u.taps = 1; u.shift[0] = 0; u.split = 1; u.epi = UEPI_DN_COND;
         u.alpha = TC_W_SCALE_INV;
         u.a_hi = (const __half*)cond_hi; u.a_lo = (const __half*)cond_lo; u.a_bstride = (long long)L * H; u.a_ld = H;
-        u.w_hi = (const __half*)wl[0]; u.w_lo = (const __half*)wl[1];
-        u.bias = F(w, o + 1);
-        u.addvec = dsp_all + (long long)l * C; u.addvec_bstride = NL;
+        u.w_hi = (const __half*)w16[0]; u.w_lo = (const __half*)w16[1];
+        u.bias = F(w, CMTTS_DN_LAYER0 + 1);
+        u.addvec = dsp_all; u.addvec_bstride = NL;
         u.x_f32 = x; u.x_bstride = bs; u.x_ld = C;
         u.out_h = y_hi; u.out_lo = y_lo; u.out_bstride = bs; u.out_ld = C;
         CMTTS_TRY(launch_umma_conv(u, s));
-        // (b) g = sigmoid(gate) * tanh(filter) of the k=3 conv               blocks.py:677-681
-        u = umma_params_default();
+    }
+    ConvParams p;
+    for (int l = 0; l < NLY; ++l) {
+        const void* const* wl = w16 + l * 7;
+        const int o = CMTTS_DN_LAYER0 + l * CMTTS_DN_PER_LAYER;
+        // g = sigmoid(gate) * tanh(filter) of the k=3 conv of y_l              blocks.py:677-681
+        UmmaConvParams u = umma_params_default();
         u.B = B; u.M = L; u.Lin = L; u.N = 2 * C; u.Cin = C; u.taps = 3; u.shift[0] = -1; u.shift[1] = 0; u.shift[2] = 1;
         u.split = 1; u.epi = UEPI_DN_GATE; u.alpha = TC_W_SCALE_INV;
         u.a_hi = y_hi; u.a_lo = y_lo; u.a_bstride = bs; u.a_ld = C;
@@ -621,25 +635,36 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
         u.bias = F(w, o + 3);
         u.out_h = g_hi; u.out_lo = g_lo; u.out_bstride = bs; u.out_ld = C;
         CMTTS_TRY(launch_umma_conv(u, s));
-        // (c) x = (Wo[:C] g + b + step[b] + x) / sqrt(2) ; skip (+)= Wo[C:] g + b     blocks.py:676, :683-686
-        u = umma_params_default();
-        u.B = B; u.M = L; u.Lin = L; u.N = 2 * C; u.Cin = C; u.taps = 1; u.shift[0] = 0; u.split = 1; u.epi = UEPI_DN_OUT;
-        u.alpha = TC_W_SCALE_INV;
-        u.a_hi = g_hi; u.a_lo = g_lo; u.a_bstride = bs; u.a_ld = C;
-        u.w_hi = (const __half*)wl[4]; u.w_lo = (const __half*)wl[5];
-        u.bias = (const float*)wl[6];
-        u.addvec = ds_all + (long long)l * C; u.addvec_bstride = NL;
-        u.x_f32 = x; u.x_bstride = bs; u.x_ld = C;
-        u.skip_f32 = skip; u.skip_accumulate = (l > 0);
-        u.out_scale = (float)(1.0 / sqrt(2.0));
-        CMTTS_TRY(launch_umma_conv(u, s));
+        if (l + 1 < NLY) {
+            // y_{l+1} (in place) and skip (+)= Wo_l[C:] g + b : one launch, see the recurrence above
+            u = umma_params_default();
+            u.B = B; u.M = L; u.Lin = L; u.N = 2 * C; u.Cin = C; u.taps = 1; u.shift[0] = 0; u.split = 1; u.epi = UEPI_DN_OUTY;
+            u.alpha = TC_W_SCALE_INV;
+            u.a_hi = g_hi; u.a_lo = g_lo; u.a_bstride = bs; u.a_ld = C;
+            u.a2_hi = (const __half*)cond_hi; u.a2_lo = (const __half*)cond_lo; u.a2_bstride = (long long)L * H; u.a2_ld = H;
+            u.Cin2 = H; u.n_k2 = C;
+            u.w_hi = (const __half*)wf[3 * l]; u.w_lo = (const __half*)wf[3 * l + 1];
+            u.bias = (const float*)wf[3 * l + 2];
+            u.addvec = yc + (long long)l * C; u.addvec_bstride = (long long)(NLY - 1) * C;
+            u.out_h = y_hi; u.out_lo = y_lo; u.out_bstride = bs; u.out_ld = C;
+            u.skip_f32 = skip; u.x_bstride = bs; u.x_ld = C; u.skip_accumulate = (l > 0);
+            u.out_scale = r;
+            CMTTS_TRY(launch_umma_conv(u, s));
+        } else {
+            // last layer: only the skip half of the output projection is used (modules.py:629-634)
+            u = tc_same(HL{g_hi, g_lo}, B, L, C, (const __half*)wl[4] + (size_t)C * C, (const __half*)wl[5] + (size_t)C * C,
+                        (const float*)wl[6] + C, C, 1, 1);
+            if (l > 0) tc_res(u, skip, L, C);
+            tc_out32(u, skip, L, C);
+            CMTTS_TRY(launch_umma_conv(u, s));
+        }
     }
-    const int o = CMTTS_DN_LAYER0 + d->res_layers * CMTTS_DN_PER_LAYER;
+    const int o = CMTTS_DN_LAYER0 + NLY * CMTTS_DN_PER_LAYER;
     // skip projection: relu(W (sum skip / sqrt(n_layers)) + b) on the hi/lo kernel (y/g buffers are free now)
     CMTTS_TRY(to_hl(skip, HL{y_hi, y_lo}, (long long)n, C, s));
     {
         UmmaConvParams u = tc_same(HL{y_hi, y_lo}, B, L, C, wx[2], wx[3], F(w, o + 1), C, 1, 1);
-        u.alpha = (float)(1.0 / sqrt((double)d->res_layers)) * TC_W_SCALE_INV; u.act = ACT_RELU;
+        u.alpha = (float)(1.0 / sqrt((double)NLY)) * TC_W_SCALE_INV; u.act = ACT_RELU;
         tc_out32(u, v, L, C);
         CMTTS_TRY(launch_umma_conv(u, s));
     }
@@ -676,11 +701,23 @@ extern "C" int cmtts_hifigan_forward_tc(const int32_t* cfg, const void* const* w
     float* pre32 = cv.take<float>((size_t)B * L * c.C0);
 
     int wi = 0;
-    // conv_pre on the fp32 path (K = 7 x 80, 0.1 % of the FLOPs) -> fp16 lrelu(x)
-    ConvParams p = conv_same(mel, B, L, 80, F(w, wi), F(w, wi + 1), c.C0, c.pre_k, 1, pre32);
-    p.out_h = xs; p.out_h_slope = 0.1f;
+    // conv_pre (hifigan/models.py:150) -> fp16 lrelu(x).  The raw log-mel input spans +-11, too coarse for a single
+    // fp16 pass, so it runs on the hi/lo kernel (fp32-class products; K = 7 taps x 80 mels zero-padded to 128):
+    // w16[n_entries-2, n_entries-1] = {pre_w hi, lo [7][C0][128]} (weights.py), input split into the pre32 scratch.
+    {
+        int n_entries = 2;
+        for (int i = 0; i < c.n_levels; ++i) n_entries += 2 + 4 * c.n_kernels * c.n_dil;
+        n_entries += 2;                                   // conv_post
+        CMTTS_REQUIRE((size_t)c.C0 * 4 >= 2 * 128 * 2, "hifigan_tc: scratch too small for the mel hi/lo pair");
+        __half* m_hi = reinterpret_cast<__half*>(pre32);
+        __half* m_lo = m_hi + (size_t)B * L * 128;
+        CMTTS_TRY(launch_f32_to_f16(mel, m_hi, m_lo, (long long)B * L, 80, 128, 1.f, s));
+        UmmaConvParams u = tc_same(HL{m_hi, m_lo}, B, L, 128, w[n_entries], w[n_entries + 1], F(w, wi + 1), c.C0, c.pre_k, 1);
+        u.act = ACT_LRELU; u.out_slope = 0.1f;
+        u.out_h = xs; u.out_lo = nullptr; u.out_bstride = (long long)L * c.C0; u.out_ld = c.C0;
+        CMTTS_TRY(launch_umma_conv(u, s));
+    }
     wi += 2;
-    CMTTS_TRY(launch_conv1d_simt(p, s));
     int ch = c.C0, len = L;
     const float inv_nk = 1.0f / (float)c.n_kernels;
     static int fuse_env = -1;

@@ -392,6 +392,19 @@ __global__ void renoise_kernel(const float4* __restrict__ x0, const float4* __re
     out[i] = r;
 }
 
+// per-(utterance, layer) additive constants of the denoiser's y-recurrence (pipeline.cu, cmtts_denoiser_forward_tc):
+//   yc[b][l][n] = r * ds[b][l][n] + dsp[b][l+1][n] - r * dsp[b][l][n],  l < layers - 1
+__global__ void dn_fuse_steps_kernel(const float* __restrict__ ds, const float* __restrict__ dsp, float* __restrict__ yc,
+                                     int layers, int C, float r, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int per_b = (layers - 1) * C;
+    const long long b = i / per_b;
+    const int j = (int)(i - b * per_b);                 // l * C + n
+    const long long src = b * (long long)layers * C + j;
+    yc[i] = r * ds[src] + dsp[src + C] - r * dsp[src];
+}
+
 __global__ void scale_kernel(const float4* __restrict__ x, float a, float4* __restrict__ out, long long n4) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
@@ -595,6 +608,15 @@ int launch_renoise(const float* x0, const float* noise, float s1, float s2, floa
     CMTTS_REQUIRE(n % 4 == 0, "renoise: n % 4");
     const long long n4 = n / 4;
     renoise_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>((const float4*)x0, (const float4*)noise, s1, s2, (float4*)out, n4);
+    CMTTS_CHECK_LAUNCH();
+    return CMTTS_OK;
+}
+
+int launch_dn_fuse_steps(const float* ds_all, const float* dsp_all, float* yc, int B, int layers, int C, float r,
+                         cudaStream_t s) {
+    const long long n = (long long)B * (layers - 1) * C;
+    if (n <= 0) return CMTTS_OK;
+    dn_fuse_steps_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ds_all, dsp_all, yc, layers, C, r, n);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }

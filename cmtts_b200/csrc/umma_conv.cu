@@ -27,12 +27,64 @@ namespace {
 using namespace umma;
 
 // ------------------------------------------------------------------------------------------
+// static tile schedule, evaluated identically by the three roles of a CTA
+// ------------------------------------------------------------------------------------------
+// Plain launches: tile = blockIdx.x, += gridDim.x (n-tile fastest).  Dual-operand launches have two tile
+// classes — "heavy" (columns < n_k2, K = Cin + Cin2) and "light" (K = Cin) — and a round-robin over one list
+// would hand whole CTAs only heavy or only light tiles (n-tile fastest, gridDim % n_tiles == 0).  Instead:
+// heavy tiles round-robin first (longest-processing-time order), then each CTA takes a contiguous run of
+// light tiles sized to level the k-block totals, then any leftovers round-robin.
+struct TileSched {
+    int n_tiles, m_tiles, heavy_n;      // n-tiles per m-tile; of which heavy
+    int H, Lt;                          // heavy / light tile counts
+    int h_next, l_next, l_end, x_next;  // cursors: heavy round-robin, light run, leftover round-robin
+    int G;
+    __device__ TileSched(const UmmaConvParams& p, int BN, int BK) {
+        G = (int)gridDim.x;
+        const int c = (int)blockIdx.x;
+        m_tiles = (p.M + 127) / 128;
+        n_tiles = p.N / BN;
+        heavy_n = p.a2_hi ? p.n_k2 / BN : 0;
+        const int rows = p.B * m_tiles;
+        H = rows * heavy_n; Lt = rows * (n_tiles - heavy_n);
+        h_next = c;
+        if (heavy_n == 0) { l_next = 0; l_end = 0; x_next = c; return; }
+        const int wl = p.Cin / BK, wh = wl + p.Cin2 / BK;
+        const long long total = (long long)H * wh + (long long)Lt * wl;
+        const int T = (int)((total + G - 1) / G);
+        const int q = H / G, rem = H % G;
+        const int nl_a = max(0, (T - (q + 1) * wh) / wl), nl_b = max(0, (T - q * wh) / wl);
+        const int off = min(c, rem) * nl_a + max(0, c - rem) * nl_b;
+        const int mine = c < rem ? nl_a : nl_b;
+        const int S = min(Lt, rem * nl_a + (G - rem) * nl_b);
+        l_next = min(off, Lt); l_end = min(off + mine, Lt);
+        x_next = S + c;
+    }
+    // next tile of this CTA: n-tile index, (b, m-tile) and whether it contracts over the second operand too
+    __device__ bool next(int& nt, int& mt, int& b, bool& heavy) {
+        int rest;
+        if (h_next < H) { heavy = true; nt = h_next % heavy_n; rest = h_next / heavy_n; h_next += G; }
+        else {
+            int l;
+            if (l_next < l_end) l = l_next++;
+            else if (x_next < Lt) { l = x_next; x_next += G; }
+            else return false;
+            const int ln = n_tiles - heavy_n;
+            heavy = false; nt = heavy_n + l % ln; rest = l / ln;
+        }
+        mt = rest % m_tiles; b = rest / m_tiles;
+        return true;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
 template <int BN, int BK, int SPLIT, int STAGES>
 __global__ void __launch_bounds__(384, 1)
 umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                  const UmmaConvParams p) {
     constexpr int BM = 128;
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
@@ -55,11 +107,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tiles = (p.M + BM - 1) / BM;
-    const int n_tiles = p.N / BN;
-    const int tiles = p.B * m_tiles * n_tiles;
     const int cblocks = p.Cin / BK;
-    const int kblocks = p.taps * cblocks;
+    const int kblocks1 = p.taps * cblocks;                // k-blocks over the first operand
+    const int kblocks2 = SPLIT ? p.Cin2 / BK : 0;         // extra k-blocks of heavy tiles (second operand)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -81,21 +131,32 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         {
             prefetch_tmap(&tmA0); prefetch_tmap(&tmB0);
             if (SPLIT) { prefetch_tmap(&tmA1); prefetch_tmap(&tmB1); }
+            if (SPLIT && p.a2_hi) { prefetch_tmap(&tmA2); prefetch_tmap(&tmA3); }
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                const int nt = tile % n_tiles; const int rest = tile / n_tiles;
-                const int mt = rest % m_tiles; const int b = rest / m_tiles;
+            TileSched ts(p, BN, BK);
+            int nt, mt, b; bool heavy;
+            while (ts.next(nt, mt, b, heavy)) {
+                const int kblocks = kblocks1 + (heavy ? kblocks2 : 0);
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * BK;
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx_elect(&full[stage], STAGE_BYTES);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
-                    const int row = mt * BM + p.shift[tap];
-                    tma_load_3d_elect(sa, &tmA0, &full[stage], c0, row, b);
-                    if (SPLIT) tma_load_3d_elect(sa + A_BYTES, &tmA1, &full[stage], c0, row, b);
                     uint8_t* sb = sa + NOP * A_BYTES;
-                    tma_load_2d_elect(sb, &tmB0, &full[stage], c0, tap * p.N + nt * BN);
-                    if (SPLIT) tma_load_2d_elect(sb + B_BYTES, &tmB1, &full[stage], c0, tap * p.N + nt * BN);
+                    if (!SPLIT || kb < kblocks1) {
+                        const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * BK;
+                        const int row = mt * BM + p.shift[tap];
+                        tma_load_3d_elect(sa, &tmA0, &full[stage], c0, row, b);
+                        if (SPLIT) tma_load_3d_elect(sa + A_BYTES, &tmA1, &full[stage], c0, row, b);
+                        // weights [taps*N][Cin (+ Cin2)]: with a second operand taps == 1 and c0 is also the W column
+                        tma_load_2d_elect(sb, &tmB0, &full[stage], c0, tap * p.N + nt * BN);
+                        if (SPLIT) tma_load_2d_elect(sb + B_BYTES, &tmB1, &full[stage], c0, tap * p.N + nt * BN);
+                    } else {
+                        const int c0 = (kb - kblocks1) * BK;
+                        tma_load_3d_elect(sa, &tmA2, &full[stage], c0, mt * BM, b);
+                        tma_load_3d_elect(sa + A_BYTES, &tmA3, &full[stage], c0, mt * BM, b);
+                        tma_load_2d_elect(sb, &tmB0, &full[stage], p.Cin + c0, nt * BN);
+                        tma_load_2d_elect(sb + B_BYTES, &tmB1, &full[stage], p.Cin + c0, nt * BN);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -107,7 +168,10 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const uint32_t idesc = make_idesc(BM, BN);
             int stage = 0; uint32_t phase = 0;
             int abuf = 0; uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            TileSched ts(p, BN, BK);
+            int nt, mt, b; bool heavy;
+            while (ts.next(nt, mt, b, heavy)) {
+                const int kblocks = kblocks1 + (heavy ? kblocks2 : 0);
                 mbar_wait(&tempty[abuf], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_u + (uint32_t)(abuf * ACC_COLS);
@@ -144,15 +208,34 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int h = (warp - 4) >> 2;
         const int row = q * 32 + lane;
         int abuf = 0; uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-            const int nt = tile % n_tiles; const int rest = tile / n_tiles;
-            const int mt = rest % m_tiles; const int b = rest / m_tiles;
+        TileSched ts(p, BN, BK);
+        int nt, mt, b; bool heavy;
+        while (ts.next(nt, mt, b, heavy)) {
             const int t = mt * BM + row;
             const bool valid = t < p.M;
             const int n0 = nt * BN + h * BNH;                 // first output column of this thread
             uint4 pre[16];
             bool have_pre = false;
             if constexpr (SPLIT) {
+                if (p.epi == UEPI_DN_OUTY) {
+                    // The y / skip segments this thread will read for its NEXT tile usually sit in DRAM (the layer's
+                    // working set exceeds what L2 retains); pull them into L2 one tile ahead so the register
+                    // prefetch below costs an L2 hit instead of a DRAM round trip in front of every epilogue.
+                    TileSched ahead = ts;
+                    int nt2, mt2, b2; bool heavy2;
+                    if (ahead.next(nt2, mt2, b2, heavy2)) {
+                        const int t2 = mt2 * BM + row, m0 = nt2 * BN + h * BNH;
+                        if (t2 < p.M) {
+                            if (m0 < p.n_k2) {
+                                const long long o2 = (long long)b2 * p.out_bstride + (long long)t2 * p.out_ld + m0;
+                                prefetch_l2(p.out_h + o2); prefetch_l2(p.out_lo + o2);
+                            } else if (p.skip_accumulate) {
+                                const float* s2 = p.skip_f32 + (long long)b2 * p.x_bstride + (long long)t2 * p.x_ld + (m0 - p.n_k2);
+                                prefetch_l2(s2); prefetch_l2(s2 + 32);
+                            }
+                        }
+                    }
+                }
                 const float* src = nullptr;
                 if (p.epi == UEPI_DN_COND || (p.epi == UEPI_F32 && p.x_f32 != nullptr && n0 < p.n_valid))
                     src = p.x_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + n0;
@@ -160,11 +243,23 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     const int half_n = p.N >> 1;
                     if (n0 < half_n) src = p.x_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + n0;
                     else if (p.skip_accumulate) src = p.skip_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + (n0 - half_n);
+                } else if (p.epi == UEPI_DN_OUTY) {
+                    if (n0 >= p.n_k2 && p.skip_accumulate)
+                        src = p.skip_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + (n0 - p.n_k2);
                 }
                 if (src && valid) {
                     have_pre = true;
 #pragma unroll
                     for (int i = 0; i < BNH / 4; ++i) pre[i] = reinterpret_cast<const uint4*>(src)[i];
+                }
+                if (p.epi == UEPI_DN_OUTY && n0 < p.n_k2 && valid) {
+                    // y (fp16 hi/lo, updated in place): hi halves in pre[0, BNH/8), lo halves in pre[BNH/8, BNH/4)
+                    have_pre = true;
+                    const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n0;
+                    const uint4* yh = reinterpret_cast<const uint4*>(p.out_h + o);
+                    const uint4* yl = reinterpret_cast<const uint4*>(p.out_lo + o);
+#pragma unroll
+                    for (int i = 0; i < BNH / 8; ++i) { pre[i] = yh[i]; pre[BNH / 8 + i] = yl[i]; }
                 }
             } else {
                 if (p.res_h && valid) {
@@ -251,11 +346,27 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         store16h(p.out_h + o, v);
                     } else {
                         float x[16];
+                        if (p.epi == UEPI_DN_OUTY && n < p.n_k2) {
+                            // old y = hi + lo of this thread's 16 columns
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint4 u = have_pre ? pre[4 * c + i] : make_uint4(0u, 0u, 0u, 0u);
-                            x[4 * i] = __uint_as_float(u.x); x[4 * i + 1] = __uint_as_float(u.y);
-                            x[4 * i + 2] = __uint_as_float(u.z); x[4 * i + 3] = __uint_as_float(u.w);
+                            for (int i = 0; i < 2; ++i) {
+                                const uint4 uh = have_pre ? pre[2 * c + i] : make_uint4(0u, 0u, 0u, 0u);
+                                const uint4 ul = have_pre ? pre[BNH / 8 + 2 * c + i] : make_uint4(0u, 0u, 0u, 0u);
+                                const __half2* hh = reinterpret_cast<const __half2*>(&uh);
+                                const __half2* hl = reinterpret_cast<const __half2*>(&ul);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 a = __half22float2(hh[j]), bq = __half22float2(hl[j]);
+                                    x[8 * i + 2 * j] = a.x + bq.x; x[8 * i + 2 * j + 1] = a.y + bq.y;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const uint4 u = have_pre ? pre[4 * c + i] : make_uint4(0u, 0u, 0u, 0u);
+                                x[4 * i] = __uint_as_float(u.x); x[4 * i + 1] = __uint_as_float(u.y);
+                                x[4 * i + 2] = __uint_as_float(u.z); x[4 * i + 3] = __uint_as_float(u.w);
+                            }
                         }
                         if (p.epi == UEPI_F32) {
                             if (n >= p.n_valid) continue;
@@ -280,7 +391,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             if (p.out_f32) store16f(p.out_f32 + (long long)b * p.out32_bstride + (long long)t * p.out32_ld + n, v);
                             if (p.out_h) {
                                 const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
-                                store16_hilo(p.out_h + o, p.out_lo + o, v);
+                                if (p.out_lo) store16_hilo(p.out_h + o, p.out_lo + o, v);
+                                else store16h(p.out_h + o, v);          // plain fp16 (vocoder activated storage)
                             }
                         } else if (p.epi == UEPI_DN_COND) {
                             float a[16];
@@ -289,6 +401,19 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             for (int j = 0; j < 16; ++j) v[j] += a[j] + x[j];
                             const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
                             store16_hilo(p.out_h + o, p.out_lo + o, v);
+                        } else if (p.epi == UEPI_DN_OUTY) {
+                            if (n < p.n_k2) {
+                                float a[16];
+                                load16f(p.addvec + (long long)b * p.addvec_bstride + n, a);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] = fmaf(x[j], p.out_scale, v[j] + a[j]);
+                                const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
+                                store16_hilo(p.out_h + o, p.out_lo + o, v);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] += x[j];     // x[] holds the old skip (or zeros)
+                                store16f(p.skip_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + (n - p.n_k2), v);
+                            }
                         } else {  // UEPI_DN_OUT
                             const int half_n = p.N >> 1;
                             if (n < half_n) {
@@ -349,16 +474,23 @@ int launch_cfg(const UmmaConvParams& p, cudaStream_t s) {
         return CMTTS_ERR_CUDA;
     }
     a1 = a0; b1 = b0;
+    CUtensorMap a2 = a0, a3 = a0;
     if (SPLIT) {
+        const int wk = p.Cin + (p.a2_hi ? p.Cin2 : 0);     // weight row length
         if (!make_act_map(&a1, p.a_lo, p.Cin, p.Lin, p.B, p.a_ld, p.a_bstride, BK) ||
-            !make_w_map(&b1, p.w_lo, p.Cin, p.taps * p.N, BK, BN)) {
+            !make_w_map(&b0, p.w_hi, wk, p.taps * p.N, BK, BN) || !make_w_map(&b1, p.w_lo, wk, p.taps * p.N, BK, BN)) {
             cmtts_set_error("umma_conv: cuTensorMapEncodeTiled failed (lo operands)", __FILE__, __LINE__);
+            return CMTTS_ERR_CUDA;
+        }
+        if (p.a2_hi && (!make_act_map(&a2, p.a2_hi, p.Cin2, p.M, p.B, p.a2_ld, p.a2_bstride, BK) ||
+                        !make_act_map(&a3, p.a2_lo, p.Cin2, p.M, p.B, p.a2_ld, p.a2_bstride, BK))) {
+            cmtts_set_error("umma_conv: cuTensorMapEncodeTiled failed (second operand)", __FILE__, __LINE__);
             return CMTTS_ERR_CUDA;
         }
     }
     const int tiles = p.B * ((p.M + 127) / 128) * (p.N / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, 384, SMEM, s>>>(a0, a1, b0, b1, p);
+    kern<<<grid, 384, SMEM, s>>>(a0, a1, b0, b1, a2, a3, p);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }
@@ -380,6 +512,14 @@ int launch_umma_conv(const UmmaConvParams& p_in, cudaStream_t s) {
     if (p.split) {
         CMTTS_REQUIRE(p.a_lo && p.w_lo, "umma_conv: split mode needs lo operands");
         CMTTS_REQUIRE(bk == 64 && p.N % 128 == 0, "umma_conv: split mode needs Cin % 64 == 0 and N % 128 == 0");
+        if (p.a2_hi) {
+            CMTTS_REQUIRE(p.a2_lo && p.taps == 1 && p.shift[0] == 0 && p.Cin2 > 0 && p.Cin2 % 64 == 0 && p.n_k2 % 128 == 0 &&
+                          p.n_k2 > 0 && p.n_k2 <= p.N && p.a2_ld % 8 == 0 && p.a2_bstride % 8 == 0 &&
+                          ((uintptr_t)p.a2_hi % 16 == 0) && ((uintptr_t)p.a2_lo % 16 == 0),
+                          "umma_conv: second operand needs taps == 1, Cin2 % 64 == 0, n_k2 % 128 == 0, 16-byte alignment");
+        }
+        CMTTS_REQUIRE(p.epi != UEPI_DN_OUTY || (p.a2_hi && p.out_h && p.out_lo && p.addvec && p.skip_f32),
+                      "umma_conv: UEPI_DN_OUTY needs the second operand, y hi/lo, addvec and skip");
         return launch_cfg<128, 64, 1>(p, s);
     }
     CMTTS_REQUIRE(p.epi == UEPI_VOC, "umma_conv: denoiser epilogues need split mode");
@@ -433,25 +573,41 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ x, __half* __restric
 
 // conv_post on fp16 "activated" input a = lrelu(xs, 0.01): tanh(sum w * (a / pre_div) + b); leaky-ReLU is
 // positively homogeneous so lrelu(xs / 3) == lrelu(xs) / 3 (hifigan/models.py:160-163).
-__global__ void conv_post_f16_kernel(const __half* __restrict__ x, const float* __restrict__ w,
-                                     const float* __restrict__ bias, float pre_div, float* __restrict__ wav,
-                                     short* __restrict__ wav_i16, float max_wav, int L, int C, int K) {
-    extern __shared__ float s_w[];
-    for (int i = threadIdx.x; i < K * C; i += blockDim.x) s_w[i] = w[i];
-    __syncthreads();
+// HBM-bound (reads B*L*C fp16 once, writes B*L samples): the (256 + K - 1)-row input tile of a block is one
+// contiguous run in memory, staged in shared memory with coalesced 16-byte loads (row pitch padded by 16 bytes
+// so a quarter-warp's row-strided 16-byte reads hit distinct banks); each thread then owns one output sample.
+constexpr int POST_TILE = 256;
+__global__ void __launch_bounds__(POST_TILE)
+conv_post_f16_kernel(const __half* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                     float pre_div, float* __restrict__ wav, short* __restrict__ wav_i16, float max_wav, int L, int C,
+                     int K) {
+    extern __shared__ __align__(16) uint8_t post_smem[];
+    float* s_w = reinterpret_cast<float*>(post_smem);                       // [K][C]
+    const int pitch = C * 2 + 16;                                           // bytes per staged row
+    uint8_t* s_x = post_smem + ((K * C * 4 + 15) & ~15);
     const int b = blockIdx.y;
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= L) return;
-    const __half* xb = x + (long long)b * L * C;
-    float acc = 0.f;
+    const int n0 = blockIdx.x * POST_TILE;
     const int pad = (K - 1) / 2;
+    const int rows = POST_TILE + K - 1;
+    const int cpr = C >> 3;                                                 // 16-byte chunks per row
+    for (int i = threadIdx.x; i < K * C; i += POST_TILE) s_w[i] = w[i];
+    const __half* xb = x + (long long)b * L * C;
+    for (int i = threadIdx.x; i < rows * cpr; i += POST_TILE) {
+        const int r = i / cpr, ch = i - r * cpr;
+        const int src = n0 - pad + r;
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (src >= 0 && src < L) u = reinterpret_cast<const uint4*>(xb + (long long)src * C)[ch];
+        *reinterpret_cast<uint4*>(s_x + r * pitch + ch * 16) = u;
+    }
+    __syncthreads();
+    const int n = n0 + threadIdx.x;
+    if (n >= L) return;
+    float acc = 0.f;
     for (int k = 0; k < K; ++k) {
-        const int src = n + k - pad;
-        if (src < 0 || src >= L) continue;
-        const uint4* xr = reinterpret_cast<const uint4*>(xb + (long long)src * C);
+        const uint8_t* xr = s_x + (threadIdx.x + k) * pitch;
         const float* wk = s_w + k * C;
-        for (int c8 = 0; c8 < (C >> 3); ++c8) {
-            const uint4 u = xr[c8];
+        for (int c8 = 0; c8 < cpr; ++c8) {
+            const uint4 u = *reinterpret_cast<const uint4*>(xr + c8 * 16);
             const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -480,9 +636,10 @@ int launch_f32_to_f16(const float* x, __half* hi, __half* lo, long long rows, in
 int launch_conv_post_f16(const __half* x, const float* w, const float* bias, float pre_div, float* wav, short* wav_i16,
                          float max_wav, int B, int L, int C, int K, cudaStream_t s) {
     if (B == 0 || L == 0) return CMTTS_OK;
-    CMTTS_REQUIRE(C % 8 == 0 && K * C * 4 <= 48 * 1024, "conv_post_f16: shape");
-    dim3 grid((L + 255) / 256, B);
-    conv_post_f16_kernel<<<grid, 256, K * C * sizeof(float), s>>>(x, w, bias, pre_div, wav, wav_i16, max_wav, L, C, K);
+    const size_t smem = (size_t)((K * C * 4 + 15) & ~15) + (size_t)(POST_TILE + K - 1) * (C * 2 + 16);
+    CMTTS_REQUIRE(C % 8 == 0 && smem <= 48 * 1024, "conv_post_f16: shape");
+    dim3 grid((L + POST_TILE - 1) / POST_TILE, B);
+    conv_post_f16_kernel<<<grid, POST_TILE, smem, s>>>(x, w, bias, pre_div, wav, wav_i16, max_wav, L, C, K);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }

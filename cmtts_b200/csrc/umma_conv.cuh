@@ -9,6 +9,9 @@ enum UmmaEpi {
     UEPI_DN_GATE = 2,  // sigmoid(gate + b) * tanh(filter + b)          -> fp16 hi/lo   (BN = 128: 64 gates | 64 filters)
     UEPI_DN_OUT = 3,   // cols <  N/2: x = (acc + b + addvec[b] + x) * out_scale (fp32, in place)
                        // cols >= N/2: skip (+)= acc + b                 (fp32)
+    UEPI_DN_OUTY = 5,  // fused "output projection + next layer's conditioner" of the y-recurrence (see pipeline.cu):
+                       // cols <  n_k2: y = acc + bias + addvec[b] + y * out_scale  (fp16 hi/lo, in place in out_h/out_lo)
+                       // cols >= n_k2: skip (+)= acc + bias                        (fp32)
     UEPI_F32 = 4,      // generic: v = act((acc*alpha + bias) * beta) + addvec[b] + res*res_scale ; v *= out_scale ;
                        // rows >= lens[b] -> 0 ; written as fp32 (out_f32) and/or fp16 hi/lo ; cols >= n_valid dropped
 };
@@ -22,6 +25,9 @@ struct UmmaConvParams {
     // operands (fp16, channels-last activations [B][Lin][Cin]; weights [taps*N][Cin])
     const __half* a_hi; const __half* a_lo; long long a_bstride; int a_ld;
     const __half* w_hi; const __half* w_lo;
+    // optional SECOND activation operand (split mode, taps == 1): the contraction runs over [A | A2], i.e.
+    // K = Cin + Cin2 with weights [N][Cin + Cin2]; output columns >= n_k2 contract over the first Cin only
+    const __half* a2_hi; const __half* a2_lo; long long a2_bstride; int a2_ld; int Cin2; int n_k2;
     // epilogue
     const float* bias; float alpha;
     // UEPI_VOC: v = acc*alpha + bias + inv_lrelu(res) + sum ; out = lrelu(v, out_slope) as fp16

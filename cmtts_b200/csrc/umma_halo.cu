@@ -15,8 +15,15 @@
 //   and the residual tile of the epilogue is ALSO fetched by TMA into its own ring, so the
 //   HBM-bound levels keep tens of KB in flight per SM instead of one row per thread.
 //
+// * WIDE EPILOGUE: 8 epilogue warps (lane quarter x column half).  A single warp per SM sub-partition
+//   issues its ~12 instructions per output element back to back at the ALU dependency latency, which
+//   made the 4-warp epilogue (not HBM, not the tensor pipe) the limiter of every shape here (ncu:
+//   epilogue warps >80 % busy, MMA warp waiting on the accumulator-empty barrier).  Each warp owns its
+//   staging slab and TMA store (column half = one channel block, or half of one), the bias sits in
+//   shared memory, and leaky-ReLU is max(v, s v) / min(v, s v).
+//
 // Roles: warp 0 = activation TMA producer (+ resident weights), warp 3 = residual + streamed-weight
-// TMA producer, warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue.
+// TMA producer, warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4-11 = epilogue.
 #include "umma_common.cuh"
 
 namespace {
@@ -31,8 +38,12 @@ struct HaloCfg {
     int box_rows;                       // 128 + span
 };
 
+// leaky-ReLU without a compare/select: slope <= 1 (forward) and slope >= 1 (the exact inverse on stored values)
+__device__ __forceinline__ float lrelu_fwd(float v, float slope) { return fmaxf(v, v * slope); }
+__device__ __forceinline__ float lrelu_inv(float v, float inv_slope) { return fminf(v, v * inv_slope); }
+
 template <int BN, int BK, int CB, int TAPS>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
                  const UmmaConvParams p, const HaloCfg cfg) {
@@ -41,8 +52,10 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int W_BLK = BN * ROW_BYTES;
     constexpr int R_BLK = BM * ROW_BYTES;          // one channel block of the residual tile
     constexpr int R_STAGE = CB * R_BLK;
-    constexpr int O_SLAB = 32 * ROW_BYTES;         // one epilogue warp's 32 output rows of one channel block
-    constexpr int O_BYTES = 4 * CB * O_SLAB;       // whole 128 x BN fp16 output tile
+    constexpr int BNH = BN / 2;                    // output columns per epilogue warp
+    constexpr int OROW = BNH * 2;                  // bytes per staged output row of one warp (128 / 64 / 32)
+    constexpr int O_SLAB = 32 * OROW;              // one epilogue warp's 32 rows x BNH columns
+    constexpr int O_BYTES = 8 * O_SLAB;            // whole 128 x BN fp16 output tile
     constexpr int TMEM_COLS = pow2_cols(2 * BN);
     constexpr bool TMA_STORE = BN >= 64;           // C = 32: a warp's 32 rows are one contiguous 2 KB run, direct stores win
 
@@ -67,6 +80,7 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tfull = r_empty + MAX_STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // float4 reads
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (p.M + BM - 1) / BM;
@@ -77,15 +91,16 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < MAX_STAGES; ++i) {
             mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
             mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
-            mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 4);
+            mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 8);
         }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (threadIdx.x >= 128 && threadIdx.x < 128 + BN) s_bias[threadIdx.x - 128] = p.bias[threadIdx.x - 128];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -199,65 +214,86 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else if (warp >= 4) {
-        // ======================= epilogue (UEPI_VOC) =======================
-        const int q = warp & 3;
+        // ======================= epilogue (UEPI_VOC), 8 warps =======================
+        const int q = warp & 3;                    // TMEM lane quarter
+        const int h = (warp - 4) >> 2;             // column half
         const int row = q * 32 + lane;
+        constexpr int CHUNKS = ROW_BYTES / 16;     // 16-byte chunks per channel-block row of the residual tile: 8 or 4
         // 16-byte chunk swizzle of the TMA-written residual tile (same pattern as the operands)
         const int swz = (BK == 64) ? (row & 7) : ((row >> 1) & 3);
-        constexpr int CHUNKS = ROW_BYTES / 16;     // 16-byte chunks per channel-block row: 8 or 4
-        const int swz_o = (BK == 64) ? (lane & 7) : ((lane >> 1) & 3);   // same pattern, row index inside the warp slab
+        // staging slab of this warp: rows of OROW bytes in the TMA box layout (128B / 64B swizzle by row pitch)
+        const int swz_o = (OROW == 128) ? (lane & 7) : ((lane >> 1) & 3);
+        uint8_t* slab = smO + (warp - 4) * O_SLAB + lane * OROW;
+        const int n_base = h * BNH;
         int abuf = 0; uint32_t aphase = 0;
         int rs = 0; uint32_t rphase = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             const int mt = tile % m_tiles, b = tile / m_tiles;
             const int t = mt * BM + row;
             const bool valid = t < p.M;
-            uint4 rres[BN / 8];
+            uint4 rres[BNH / 8];
             if (has_res) {
                 mbar_wait(&r_full[rs], rphase);
                 const uint8_t* rb = smR + rs * R_STAGE + row * ROW_BYTES;
 #pragma unroll
-                for (int i = 0; i < BN / 8; ++i) {
-                    const int cb = i / CHUNKS, j = i % CHUNKS;
+                for (int i = 0; i < BNH / 8; ++i) {
+                    const int gi = n_base / 8 + i;
+                    const int cb = gi / CHUNKS, j = gi % CHUNKS;
                     rres[i] = *reinterpret_cast<const uint4*>(rb + cb * R_BLK + ((j ^ swz) << 4));
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&r_empty[rs]);
                 if (++rs == cfg.r_stages) { rs = 0; rphase ^= 1; }
             }
+            // MRF partial sum (last iteration of a resblock): global reads issued before the accumulator wait
+            uint4 rsum[BNH / 8];
+            const bool has_sum = p.sum_h != nullptr && valid;
+            if (has_sum) {
+                const uint4* sp = reinterpret_cast<const uint4*>(p.sum_h + (long long)b * p.out_bstride + (long long)t * p.out_ld + n_base);
+#pragma unroll
+                for (int i = 0; i < BNH / 8; ++i) rsum[i] = sp[i];
+            }
             mbar_wait(&tfull[abuf], aphase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (uint32_t)(abuf * BN) + ((uint32_t)(q * 32) << 16);
+            const uint32_t taddr = tmem_base + (uint32_t)(abuf * BN + n_base) + ((uint32_t)(q * 32) << 16);
             // the previous tile's TMA store must have finished READING this warp's staging slab
             if (TMA_STORE) {
                 if (lane == 0) tma_store_wait_read();
                 __syncwarp();
             }
-            uint8_t* slab = smO + q * (CB * O_SLAB) + lane * ROW_BYTES;     // this thread's row inside the warp slab
 #pragma unroll
-            for (int c = 0; c < BN / 16; ++c) {
+            for (int c = 0; c < BNH / 16; ++c) {
                 uint32_t r[16];
                 tmem_ld16(taddr + c * 16, r);
                 tmem_ld_wait();
-                const int n = c * 16;
+                const int n = n_base + c * 16;
                 float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, p.bias[n + j]);
+                for (int j = 0; j < 4; ++j) {
+                    const float4 bq = *reinterpret_cast<const float4*>(s_bias + n + 4 * j);
+                    v[4 * j] = fmaf(__uint_as_float(r[4 * j]), p.alpha, bq.x);
+                    v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), p.alpha, bq.y);
+                    v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), p.alpha, bq.z);
+                    v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), p.alpha, bq.w);
+                }
                 if (has_res) {
                     const __half2* h0 = reinterpret_cast<const __half2*>(&rres[2 * c]);
                     const __half2* h1 = reinterpret_cast<const __half2*>(&rres[2 * c + 1]);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float2 a = __half22float2(h0[i]), bb = __half22float2(h1[i]);
-                        v[2 * i] += lrelu(a.x, p.res_inv_slope); v[2 * i + 1] += lrelu(a.y, p.res_inv_slope);
-                        v[8 + 2 * i] += lrelu(bb.x, p.res_inv_slope); v[8 + 2 * i + 1] += lrelu(bb.y, p.res_inv_slope);
+                        v[2 * i] += lrelu_inv(a.x, p.res_inv_slope); v[2 * i + 1] += lrelu_inv(a.y, p.res_inv_slope);
+                        v[8 + 2 * i] += lrelu_inv(bb.x, p.res_inv_slope); v[8 + 2 * i + 1] += lrelu_inv(bb.y, p.res_inv_slope);
                     }
                 }
-                if (p.sum_h && valid) {
-                    float ss[16];
-                    load16h(p.sum_h + (long long)b * p.out_bstride + (long long)t * p.out_ld + n, ss);
+                if (has_sum) {
+                    const __half2* s0 = reinterpret_cast<const __half2*>(&rsum[2 * c]);
+                    const __half2* s1 = reinterpret_cast<const __half2*>(&rsum[2 * c + 1]);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += ss[j];
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 a = __half22float2(s0[i]), bb = __half22float2(s1[i]);
+                        v[2 * i] += a.x; v[2 * i + 1] += a.y; v[8 + 2 * i] += bb.x; v[8 + 2 * i + 1] += bb.y;
+                    }
                 }
                 // stage as fp16 in the TMA box layout: 16-byte chunk j of a row lives at chunk (j ^ swz)
                 uint4 u0, u1;
@@ -265,13 +301,12 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 __half2* p1 = reinterpret_cast<__half2*>(&u1);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    p0[i] = __floats2half2_rn(lrelu(v[2 * i], p.out_slope), lrelu(v[2 * i + 1], p.out_slope));
-                    p1[i] = __floats2half2_rn(lrelu(v[8 + 2 * i], p.out_slope), lrelu(v[8 + 2 * i + 1], p.out_slope));
+                    p0[i] = __floats2half2_rn(lrelu_fwd(v[2 * i], p.out_slope), lrelu_fwd(v[2 * i + 1], p.out_slope));
+                    p1[i] = __floats2half2_rn(lrelu_fwd(v[8 + 2 * i], p.out_slope), lrelu_fwd(v[8 + 2 * i + 1], p.out_slope));
                 }
                 if (TMA_STORE) {
-                    const int cb = (2 * c) / CHUNKS, j0 = (2 * c) % CHUNKS;
-                    *reinterpret_cast<uint4*>(slab + cb * O_SLAB + ((j0 ^ swz_o) << 4)) = u0;
-                    *reinterpret_cast<uint4*>(slab + cb * O_SLAB + (((j0 + 1) ^ swz_o) << 4)) = u1;
+                    *reinterpret_cast<uint4*>(slab + (((2 * c) ^ swz_o) << 4)) = u0;
+                    *reinterpret_cast<uint4*>(slab + (((2 * c + 1) ^ swz_o) << 4)) = u1;
                 } else if (valid) {
                     __half* op = p.out_h + (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
                     *reinterpret_cast<uint4*>(op) = u0;
@@ -284,9 +319,7 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (lane == 0) {
                 mbar_arrive(&tempty[abuf]);
                 if (TMA_STORE) {
-#pragma unroll
-                    for (int cb = 0; cb < CB; ++cb)
-                        tma_store_3d(&tmO, smO + q * (CB * O_SLAB) + cb * O_SLAB, cb * BK, mt * BM + q * 32, b);
+                    tma_store_3d(&tmO, smO + (warp - 4) * O_SLAB, n_base, mt * BM + q * 32, b);
                     tma_store_commit();
                 }
             }
@@ -310,8 +343,8 @@ int launch_halo_cfg(const UmmaConvParams& p, cudaStream_t s) {
     constexpr int R_STAGE = CB * 128 * ROW_BYTES;
     constexpr int ROW_ALIGN = 1024 / ROW_BYTES;        // rows per 1024-byte swizzle-aligned unit
     constexpr size_t LIMIT = 227 * 1024;
-    constexpr size_t O_BYTES = (size_t)4 * CB * 32 * ROW_BYTES;
-    constexpr size_t FIXED = (6 * MAX_STAGES + 4) * 8 + 16 + 1024 + O_BYTES;
+    constexpr size_t O_BYTES = (size_t)8 * 32 * BN;        // 8 warps x 32 rows x BN/2 fp16
+    constexpr size_t FIXED = (6 * MAX_STAGES + 4) * 8 + 32 + BN * 4 + 1024 + O_BYTES;
 
     HaloCfg cfg{};
     const int span = p.shift[p.taps - 1] - p.shift[0];
@@ -360,13 +393,14 @@ int launch_halo_cfg(const UmmaConvParams& p, cudaStream_t s) {
         cmtts_set_error("umma_halo: cuTensorMapEncodeTiled failed (residual)", __FILE__, __LINE__);
         return CMTTS_ERR_CUDA;
     }
-    if (!make_act_map(&o_map, p.out_h, p.N, p.M, p.B, p.out_ld, p.out_bstride, BK, 32)) {
+    // output boxes: one per epilogue warp, BN/2 channels x 32 rows (128B swizzle for 64 channels, 64B for 32)
+    if (!make_act_map(&o_map, p.out_h, p.N, p.M, p.B, p.out_ld, p.out_bstride, BN >= 128 ? 64 : 32, 32)) {
         cmtts_set_error("umma_halo: cuTensorMapEncodeTiled failed (output)", __FILE__, __LINE__);
         return CMTTS_ERR_CUDA;
     }
     const int tiles = p.B * ((p.M + 127) / 128);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, 256, smem, s>>>(a_map, w_map, r_map, o_map, p, cfg);
+    kern<<<grid, 384, smem, s>>>(a_map, w_map, r_map, o_map, p, cfg);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }
@@ -382,6 +416,8 @@ int launch_umma_halo(const UmmaConvParams& p, cudaStream_t s) {
     if (p.shift[p.taps - 1] - p.shift[0] > 96) return CMTTS_ERR_UNSUPPORTED;
     if (p.out_ld % 8 != 0 || p.out_bstride % 8 != 0 || ((uintptr_t)p.out_h % 16) != 0) return CMTTS_ERR_UNSUPPORTED;
     if (p.res_h && (p.res_ld % 8 != 0 || p.res_bstride % 8 != 0 || ((uintptr_t)p.res_h % 16) != 0)) return CMTTS_ERR_UNSUPPORTED;
+    // max / min form of leaky-ReLU: forward slope in (0, 1], inverse slope >= 1
+    if (!(p.out_slope > 0.f && p.out_slope <= 1.f && p.res_inv_slope >= 1.f)) return CMTTS_ERR_UNSUPPORTED;
     if (p.B == 0 || p.M == 0) return CMTTS_OK;
     for (int i = 2; i < p.taps; ++i)   // uniform tap spacing (dilation)
         if (p.shift[i] - p.shift[i - 1] != p.shift[1] - p.shift[0]) return CMTTS_ERR_UNSUPPORTED;

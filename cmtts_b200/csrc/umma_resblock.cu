@@ -10,40 +10,58 @@
 //     rows outside the utterance are written as zeros (conv2 zero-pads t, not c1(padding));
 //   * conv2 (dilation 1) reads that tile, again by row offsets; each tile yields 128 - (k-1) valid
 //     output rows (92-98 % of the MMA rows);
-//   * the residual y is read back from the input tile already in shared memory (stored as lrelu(y),
-//     inverted exactly in the epilogue), the output is staged in the TMA box layout and TMA-stored.
+//   * the residual y is re-read from global memory (L2-hot: the TMA just fetched the same rows) into
+//     registers BEFORE the accumulator wait (stored as lrelu(y), inverted exactly in the epilogue); the
+//     output is staged in the TMA box layout and TMA-stored.
 // HBM traffic per iteration: read y once (+halo), write y' once.
 //
-// Pipelining: the MMA-issuing warp alternates conv1(i+1) / conv2(i); epilogue 1 (TMEM -> t tile) and
-// epilogue 2 (output) run on separate warp quartets concurrently; accumulators and the t tile are
-// double-buffered.
+// Pipelining: conv2 of a tile can only start after conv1 -> commit -> epilogue 1 -> t tile, a chain of
+// ~1.5k cycles, so the MMA-issuing warp runs conv1 `lag` = nb-1 tiles AHEAD of conv2 (conv1(i+lag) is
+// issued before conv2(i)); conv1 accumulators and t tiles are nb-deep rings (nb = 3 or 4).  Epilogue 1
+// (TMEM -> t tile) and epilogue 2 (output) run on separate warps concurrently — EIGHT warps each (lane
+// quarter x column half): a lone warp per SM sub-partition issues its dependent ALU chain at ~4 cycles per
+// instruction, which made the epilogues (not HBM, not the tensor pipe) the limiter (ncu: MMA warp stalled on
+// acc2_empty, epilogue-2 warps > 80 % busy).  Biases sit in shared memory; leaky-ReLU is max / min(v, s v).
+// The input stage is released by the conv1 commit.
+//
+// Roles (576 threads): warp 0 TMEM allocator + TMA producer, 1 MMA issuer, 2-9 epilogue 1, 10-17 epilogue 2
+// (an epilogue warp's TMEM lane quarter is warp % 4, its column half the warp's position in its group of eight).
 // Both weight sets stay resident in shared memory for the whole persistent loop.
 #include "umma_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
 using namespace umma;
 
 constexpr int RB_MAX_STAGES = 8;
+constexpr int RB_MAX_NB = 4;           // depth of the conv1-accumulator / t-tile rings
 constexpr int T_ROWS_ALLOC = 144;      // 128 + (k_max - 1) rounded to the swizzle atom
 
 struct RbCfg {
-    int a_stages, rows_alloc, box_rows, valid, m_tiles;
+    int a_stages, rows_alloc, box_rows, valid, m_tiles, nb, nb2;   // nb2: depth of the conv2-accumulator ring (2..4)
 };
 
-template <int C, int TAPS>
-__global__ void __launch_bounds__(384, 1)
+__device__ __forceinline__ float lrelu_fwd(float v, float slope) { return fmaxf(v, v * slope); }          // slope <= 1
+__device__ __forceinline__ float lrelu_inv(float v, float inv_slope) { return fminf(v, v * inv_slope); }  // inv_slope >= 1
+
+constexpr int RB_THREADS = 576;          // 18 warps -> 112 registers per thread
+
+template <int C, int TAPS, bool HAS_SUM>
+__global__ void __launch_bounds__(RB_THREADS, 1)
 umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                      const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmO,
                      const __grid_constant__ CUtensorMap tmOtail, const UmmaResblockParams p, const RbCfg cfg) {
     constexpr int BM = 128;
     constexpr int BK = C;                          // one channel block (C = 64 -> SW128, C = 32 -> SW64)
     constexpr int ROW_BYTES = BK * 2;
-    constexpr int CHUNKS = ROW_BYTES / 16;
     constexpr int W_BLK = C * ROW_BYTES;           // one tap of one conv
     constexpr int T_ALLOC = T_ROWS_ALLOC * ROW_BYTES;
-    constexpr int O_SLAB = 32 * ROW_BYTES;
-    constexpr int TMEM_COLS = pow2_cols(4 * C);
+    constexpr int CH = C / 2;                      // columns per epilogue warp
+    constexpr int OROW = CH * 2;                   // bytes per staged output row of one epilogue-2 warp
+    constexpr int O_SLAB = 32 * OROW;
+    constexpr bool TMA_STORE = C >= 64;            // C = 32: 32-byte half rows, direct stores
+    constexpr int TMEM_COLS = pow2_cols(2 * RB_MAX_NB * C);
     constexpr int P2 = (TAPS - 1) / 2;
     constexpr uint32_t DESC_HI = (uint32_t)((8 * ROW_BYTES) >> 4) | (1u << 14) | ((BK == 64 ? 2u : 4u) << 29);
 
@@ -53,43 +71,47 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smA = smem;
     uint8_t* smT = smA + cfg.a_stages * a_alloc;
-    uint8_t* smO = smT + 2 * T_ALLOC;
-    uint8_t* smW1 = smO + 4 * O_SLAB;
+    uint8_t* smO = smT + cfg.nb * T_ALLOC;
+    uint8_t* smW1 = smO + 8 * O_SLAB;
     uint8_t* smW2 = smW1 + TAPS * W_BLK;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smW2 + TAPS * W_BLK);
     uint64_t* a_empty = a_full + RB_MAX_STAGES;
     uint64_t* w_full = a_empty + RB_MAX_STAGES;    // [1]
-    uint64_t* acc1_full = w_full + 1;              // [2]
-    uint64_t* acc1_empty = acc1_full + 2;
-    uint64_t* acc2_full = acc1_empty + 2;
-    uint64_t* acc2_empty = acc2_full + 2;
-    uint64_t* t_full = acc2_empty + 2;
-    uint64_t* t_empty = t_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    uint64_t* acc1_full = w_full + 1;              // [RB_MAX_NB]
+    uint64_t* acc1_empty = acc1_full + RB_MAX_NB;
+    uint64_t* t_full = acc1_empty + RB_MAX_NB;
+    uint64_t* t_empty = t_full + RB_MAX_NB;
+    uint64_t* acc2_full = t_empty + RB_MAX_NB;     // [RB_MAX_NB]
+    uint64_t* acc2_empty = acc2_full + RB_MAX_NB;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + RB_MAX_NB);
+    float* s_b1 = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // float4 reads
+    float* s_b2 = s_b1 + C;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = p.B * cfg.m_tiles;
     const int p1d = ((TAPS - 1) / 2) * p.dil;      // conv1 half-span in rows
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < RB_MAX_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 4); }
+        for (int i = 0; i < RB_MAX_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         mbar_init(&w_full[0], 1);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], 4);
-            mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], 4);
-            mbar_init(&t_full[i], 4); mbar_init(&t_empty[i], 1);
+        for (int i = 0; i < RB_MAX_NB; ++i) {
+            mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], 8);
+            mbar_init(&t_full[i], 8); mbar_init(&t_empty[i], 1);
+            mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + C) { s_b1[threadIdx.x - 64] = p.b1[threadIdx.x - 64]; s_b2[threadIdx.x - 64] = p.b2[threadIdx.x - 64]; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // TMEM columns: acc1[b] at b*C, acc2[b] at 2C + b*C
+    // TMEM columns: acc1[b] at b*C (b < nb), acc2[b] at RB_MAX_NB*C + b*C
+    const int nb = cfg.nb;
 
     if (warp == 0) {
         // ======================= producer: resident weights, then one halo tile per output tile =======
@@ -126,13 +148,17 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             tc_fence_after();
             int stage = 0; uint32_t phase = 0;
             int it = 0;
-            auto conv2 = [&](int j) {
-                const int bb = j & 1; const uint32_t ph = (uint32_t)((j >> 1) & 1);
-                mbar_wait(&t_full[bb], ph);
-                mbar_wait(&acc2_empty[bb], ph ^ 1);
+            // ring positions: conv1 side (b1, ph1), conv2 side (t ring: b2, ph2; conv2 accumulators: ab, aph)
+            int b1 = 0; uint32_t ph1 = 0;
+            int b2 = 0; uint32_t ph2 = 0;
+            int j2 = 0;
+            int ab = 0; uint32_t aph = 0;
+            auto conv2 = [&]() {
+                mbar_wait(&t_full[b2], ph2);
+                mbar_wait(&acc2_empty[ab], aph ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_u + (uint32_t)(2 * C + bb * C);
-                const uint32_t t_lo = ((smem_u32(smT + bb * T_ALLOC) >> 4) & 0x3FFF) | (1u << 16);
+                const uint32_t d_tmem = tmem_u + (uint32_t)(RB_MAX_NB * C + ab * C);
+                const uint32_t t_lo = ((smem_u32(smT + b2 * T_ALLOC) >> 4) & 0x3FFF) | (1u << 16);
 #pragma unroll
                 for (int tap = 0; tap < TAPS; ++tap) {
 #pragma unroll
@@ -141,15 +167,18 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                  ((uint64_t)DESC_HI << 32) | (w2_lo + (uint32_t)((tap * W_BLK) >> 4) + 2 * k), idesc,
                                  (tap | k) ? 1u : 0u, issue);
                 }
-                umma_commit_pred(&t_empty[bb], issue);
-                umma_commit_pred(&acc2_full[bb], issue);
+                umma_commit_pred(&t_empty[b2], issue);
+                umma_commit_pred(&acc2_full[ab], issue);
+                ++j2;
+                if (++b2 == nb) { b2 = 0; ph2 ^= 1; }
+                if (++ab == cfg.nb2) { ab = 0; aph ^= 1; }
             };
+            const int lag = nb - 1;
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-                const int bb = it & 1; const uint32_t ph = (uint32_t)((it >> 1) & 1);
-                mbar_wait(&acc1_empty[bb], ph ^ 1);
+                mbar_wait(&acc1_empty[b1], ph1 ^ 1);
                 mbar_wait(&a_full[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_u + (uint32_t)(bb * C);
+                const uint32_t d_tmem = tmem_u + (uint32_t)(b1 * C);
                 const uint32_t a_lo = ((smem_u32(smA + stage * a_alloc) >> 4) & 0x3FFF) | (1u << 16);
 #pragma unroll
                 for (int tap = 0; tap < TAPS; ++tap) {
@@ -159,155 +188,193 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                  ((uint64_t)DESC_HI << 32) | (w1_lo + (uint32_t)((tap * W_BLK) >> 4) + 2 * k), idesc,
                                  (tap | k) ? 1u : 0u, issue);
                 }
-                umma_commit_pred(&acc1_full[bb], issue);
+                umma_commit_pred(&a_empty[stage], issue);      // input stage free once conv1 has read it
+                umma_commit_pred(&acc1_full[b1], issue);
                 if (++stage == cfg.a_stages) { stage = 0; phase ^= 1; }
-                if (it > 0) conv2(it - 1);
+                if (++b1 == nb) { b1 = 0; ph1 ^= 1; }
+                if (it >= lag) conv2();
             }
-            if (it > 0) conv2(it - 1);
+            while (j2 < it) conv2();
         }
-    } else if (warp >= 4) {
+    } else {
         // ======================= epilogue warps =======================
-        const int q = warp & 3;
+        const bool is_e1 = warp < 10;     // warps 2-9: epilogue 1 (conv1 -> t tile); warps 10-17: epilogue 2 (output)
+        const int q = warp & 3;                                             // TMEM lane quarter
+        const int h = ((warp - 2) >> 2) & 1;                                // column half
+        const int ew = (warp - 2) & 7;                                      // index inside the group of eight
         const int row = q * 32 + lane;
-        const int swz = (BK == 64) ? (row & 7) : ((row >> 1) & 3);         // t tile / staging slab (row-relative)
+        const int n_base = h * CH;
         const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
         int it = 0;
-        int e2_stage = 0;                                                   // A stage of the tile epilogue2 handles next
-
-        auto epilogue2 = [&](int j, int mt, int b) {
-            const int bb = j & 1; const uint32_t ph = (uint32_t)((j >> 1) & 1);
-            const int o = mt * cfg.valid + row;                             // output row of this thread
-            const bool valid = row < cfg.valid && o < p.L;
-            // conv2(j) complete  =>  conv1(j) complete  =>  this tile's input stage is loaded and no longer
-            // needed by the tensor core; only now may it be read (residual) and handed back to the producer
-            mbar_wait(&acc2_full[bb], ph);
-            tc_fence_after();
-            // residual: lrelu(y) sits in the input halo tile at row (row + P2 + p1d)
-            uint4 rres[C / 8];
-            {
-                const int ra = row + P2 + p1d;
-                const int swa = (BK == 64) ? (ra & 7) : ((ra >> 1) & 3);
-                const uint8_t* rb = smA + e2_stage * a_alloc + ra * ROW_BYTES;
-#pragma unroll
-                for (int i = 0; i < C / 8; ++i) rres[i] = *reinterpret_cast<const uint4*>(rb + ((i ^ swa) << 4));
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_empty[e2_stage]);
-            if (++e2_stage == cfg.a_stages) e2_stage = 0;
-            if (lane == 0) tma_store_wait_read();
-            __syncwarp();
-            const uint32_t taddr = tmem_base + (uint32_t)(2 * C + bb * C) + lane_addr;
-            uint8_t* slab = smO + q * O_SLAB + lane * ROW_BYTES;
-            const int swo = (BK == 64) ? (lane & 7) : ((lane >> 1) & 3);
-#pragma unroll
-            for (int c = 0; c < C / 16; ++c) {
-                uint32_t r[16];
-                tmem_ld16(taddr + c * 16, r);
-                tmem_ld_wait();
-                const int n = c * 16;
-                float v[16];
-#pragma unroll
-                for (int jj = 0; jj < 16; ++jj) v[jj] = fmaf(__uint_as_float(r[jj]), p.alpha2, p.b2[n + jj]);
-                const __half2* h0 = reinterpret_cast<const __half2*>(&rres[2 * c]);
-                const __half2* h1 = reinterpret_cast<const __half2*>(&rres[2 * c + 1]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 a = __half22float2(h0[i]), bq = __half22float2(h1[i]);
-                    v[2 * i] += lrelu(a.x, p.res_inv_slope); v[2 * i + 1] += lrelu(a.y, p.res_inv_slope);
-                    v[8 + 2 * i] += lrelu(bq.x, p.res_inv_slope); v[8 + 2 * i + 1] += lrelu(bq.y, p.res_inv_slope);
-                }
-                if (p.sum_h && valid) {
-                    float ss[16];
-                    load16h(p.sum_h + ((long long)b * p.L + o) * C + n, ss);
-#pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) v[jj] += ss[jj];
-                }
-                uint4 u0, u1;
-                __half2* p0 = reinterpret_cast<__half2*>(&u0);
-                __half2* p1 = reinterpret_cast<__half2*>(&u1);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    p0[i] = __floats2half2_rn(lrelu(v[2 * i], p.out_slope), lrelu(v[2 * i + 1], p.out_slope));
-                    p1[i] = __floats2half2_rn(lrelu(v[8 + 2 * i], p.out_slope), lrelu(v[8 + 2 * i + 1], p.out_slope));
-                }
-                *reinterpret_cast<uint4*>(slab + (((2 * c) ^ swo) << 4)) = u0;
-                *reinterpret_cast<uint4*>(slab + (((2 * c + 1) ^ swo) << 4)) = u1;
-            }
-            tc_fence_before();
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&acc2_empty[bb]);
-                // rows [q*32, q*32+32) of the tile; the last warp only owns `valid - 96` rows
-                const int r0 = mt * cfg.valid + q * 32;
-                if (q < 3) tma_store_3d(&tmO, smO + q * O_SLAB, 0, r0, b);
-                else tma_store_3d(&tmOtail, smO + q * O_SLAB, 0, r0, b);
-                tma_store_commit();
-            }
-        };
-
-        const bool is_e1 = warp < 8;      // warps 4-7: epilogue 1 (conv1 -> t tile); warps 8-11: epilogue 2 (output)
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-            const int mt = tile % cfg.m_tiles, b = tile / cfg.m_tiles;
+        if (is_e1) {
             // ---- epilogue 1: t = lrelu(c1 + b1) -> fp16 swizzled smem tile (zeros outside the utterance)
-            if (is_e1) {
-                const int bb = it & 1; const uint32_t ph = (uint32_t)((it >> 1) & 1);
+            const int swz = (BK == 64) ? (row & 7) : ((row >> 1) & 3);
+            int bb = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+                const int mt = tile % cfg.m_tiles;
                 mbar_wait(&acc1_full[bb], ph);
                 mbar_wait(&t_empty[bb], ph ^ 1);
                 tc_fence_after();
                 const int trow = mt * cfg.valid - P2 + row;                 // global row of this t row
                 const bool inside = trow >= 0 && trow < p.L;
-                const uint32_t taddr = tmem_base + (uint32_t)(bb * C) + lane_addr;
+                const uint32_t taddr = tmem_base + (uint32_t)(bb * C + n_base) + lane_addr;
                 uint8_t* trow_ptr = smT + bb * T_ALLOC + row * ROW_BYTES;
 #pragma unroll
-                for (int c = 0; c < C / 16; ++c) {
+                for (int c = 0; c < CH / 16; ++c) {
                     uint32_t r[16];
                     tmem_ld16(taddr + c * 16, r);
                     tmem_ld_wait();
-                    uint4 u0, u1;
-                    __half2* p0 = reinterpret_cast<__half2*>(&u0);
-                    __half2* p1 = reinterpret_cast<__half2*>(&u1);
+                    float v[16];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float a0 = lrelu(__uint_as_float(r[2 * i]) + p.b1[c * 16 + 2 * i], p.t_slope);
-                        float a1 = lrelu(__uint_as_float(r[2 * i + 1]) + p.b1[c * 16 + 2 * i + 1], p.t_slope);
-                        float c0 = lrelu(__uint_as_float(r[8 + 2 * i]) + p.b1[c * 16 + 8 + 2 * i], p.t_slope);
-                        float c1 = lrelu(__uint_as_float(r[8 + 2 * i + 1]) + p.b1[c * 16 + 8 + 2 * i + 1], p.t_slope);
-                        if (!inside) { a0 = a1 = c0 = c1 = 0.f; }
-                        p0[i] = __floats2half2_rn(a0, a1);
-                        p1[i] = __floats2half2_rn(c0, c1);
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 bq = *reinterpret_cast<const float4*>(s_b1 + n_base + c * 16 + 4 * j);
+                        v[4 * j] = lrelu_fwd(__uint_as_float(r[4 * j]) + bq.x, p.t_slope);
+                        v[4 * j + 1] = lrelu_fwd(__uint_as_float(r[4 * j + 1]) + bq.y, p.t_slope);
+                        v[4 * j + 2] = lrelu_fwd(__uint_as_float(r[4 * j + 2]) + bq.z, p.t_slope);
+                        v[4 * j + 3] = lrelu_fwd(__uint_as_float(r[4 * j + 3]) + bq.w, p.t_slope);
                     }
-                    *reinterpret_cast<uint4*>(trow_ptr + (((2 * c) ^ swz) << 4)) = u0;
-                    *reinterpret_cast<uint4*>(trow_ptr + (((2 * c + 1) ^ swz) << 4)) = u1;
+                    uint4 u0 = make_uint4(0u, 0u, 0u, 0u), u1 = u0;
+                    if (inside) {
+                        __half2* p0 = reinterpret_cast<__half2*>(&u0);
+                        __half2* p1 = reinterpret_cast<__half2*>(&u1);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            p0[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                            p1[i] = __floats2half2_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+                        }
+                    }
+                    const int j0 = n_base / 8 + 2 * c;                      // 16-byte chunk index inside the row
+                    *reinterpret_cast<uint4*>(trow_ptr + ((j0 ^ swz) << 4)) = u0;
+                    *reinterpret_cast<uint4*>(trow_ptr + (((j0 + 1) ^ swz) << 4)) = u1;
                 }
                 tc_fence_before();
                 fence_proxy_async_smem();          // t tile (generic-proxy writes) -> visible to tcgen05.mma
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&acc1_empty[bb]); mbar_arrive(&t_full[bb]); }
+                if (++bb == nb) { bb = 0; ph ^= 1; }
             }
-            // ---- epilogue 2 (its own warps, running concurrently with epilogue 1 of later tiles)
-            if (!is_e1) epilogue2(it, mt, b);
+        } else {
+            // ---- epilogue 2: y' = lrelu_out(c2 + b2 + inv_lrelu(a) [+ sum]) -> staged + TMA store (direct for C = 32)
+            const int swo = (OROW == 64) ? ((lane >> 1) & 3) : (lane & 1);
+            uint8_t* slab = smO + ew * O_SLAB + lane * OROW;
+            // residual lrelu(y) [+ MRF partial sum] of this thread's output row: global reads (L2-hot: the rows were
+            // fetched by the tile's TMA a moment ago), software-pipelined ONE TILE AHEAD so that their latency never
+            // sits between the accumulator wait and the stores
+            uint4 rnext[CH / 8], snext[HAS_SUM ? CH / 8 : 1];
+            auto prefetch = [&](int tile_) {
+                const int mt_ = tile_ % cfg.m_tiles, b_ = tile_ / cfg.m_tiles;
+                const int o_ = mt_ * cfg.valid + row;
+                const bool ok = tile_ < tiles && row < cfg.valid && o_ < p.L;
+                const long long g_ = ((long long)b_ * p.L + o_) * C + n_base;
+#pragma unroll
+                for (int i = 0; i < CH / 8; ++i) {
+                    rnext[i] = ok ? reinterpret_cast<const uint4*>(p.a + g_)[i] : make_uint4(0u, 0u, 0u, 0u);
+                    if constexpr (HAS_SUM) snext[i] = ok ? reinterpret_cast<const uint4*>(p.sum_h + g_)[i] : make_uint4(0u, 0u, 0u, 0u);
+                }
+            };
+            prefetch((int)blockIdx.x);
+            int bb = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+                const int mt = tile % cfg.m_tiles, b = tile / cfg.m_tiles;
+                const int o = mt * cfg.valid + row;                         // output row of this thread
+                const bool valid = row < cfg.valid && o < p.L;
+                const long long goff = ((long long)b * p.L + o) * C + n_base;
+                uint4 rres[CH / 8], rsum[HAS_SUM ? CH / 8 : 1];
+#pragma unroll
+                for (int i = 0; i < CH / 8; ++i) { rres[i] = rnext[i]; if constexpr (HAS_SUM) rsum[i] = snext[i]; }
+                prefetch(tile + (int)gridDim.x);
+                mbar_wait(&acc2_full[bb], ph);
+                tc_fence_after();
+                if (TMA_STORE) {
+                    if (lane == 0) tma_store_wait_read();                   // previous store has finished reading the slab
+                    __syncwarp();
+                }
+                const uint32_t taddr = tmem_base + (uint32_t)(RB_MAX_NB * C + bb * C + n_base) + lane_addr;
+#pragma unroll
+                for (int c = 0; c < CH / 16; ++c) {
+                    uint32_t r[16];
+                    tmem_ld16(taddr + c * 16, r);
+                    tmem_ld_wait();
+                    const int n = n_base + c * 16;
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 bq = *reinterpret_cast<const float4*>(s_b2 + n + 4 * j);
+                        v[4 * j] = fmaf(__uint_as_float(r[4 * j]), p.alpha2, bq.x);
+                        v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), p.alpha2, bq.y);
+                        v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), p.alpha2, bq.z);
+                        v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), p.alpha2, bq.w);
+                    }
+                    const __half2* h0 = reinterpret_cast<const __half2*>(&rres[2 * c]);
+                    const __half2* h1 = reinterpret_cast<const __half2*>(&rres[2 * c + 1]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 a = __half22float2(h0[i]), bq = __half22float2(h1[i]);
+                        v[2 * i] += lrelu_inv(a.x, p.res_inv_slope); v[2 * i + 1] += lrelu_inv(a.y, p.res_inv_slope);
+                        v[8 + 2 * i] += lrelu_inv(bq.x, p.res_inv_slope); v[8 + 2 * i + 1] += lrelu_inv(bq.y, p.res_inv_slope);
+                    }
+                    if constexpr (HAS_SUM) {
+                        const __half2* s0 = reinterpret_cast<const __half2*>(&rsum[2 * c]);
+                        const __half2* s1 = reinterpret_cast<const __half2*>(&rsum[2 * c + 1]);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 a = __half22float2(s0[i]), bq = __half22float2(s1[i]);
+                            v[2 * i] += a.x; v[2 * i + 1] += a.y; v[8 + 2 * i] += bq.x; v[8 + 2 * i + 1] += bq.y;
+                        }
+                    }
+                    uint4 u0, u1;
+                    __half2* p0 = reinterpret_cast<__half2*>(&u0);
+                    __half2* p1 = reinterpret_cast<__half2*>(&u1);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        p0[i] = __floats2half2_rn(lrelu_fwd(v[2 * i], p.out_slope), lrelu_fwd(v[2 * i + 1], p.out_slope));
+                        p1[i] = __floats2half2_rn(lrelu_fwd(v[8 + 2 * i], p.out_slope), lrelu_fwd(v[8 + 2 * i + 1], p.out_slope));
+                    }
+                    if (TMA_STORE) {
+                        *reinterpret_cast<uint4*>(slab + (((2 * c) ^ swo) << 4)) = u0;
+                        *reinterpret_cast<uint4*>(slab + (((2 * c + 1) ^ swo) << 4)) = u1;
+                    } else if (valid) {
+                        __half* op = p.out_h + goff + c * 16;
+                        *reinterpret_cast<uint4*>(op) = u0;
+                        *reinterpret_cast<uint4*>(op + 8) = u1;
+                    }
+                }
+                tc_fence_before();
+                if (TMA_STORE) fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&acc2_empty[bb]);
+                    if (TMA_STORE) {
+                        // rows [q*32, q*32+32) of the tile; the last lane quarter only owns `valid - 96` rows
+                        const int r0 = mt * cfg.valid + q * 32;
+                        if (q < 3) tma_store_3d(&tmO, smO + ew * O_SLAB, n_base, r0, b);
+                        else tma_store_3d(&tmOtail, smO + ew * O_SLAB, n_base, r0, b);
+                        tma_store_commit();
+                    }
+                }
+                if (++bb == cfg.nb2) { bb = 0; ph ^= 1; }
+            }
+            if (TMA_STORE && lane == 0) tma_store_wait_all();
         }
-        if (!is_e1 && lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
-template <int C, int TAPS>
+template <int C, int TAPS, bool HAS_SUM>
 int launch_rb_cfg(const UmmaResblockParams& p, cudaStream_t s) {
     constexpr int BK = C;
     constexpr int ROW_BYTES = BK * 2;
     constexpr int ROW_ALIGN = 1024 / ROW_BYTES;
     constexpr size_t W_BYTES = (size_t)2 * TAPS * C * ROW_BYTES;
-    constexpr size_t T_BYTES = (size_t)2 * T_ROWS_ALLOC * ROW_BYTES;
-    constexpr size_t O_BYTES = (size_t)4 * 32 * ROW_BYTES;
-    constexpr size_t FIXED = (2 * RB_MAX_STAGES + 1 + 12) * 8 + 16 + 1024;
+    constexpr size_t T_ALLOC = (size_t)T_ROWS_ALLOC * ROW_BYTES;
+    constexpr size_t O_BYTES = (size_t)8 * 32 * C;         // 8 epilogue-2 warps x 32 rows x C/2 fp16
+    constexpr size_t FIXED = (2 * RB_MAX_STAGES + 1 + 6 * RB_MAX_NB) * 8 + 32 + 2 * C * 4 + 1024;
     constexpr size_t LIMIT = 227 * 1024;
     static_assert((T_ROWS_ALLOC * ROW_BYTES) % 1024 == 0, "t tile must keep the swizzle alignment");
 
@@ -318,13 +385,26 @@ int launch_rb_cfg(const UmmaResblockParams& p, cudaStream_t s) {
     cfg.rows_alloc = (cfg.box_rows + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
     cfg.m_tiles = (p.L + cfg.valid - 1) / cfg.valid;
     const size_t a_alloc = (size_t)cfg.rows_alloc * ROW_BYTES;
-    const size_t rest = W_BYTES + T_BYTES + O_BYTES + FIXED;
-    if (rest + 2 * a_alloc > LIMIT) return CMTTS_ERR_UNSUPPORTED;
+    // deepest conv1 -> conv2 lag that still leaves room for >= 3 input stages (CMTTS_RB_NB overrides, 2..4)
+    static int nb_env = -1;
+    if (nb_env < 0) { const char* e = getenv("CMTTS_RB_NB"); nb_env = e ? atoi(e) : 0; }
+    cfg.nb = 0;
+    size_t rest = 0;
+    for (int nb = RB_MAX_NB; nb >= 2; --nb) {
+        if (nb_env >= 2 && nb_env <= RB_MAX_NB && nb != nb_env) continue;
+        rest = W_BYTES + (size_t)nb * T_ALLOC + O_BYTES + FIXED;
+        const size_t min_stages = (nb == 2 || nb == nb_env) ? 2 : 3;
+        if (rest + min_stages * a_alloc <= LIMIT) { cfg.nb = nb; break; }
+    }
+    if (cfg.nb == 0) return CMTTS_ERR_UNSUPPORTED;
+    static int nb2_env = -1;
+    if (nb2_env < 0) { const char* e = getenv("CMTTS_RB_NB2"); nb2_env = e ? atoi(e) : 0; }
+    cfg.nb2 = (nb2_env >= 2 && nb2_env <= RB_MAX_NB) ? nb2_env : RB_MAX_NB;
     size_t st = (LIMIT - rest) / a_alloc;
     cfg.a_stages = (int)(st > RB_MAX_STAGES ? RB_MAX_STAGES : st);
     const size_t smem = rest + (size_t)cfg.a_stages * a_alloc;
 
-    auto kern = umma_resblock_kernel<C, TAPS>;
+    auto kern = umma_resblock_kernel<C, TAPS, HAS_SUM>;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIMIT) != cudaSuccess) {
@@ -337,14 +417,14 @@ int launch_rb_cfg(const UmmaResblockParams& p, cudaStream_t s) {
     const long long bs = (long long)p.L * C;
     if (!make_act_map(&a_map, p.a, C, p.L, p.B, C, bs, BK, cfg.box_rows) ||
         !make_w_map(&w1_map, p.w1, C, TAPS * C, BK, C) || !make_w_map(&w2_map, p.w2, C, TAPS * C, BK, C) ||
-        !make_act_map(&o_map, p.out_h, C, p.L, p.B, C, bs, BK, 32) ||
-        !make_act_map(&ot_map, p.out_h, C, p.L, p.B, C, bs, BK, cfg.valid - 96)) {
+        !make_act_map(&o_map, p.out_h, C, p.L, p.B, C, bs, 32, 32) ||              // per-warp box: C/2 (<= 32) channels
+        !make_act_map(&ot_map, p.out_h, C, p.L, p.B, C, bs, 32, cfg.valid - 96)) {
         cmtts_set_error("umma_resblock: cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
         return CMTTS_ERR_CUDA;
     }
     const int tiles = p.B * cfg.m_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, 384, smem, s>>>(a_map, w1_map, w2_map, o_map, ot_map, p, cfg);
+    kern<<<grid, RB_THREADS, smem, s>>>(a_map, w1_map, w2_map, o_map, ot_map, p, cfg);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }
@@ -356,11 +436,14 @@ int launch_umma_resblock(const UmmaResblockParams& p, cudaStream_t s) {
     if (p.B == 0 || p.L == 0) return CMTTS_OK;
     if (p.dil < 1 || !p.a || !p.w1 || !p.w2 || !p.b1 || !p.b2 || !p.out_h) return CMTTS_ERR_UNSUPPORTED;
     if (((uintptr_t)p.a % 16) || ((uintptr_t)p.out_h % 16)) return CMTTS_ERR_UNSUPPORTED;
+    // max / min form of leaky-ReLU: forward slopes in (0, 1], inverse slope >= 1
+    if (!(p.t_slope > 0.f && p.t_slope <= 1.f && p.out_slope > 0.f && p.out_slope <= 1.f && p.res_inv_slope >= 1.f))
+        return CMTTS_ERR_UNSUPPORTED;
 #define RB_DISPATCH(C_)                                                   \
     switch (p.taps) {                                                     \
-        case 3: return launch_rb_cfg<C_, 3>(p, s);                        \
-        case 7: return launch_rb_cfg<C_, 7>(p, s);                        \
-        case 11: return launch_rb_cfg<C_, 11>(p, s);                      \
+        case 3: return p.sum_h ? launch_rb_cfg<C_, 3, true>(p, s) : launch_rb_cfg<C_, 3, false>(p, s);      \
+        case 7: return p.sum_h ? launch_rb_cfg<C_, 7, true>(p, s) : launch_rb_cfg<C_, 7, false>(p, s);      \
+        case 11: return p.sum_h ? launch_rb_cfg<C_, 11, true>(p, s) : launch_rb_cfg<C_, 11, false>(p, s);   \
         default: return CMTTS_ERR_UNSUPPORTED;                            \
     }
     if (p.C == 32) { RB_DISPATCH(32) }

@@ -27,6 +27,18 @@ from .sampler import karras_sample_tts, sampler_plan
 from .vocoder import Generator, vocoder_infer
 
 
+def checkpoint_path(model_path: str, step: int, kind: str = "model") -> str:
+    """`<model_path>/CMDenoiserTTS/{model|target_model|teacher_model}{step:06d}.pt` or `ema_<rate>_{step:06d}.pt`
+    (written by train_util.py:890-917; synthesize.py:44-48 reads the first)."""
+    if kind in ("model", "target_model", "teacher_model"):
+        name = "{}{:06d}.pt".format(kind, int(step))
+    elif kind.startswith("ema_"):
+        name = "{}_{:06d}.pt".format(kind, int(step))
+    else:
+        raise ValueError(f"unknown checkpoint kind {kind!r}")
+    return os.path.join(model_path, "CMDenoiserTTS", name)
+
+
 def to_device(data, device):
     """utils/tools.py:103-112 — the 7-tuple inference batch:
     (ids, raw_texts, speakers, texts, src_lens, max_src_len, spker_embeds)."""
@@ -45,9 +57,15 @@ class CMTotalTTSSynthesize:
     """synthesize.py:35-153."""
 
     def __init__(self, model_path, model_step_num, args, preprocess_config, model_config, train_config,
-                 p_control=1.0, e_control=1.0, d_control=1.0, device=None, spec: Optional[ModelSpec] = None):
+                 p_control=1.0, e_control=1.0, d_control=1.0, device=None, spec: Optional[ModelSpec] = None,
+                 checkpoint: str = "model", forward_controls: bool = False):
+        """`checkpoint` picks which of the trainer's files is loaded (train_util.py:890-917): "model" (what the
+        reference's synthesize.py:44-48 reads), "target_model", "teacher_model" or "ema_<rate>" — all are flat
+        CMTotalTTS state_dicts.  `forward_controls=True` hands p/e/d_control to the variance adaptor; the reference
+        parses them (synthesize.py:275-292) but never forwards them (:96-102), so the default keeps them inert."""
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.CMDenoiserTTS_path = os.path.join(model_path, "CMDenoiserTTS", "model{:06d}.pt".format(model_step_num))
+        self.CMDenoiserTTS_path = checkpoint_path(model_path, model_step_num, checkpoint)
+        self.forward_controls = bool(forward_controls)
         self.args = args
         self.train_config = train_config
         self.p_control, self.e_control, self.d_control = p_control, e_control, d_control
@@ -82,7 +100,9 @@ class CMTotalTTSSynthesize:
     def synthesize(self, batch, T: Optional[int] = None, generator=None, trace=None):
         T = int(T if T is not None else getattr(self.args, "T", 1))
         kw = {"speakers": batch[2], "texts": batch[3], "src_lens": batch[4], "spker_embeds": batch[-1]}
-        out_dict = self.duration_pitch_energy_net(**kw)
+        ctl = {"p_control": self.p_control, "e_control": self.e_control, "d_control": self.d_control} \
+            if self.forward_controls else {}
+        out_dict = self.duration_pitch_energy_net(**kw, **ctl)
         batch_size, seq_len, _ = out_dict["cond"].size()
         sampler, steps, ts = sampler_plan(T)
         s = self.model.spec

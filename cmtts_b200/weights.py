@@ -94,12 +94,35 @@ TC_W_SCALE = 1024.0
 
 def split_f16(w: torch.Tensor, scale: float = TC_W_SCALE):
     """fp32 -> (hi, lo) fp16 with (hi + lo) / scale == w to ~22 bits (hi = fp16(w s), lo = fp16(w s - hi))."""
-    ws = w.to(torch.float32) * scale
+    wide = torch.float64 if w.dtype == torch.float64 else torch.float32   # fp64 in: weights derived on the host
+    ws = w.to(wide) * scale
     if float(ws.abs().max()) >= 60000.0:
         raise ValueError("weight too large for the fp16 hi/lo split")
     hi = ws.to(torch.float16)
-    lo = (ws - hi.to(torch.float32)).to(torch.float16)
+    lo = (ws - hi.to(wide)).to(torch.float16)
     return hi, lo
+
+
+def fused_recurrence_weights(sd: Dict[str, torch.Tensor], l: int, C: int, H: int):
+    """Operands of layer l of the denoiser's y-recurrence (fp64): weights (2C, C + H) and bias (2C,).
+
+    With y_l = x_l + Wc_l cond + bc_l + step_l + spk_l (the k=3 conv's input, model/blocks.py:669-678) and
+    r = 1/sqrt(2): y_{l+1} = [r Wo_l[:C] | Wc_{l+1} - r Wc_l] [g_l ; cond] + r y_l + const, so the rows < C are
+    that block matrix, the rows >= C the skip half [Wo_l[C:] | 0] of the output projection (:683-686)."""
+    r = 1.0 / math.sqrt(2.0)
+    p, pn = f"net.residual_layers.{l}.", f"net.residual_layers.{l + 1}."
+    wo = sd[p + "output_projection.conv.weight"][:, :, 0].double()
+    bo = sd[p + "output_projection.conv.bias"].double()
+    wc = sd[p + "conditioner_projection.conv.weight"][:, :, 0].double()
+    bc = sd[p + "conditioner_projection.conv.bias"].double()
+    wcn = sd[pn + "conditioner_projection.conv.weight"][:, :, 0].double()
+    bcn = sd[pn + "conditioner_projection.conv.bias"].double()
+    wf = torch.zeros(2 * C, C + H, dtype=torch.float64)
+    wf[:C, :C] = r * wo[:C]
+    wf[:C, C:] = wcn - r * wc
+    wf[C:, :C] = wo[C:]
+    bf = torch.cat([r * bo[:C] + bcn - r * bc, bo[C:]])
+    return wf, bf
 
 
 class _Table:
@@ -268,6 +291,14 @@ class PackedAcoustic:
         for w in (w_in, sd["net.skip_projection.conv.weight"][:, :, 0].contiguous()):
             hi, lo = split_f16(w)
             dn16.add(hi); dn16.add(lo)
+        # y-recurrence of the residual stack (csrc/pipeline.cu, cmtts_denoiser_forward_tc): per layer l < last,
+        #   [ r Wo_l[:C] | Wc_{l+1} - r Wc_l ]   rows < C  : y_{l+1}  (K = C + H)
+        #   [   Wo_l[C:] |         0         ]   rows >= C : skip     (the kernel only contracts these over K = C)
+        # derived in fp64, then split into fp16 hi/lo like every other operand
+        for l in range(s.res_layers - 1):
+            wf, bf = fused_recurrence_weights(sd, l, C, s.hidden)
+            hi, lo = split_f16(wf)
+            dn16.add(hi); dn16.add(lo); dn16.add(bf.to(torch.float32))
         self.dn16 = dn16.finish()
 
         def add_pair(tab, w):
@@ -343,6 +374,11 @@ class PackedHifiGan:
                     t16.add(conv_w_nk(sd[f"resblocks.{r}.convs1.{m}.weight"]).to(torch.float16)); t16.add(sd[f"resblocks.{r}.convs1.{m}.bias"])
                     t16.add(conv_w_nk(sd[f"resblocks.{r}.convs2.{m}.weight"]).to(torch.float16)); t16.add(sd[f"resblocks.{r}.convs2.{m}.bias"])
         t16.add(wp[0].t().contiguous()); t16.add(sd["conv_post.bias"].reshape(1).repeat(4))
+        # conv_pre on the hi/lo tensor-core kernel: [k][C0][128] (mel channels zero-padded to one 128-wide K block)
+        w_pre = torch.zeros(sd["conv_pre.weight"].shape[2], C0, 128)
+        w_pre[:, :, :hspec.n_mels] = conv_w_nk(sd["conv_pre.weight"])
+        hi, lo = split_f16(w_pre)
+        t16.add(hi); t16.add(lo)
         self.table16 = t16.finish()
         dil = [d for ds in hspec.resblock_dilation_sizes for d in ds]
         cfg = [len(hspec.upsample_rates), C0, nk, nd, 7, wp.shape[2]] + list(hspec.upsample_rates) + taps + shift0 \

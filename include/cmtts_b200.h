@@ -175,7 +175,7 @@ int cmtts_round_durations(const float* log_d, float d_control, const int64_t* sr
 typedef struct cmtts_umma_desc {
     int32_t B, M, Lin, N, Cin, taps;
     int32_t shift[16];
-    int32_t split, epi;                   /* epi: 0 VOC, 1 DN_COND, 2 DN_GATE, 3 DN_OUT */
+    int32_t split, epi;                   /* epi: 0 VOC, 1 DN_COND, 2 DN_GATE, 3 DN_OUT, 4 F32 */
     int32_t a_ld, res_ld, out_ld, x_ld;
     int64_t a_bstride, res_bstride, out_bstride, x_bstride, addvec_bstride;
     float alpha, res_inv_slope, out_slope, out_scale;
@@ -191,7 +191,9 @@ int cmtts_f32_to_f16(const float* x, void* hi, void* lo, int64_t rows, int64_t C
 
 /* D1/D3 + S4 on tensor cores: same contract as cmtts_denoiser_forward; `w16` holds per layer
  * {cond_w hi, lo [C][H]; k3_w hi, lo [3*2C][C] (gate/filter interleaved per 64); out_w hi, lo [2C][C];
- *  out_b fp32 [2C]}, then {in_w hi, lo [C][128] (K zero-padded); skip_w hi, lo [C][C]};
+ *  out_b fp32 [2C]}, then {in_w hi, lo [C][128] (K zero-padded); skip_w hi, lo [C][C]}, then per layer
+ * l < res_layers-1 the y-recurrence operands {fused_w hi, lo [2C][C+H]; fused_b fp32 [2C]} with
+ * fused_w = [[r Wo_l[:C] | Wc_{l+1} - r Wc_l], [Wo_l[C:] | 0]], r = 1/sqrt(2) (cmtts_b200/weights.py);
  * cond_hi/cond_lo are the fp16 split of the conditioner (cmtts_f32_to_f16). */
 size_t cmtts_denoiser_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t L);
 int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const* w, const void* const* w16,
