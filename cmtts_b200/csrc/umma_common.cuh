@@ -118,6 +118,16 @@ __device__ __forceinline__ void tma_load_2d_elect(void* dst, const CUtensorMap* 
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// L2 prefetch of a TMA box (no shared memory, no barrier): issued several tiles ahead so that the real load, which can
+// only be issued once a shared-memory stage frees up, finds its data in L2 instead of paying a DRAM round trip
+__device__ __forceinline__ void tma_prefetch_3d_elect(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];\n\t}"
+        ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 // value known to be identical in all lanes -> move it to a uniform register (REDUX writes a UR)
 __device__ __forceinline__ uint32_t make_uniform(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

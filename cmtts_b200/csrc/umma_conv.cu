@@ -7,7 +7,7 @@
 //   row (t0 + shift[s]); rows outside [0, L) of an utterance are zero-filled by the TMA unit (3-D
 //   tensor map {C, L, B}), which is exactly the conv's zero padding and keeps utterances apart;
 // * warp-specialised persistent CTA (one per SM): warp 0 = TMA producer, warp 1 = single-thread
-//   tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4-11 = epilogue (one thread per accumulator
+//   tcgen05.mma issuer (split mode: warp 3 issues the cross terms), warp 2 = TMEM allocator, warps 4-11 = epilogue (one thread per accumulator
 //   row / TMEM lane and column half; global operands of the epilogue are prefetched into registers
 //   before the accumulator wait).  mbarrier ring between producer and MMA, double-buffered TMEM accumulator
 //   between MMA and epilogue so tile i+1's MMAs overlap tile i's epilogue;
@@ -112,8 +112,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int kblocks2 = SPLIT ? p.Cin2 / BK : 0;         // extra k-blocks of heavy tiles (second operand)
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+        // SPLIT: two issuing warps (main products / cross terms) each commit to `empty` and `tfull`
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], SPLIT ? 2 : 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], SPLIT ? 2 : 1); mbar_init(&tempty[i], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -137,6 +138,26 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             int nt, mt, b; bool heavy;
             while (ts.next(nt, mt, b, heavy)) {
                 const int kblocks = kblocks1 + (heavy ? kblocks2 : 0);
+                {
+                    // pull the NEXT tile's activation boxes into L2 now: the real loads can only be issued as stages
+                    // free up, and for operands that come from DRAM (conditioner, a just-written g) a 3-stage ring
+                    // does not hold enough bytes in flight to hide that latency
+                    TileSched ahead = ts;
+                    int nt2, mt2, b2; bool heavy2;
+                    if ((p.dbg & 128) && ahead.next(nt2, mt2, b2, heavy2) && (mt2 != mt || b2 != b)) {
+                        for (int kb = 0; kb < kblocks1; ++kb) {
+                            const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * BK;
+                            if (tap > 0) break;                       // the taps of a conv re-read the same rows (+-halo)
+                            tma_prefetch_3d_elect(&tmA0, c0, mt2 * BM + p.shift[0], b2);
+                            if (SPLIT) tma_prefetch_3d_elect(&tmA1, c0, mt2 * BM + p.shift[0], b2);
+                        }
+                        if (SPLIT && heavy2)
+                            for (int kb = 0; kb < kblocks2; ++kb) {
+                                tma_prefetch_3d_elect(&tmA2, kb * BK, mt2 * BM, b2);
+                                tma_prefetch_3d_elect(&tmA3, kb * BK, mt2 * BM, b2);
+                            }
+                    }
+                }
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx_elect(&full[stage], STAGE_BYTES);
@@ -161,9 +182,14 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================================ MMA issuer ================================
+    } else if (warp == 1 || (SPLIT && warp == 3)) {
+        // ================================ MMA issuer(s) ================================
+        // SPLIT: warp 1 issues the main products A_hi W_hi (accumulator 0), warp 3 the cross terms A_hi W_lo +
+        // A_lo W_hi (accumulator 1).  One tcgen05.mma costs ~10 uniform-datapath instructions of descriptor set-up
+        // (~60-70 cycles) against 64 tensor-pipe cycles for 128x128x16, so a single issuer kept the pipe ~65 % busy;
+        // the accumulators are disjoint, so the two instruction streams need no ordering between them.
         {
+            const bool cross = SPLIT && warp == 3;
             const uint32_t tmem_u = make_uniform(tmem_base);
             const uint32_t idesc = make_idesc(BM, BN);
             int stage = 0; uint32_t phase = 0;
@@ -182,11 +208,18 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     const uint32_t sb = sa + NOP * A_BYTES;
                     const uint64_t a0 = make_smem_desc<BK>(sa), b0 = make_smem_desc<BK>(sb);
                     const uint64_t a1 = make_smem_desc<BK>(sa + A_BYTES), b1 = make_smem_desc<BK>(sb + B_BYTES);
+                    if (p.dbg & 32) {
+                        // timing ablation: no MMAs
+                    } else if (!cross) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 x 16B units along K
-                        umma_f16_pred(d_tmem, a0 + adv, b0 + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u, 0u);
-                        if (SPLIT) {
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 x 16B units along K
+                            umma_f16_pred(d_tmem, a0 + adv, b0 + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u, 0u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 2);
                             umma_f16_pred(d_tmem + BN, a0 + adv, b1 + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u, 0u);
                             umma_f16_pred(d_tmem + BN, a1 + adv, b0 + adv, idesc, 1u, 0u);
                         }
@@ -217,25 +250,6 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             uint4 pre[16];
             bool have_pre = false;
             if constexpr (SPLIT) {
-                if (p.epi == UEPI_DN_OUTY) {
-                    // The y / skip segments this thread will read for its NEXT tile usually sit in DRAM (the layer's
-                    // working set exceeds what L2 retains); pull them into L2 one tile ahead so the register
-                    // prefetch below costs an L2 hit instead of a DRAM round trip in front of every epilogue.
-                    TileSched ahead = ts;
-                    int nt2, mt2, b2; bool heavy2;
-                    if (ahead.next(nt2, mt2, b2, heavy2)) {
-                        const int t2 = mt2 * BM + row, m0 = nt2 * BN + h * BNH;
-                        if (t2 < p.M) {
-                            if (m0 < p.n_k2) {
-                                const long long o2 = (long long)b2 * p.out_bstride + (long long)t2 * p.out_ld + m0;
-                                prefetch_l2(p.out_h + o2); prefetch_l2(p.out_lo + o2);
-                            } else if (p.skip_accumulate) {
-                                const float* s2 = p.skip_f32 + (long long)b2 * p.x_bstride + (long long)t2 * p.x_ld + (m0 - p.n_k2);
-                                prefetch_l2(s2); prefetch_l2(s2 + 32);
-                            }
-                        }
-                    }
-                }
                 const float* src = nullptr;
                 if (p.epi == UEPI_DN_COND || (p.epi == UEPI_F32 && p.x_f32 != nullptr && n0 < p.n_valid))
                     src = p.x_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + n0;
@@ -247,12 +261,12 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     if (n0 >= p.n_k2 && p.skip_accumulate)
                         src = p.skip_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + (n0 - p.n_k2);
                 }
-                if (src && valid) {
+                if (src && valid && !(p.dbg & 8)) {
                     have_pre = true;
 #pragma unroll
                     for (int i = 0; i < BNH / 4; ++i) pre[i] = reinterpret_cast<const uint4*>(src)[i];
                 }
-                if (p.epi == UEPI_DN_OUTY && n0 < p.n_k2 && valid) {
+                if (p.epi == UEPI_DN_OUTY && n0 < p.n_k2 && valid && !(p.dbg & 8)) {
                     // y (fp16 hi/lo, updated in place): hi halves in pre[0, BNH/8), lo halves in pre[BNH/8, BNH/4)
                     have_pre = true;
                     const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n0;
@@ -273,7 +287,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(abuf * ACC_COLS) + ((uint32_t)(q * 32) << 16);
 
-            if (SPLIT && p.epi == UEPI_DN_GATE) {
+            if (p.dbg & 64) {
+                // timing ablation: the epilogue does nothing
+            } else if (SPLIT && p.epi == UEPI_DN_GATE) {
                 // tile columns [0, BN/2) are gates, [BN/2, BN) the matching filters (weights.py gate_permutation)
                 constexpr int GH = BN / 4;                        // gate columns per column-half
 #pragma unroll

@@ -23,8 +23,10 @@
 //   shared memory, and leaky-ReLU is max(v, s v) / min(v, s v).
 //
 // Roles: warp 0 = activation TMA producer (+ resident weights), warp 3 = residual + streamed-weight
-// TMA producer, warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4-11 = epilogue.
+// TMA producer, warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator (+ second issuer when the weights
+// are resident), warps 4-11 = epilogue.
 #include "umma_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -36,6 +38,7 @@ struct HaloCfg {
     int a_stages, r_stages, w_stages;   // ring depths (w_stages = 0: weights resident)
     int rows_alloc;                     // rows reserved per activation block (>= 128 + span)
     int box_rows;                       // 128 + span
+    int pf;                             // L2 prefetch distance in tiles (0 = off; CMTTS_PF)
 };
 
 // leaky-ReLU without a compare/select: slope <= 1 (forward) and slope >= 1 (the exact inverse on stored values)
@@ -118,8 +121,16 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             int stage = 0; uint32_t phase = 0;
             const uint32_t bytes = (uint32_t)(CB * cfg.box_rows * ROW_BYTES);
+            // L2 prefetch of the halo tiles PF tiles ahead of the shared-memory ring (see tma_prefetch_3d_elect)
+            const int PF = cfg.pf;
+            auto prefetch_tile = [&](int tl) {
+                if (PF > 0 && tl < tiles)
+                    for (int cb = 0; cb < CB; ++cb) tma_prefetch_3d_elect(&tmA, cb * BK, (tl % m_tiles) * BM + shift0, tl / m_tiles);
+            };
+            for (int i = 0; i < PF; ++i) prefetch_tile(blockIdx.x + i * gridDim.x);
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
                 const int mt = tile % m_tiles, b = tile / m_tiles;
+                prefetch_tile(tile + PF * gridDim.x);
                 mbar_wait(&a_empty[stage], phase ^ 1);
                 mbar_expect_tx_elect(&a_full[stage], bytes);
                 for (int cb = 0; cb < CB; ++cb)
@@ -133,8 +144,15 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (has_res) prefetch_tmap(&tmR);
             int ws = 0; uint32_t wphase = 0;
             int rs = 0; uint32_t rphase = 0;
+            const int PF = cfg.pf;
+            auto prefetch_res = [&](int tl) {
+                if (PF > 0 && has_res && tl < tiles)
+                    for (int cb = 0; cb < CB; ++cb) tma_prefetch_3d_elect(&tmR, cb * BK, (tl % m_tiles) * BM, tl / m_tiles);
+            };
+            for (int i = 0; i < PF; ++i) prefetch_res(blockIdx.x + i * gridDim.x);
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
                 const int mt = tile % m_tiles, b = tile / m_tiles;
+                prefetch_res(tile + PF * gridDim.x);
                 if (has_res) {
                     mbar_wait(&r_empty[rs], rphase ^ 1);
                     mbar_expect_tx_elect(&r_full[rs], R_STAGE);
@@ -153,9 +171,15 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 1) {
-        // ======================= MMA issuer =======================
+    } else if (warp == 1 || (warp == 2 && wres)) {
+        // ======================= MMA issuer(s) =======================
+        // With resident weights TWO warps issue, on alternating tiles (warp 1: even, warp 2: odd; the accumulator
+        // buffer is the tile parity): each tcgen05.mma costs ~10 uniform-datapath instructions of descriptor set-up
+        // (~60-70 cycles), which is more than a 128 x 64 x 16 MMA occupies the tensor pipe and left a single issuer
+        // as the limiter of the C <= 64 shapes.  With streamed weights the ring is consumed in tile order, so one
+        // warp issues (those shapes are bound by the L2 -> SM weight traffic anyway).
         {
+            const int first = wres ? warp - 1 : 0, step = wres ? 2 : 1;
             const uint32_t tmem_u = make_uniform(tmem_base);
             // The issuing thread is a single lane: every integer instruction on its path delays the next
             // tcgen05.mma.  With the tap count a template parameter the loops unroll completely, all
@@ -166,11 +190,12 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t cb_step = (uint32_t)(a_alloc >> 4);
             const uint32_t w_lo0 = ((smem_u32(smW) >> 4) & 0x3FFF) | (1u << 16);
             const int ntaps = TAPS > 0 ? TAPS : p.taps;
-            int stage = 0; uint32_t phase = 0;
+            int stage = first % cfg.a_stages; uint32_t phase = (uint32_t)((first / cfg.a_stages) & 1);
             int ws = 0; uint32_t wphase = 0;
-            int abuf = 0; uint32_t aphase = 0;
             if (wres) { mbar_wait(&w_full[0], 0); tc_fence_after(); }
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            int it = first;
+            for (int tile = blockIdx.x + first * gridDim.x; tile < tiles; tile += step * gridDim.x, it += step) {
+                const int abuf = it & 1; const uint32_t aphase = (uint32_t)((it >> 1) & 1);
                 mbar_wait(&tempty[abuf], aphase ^ 1);
                 mbar_wait(&a_full[stage], phase);
                 tc_fence_after();
@@ -209,8 +234,8 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 umma_commit_pred(&a_empty[stage], 0u);
                 umma_commit_pred(&tfull[abuf], 0u);
-                if (++stage == cfg.a_stages) { stage = 0; phase ^= 1; }
-                abuf ^= 1; if (abuf == 0) aphase ^= 1;
+                stage += step;
+                if (stage >= cfg.a_stages) { stage -= cfg.a_stages; phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -373,6 +398,9 @@ int launch_halo_cfg(const UmmaConvParams& p, cudaStream_t s) {
     if (cfg.a_stages < 2) return CMTTS_ERR_UNSUPPORTED;
     const size_t smem = (size_t)cfg.a_stages * a_stage + (size_t)cfg.r_stages * R_STAGE + w_bytes + FIXED;
 
+    static int pf_env = -1;
+    if (pf_env < 0) { const char* e = getenv("CMTTS_PF"); pf_env = e ? atoi(e) : 0; }
+    cfg.pf = pf_env;
     auto kern = umma_halo_kernel<BN, BK, CB, TAPS>;
     static bool attr_done = false;
     if (!attr_done) {

@@ -16,16 +16,17 @@
 // HBM traffic per iteration: read y once (+halo), write y' once.
 //
 // Pipelining: conv2 of a tile can only start after conv1 -> commit -> epilogue 1 -> t tile, a chain of
-// ~1.5k cycles, so the MMA-issuing warp runs conv1 `lag` = nb-1 tiles AHEAD of conv2 (conv1(i+lag) is
-// issued before conv2(i)); conv1 accumulators and t tiles are nb-deep rings (nb = 3 or 4).  Epilogue 1
+// ~1.5k cycles, so conv1 runs up to nb-1 tiles AHEAD of conv2 (separate issuing warps; conv1 accumulators,
+// t tiles and conv2 accumulators are nb-deep rings, nb = 3 or 4).  Epilogue 1
 // (TMEM -> t tile) and epilogue 2 (output) run on separate warps concurrently — EIGHT warps each (lane
 // quarter x column half): a lone warp per SM sub-partition issues its dependent ALU chain at ~4 cycles per
 // instruction, which made the epilogues (not HBM, not the tensor pipe) the limiter (ncu: MMA warp stalled on
 // acc2_empty, epilogue-2 warps > 80 % busy).  Biases sit in shared memory; leaky-ReLU is max / min(v, s v).
 // The input stage is released by the conv1 commit.
 //
-// Roles (576 threads): warp 0 TMEM allocator + TMA producer, 1 MMA issuer, 2-9 epilogue 1, 10-17 epilogue 2
-// (an epilogue warp's TMEM lane quarter is warp % 4, its column half the warp's position in its group of eight).
+// Roles (608 threads): warp 0 TMEM allocator + TMA producer, 1 conv1 issuer, 2 conv2 issuer, 3-10 epilogue 1,
+// 11-18 epilogue 2 (an epilogue warp's TMEM lane quarter is warp % 4, its column half the warp's position in its
+// group of eight).
 // Both weight sets stay resident in shared memory for the whole persistent loop.
 #include "umma_common.cuh"
 #include <stdlib.h>
@@ -40,12 +41,15 @@ constexpr int T_ROWS_ALLOC = 144;      // 128 + (k_max - 1) rounded to the swizz
 
 struct RbCfg {
     int a_stages, rows_alloc, box_rows, valid, m_tiles, nb, nb2;   // nb2: depth of the conv2-accumulator ring (2..4)
+    int pf;    // L2 prefetch distance of the halo tiles, in tiles (0 = off; CMTTS_PF)
+    int dbg;   // timing ablations (CMTTS_RB_DBG, results become wrong): 1 epilogue 2 does no work, 2 epilogue 1 does no
+               // work, 4 no MMAs are issued, 8 no residual read, 16 no output store
 };
 
 __device__ __forceinline__ float lrelu_fwd(float v, float slope) { return fmaxf(v, v * slope); }          // slope <= 1
 __device__ __forceinline__ float lrelu_inv(float v, float inv_slope) { return fminf(v, v * inv_slope); }  // inv_slope >= 1
 
-constexpr int RB_THREADS = 576;          // 18 warps -> 112 registers per thread
+constexpr int RB_THREADS = 608;          // 19 warps
 
 template <int C, int TAPS, bool HAS_SUM>
 __global__ void __launch_bounds__(RB_THREADS, 1)
@@ -105,7 +109,7 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + C) { s_b1[threadIdx.x - 64] = p.b1[threadIdx.x - 64]; s_b2[threadIdx.x - 64] = p.b2[threadIdx.x - 64]; }
+    if (threadIdx.x >= 96 && threadIdx.x < 96 + C) { s_b1[threadIdx.x - 96] = p.b1[threadIdx.x - 96]; s_b2[threadIdx.x - 96] = p.b2[threadIdx.x - 96]; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -124,9 +128,21 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
             int stage = 0; uint32_t phase = 0;
             const uint32_t bytes = (uint32_t)(cfg.box_rows * ROW_BYTES);
+            // L2 prefetch distance (tiles): the smem ring alone (2-8 stages of 9-20 KB) holds too few bytes in flight
+            // to cover the DRAM latency at this kernel's per-SM bandwidth share (ncu: producer stalled on a_empty,
+            // DRAM 25-30 % busy), so the halo tiles are pulled into L2 well ahead of the ring
+            const int PF = cfg.pf;
+            for (int i = 0; i < PF; ++i) {
+                const int tl = blockIdx.x + i * gridDim.x;
+                if (tl < tiles) tma_prefetch_3d_elect(&tmA, 0, (tl % cfg.m_tiles) * cfg.valid - P2 - p1d, tl / cfg.m_tiles);
+            }
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
                 const int mt = tile % cfg.m_tiles, b = tile / cfg.m_tiles;
                 const int row0 = mt * cfg.valid - P2 - p1d;          // first input row of the halo tile
+                if (PF > 0) {
+                    const int tl = tile + PF * gridDim.x;
+                    if (tl < tiles) tma_prefetch_3d_elect(&tmA, 0, (tl % cfg.m_tiles) * cfg.valid - P2 - p1d, tl / cfg.m_tiles);
+                }
                 mbar_wait(&a_empty[stage], phase ^ 1);
                 mbar_expect_tx_elect(&a_full[stage], bytes);
                 tma_load_3d_elect(smA + stage * a_alloc, &tmA, &a_full[stage], 0, row0, b);
@@ -134,52 +150,28 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ======================= MMA issuer =======================
+        // ======================= conv1 issuer =======================
+        // (the whole warp runs the loop convergently; one lane's tcgen05 instructions are predicated on.)
+        // Every tcgen05.mma costs ~10 uniform-datapath instructions of descriptor set-up (~60-70 cycles), more than
+        // a 128 x C x 16 MMA occupies the tensor pipe for C <= 64, so conv1 and conv2 are issued by TWO warps:
+        // a single issuer left the pipe idle ~45 % of the time with every other role waiting on it (ncu).
         {
-            // the whole warp runs this loop convergently; one lane's tcgen05 instructions are predicated on
             const uint32_t issue = 0;
             const uint32_t tmem_u = make_uniform(tmem_base);
             const uint32_t idesc = make_idesc(BM, C);
             const uint32_t tap_step1 = (uint32_t)((p.dil * ROW_BYTES) >> 4);
-            constexpr uint32_t tap_step2 = (uint32_t)(ROW_BYTES >> 4);
             const uint32_t w1_lo = ((smem_u32(smW1) >> 4) & 0x3FFF) | (1u << 16);
-            const uint32_t w2_lo = ((smem_u32(smW2) >> 4) & 0x3FFF) | (1u << 16);
             mbar_wait(&w_full[0], 0);
             tc_fence_after();
             int stage = 0; uint32_t phase = 0;
-            int it = 0;
-            // ring positions: conv1 side (b1, ph1), conv2 side (t ring: b2, ph2; conv2 accumulators: ab, aph)
             int b1 = 0; uint32_t ph1 = 0;
-            int b2 = 0; uint32_t ph2 = 0;
-            int j2 = 0;
-            int ab = 0; uint32_t aph = 0;
-            auto conv2 = [&]() {
-                mbar_wait(&t_full[b2], ph2);
-                mbar_wait(&acc2_empty[ab], aph ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_u + (uint32_t)(RB_MAX_NB * C + ab * C);
-                const uint32_t t_lo = ((smem_u32(smT + b2 * T_ALLOC) >> 4) & 0x3FFF) | (1u << 16);
-#pragma unroll
-                for (int tap = 0; tap < TAPS; ++tap) {
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_f16_pred(d_tmem, ((uint64_t)DESC_HI << 32) | (t_lo + tap * tap_step2 + 2 * k),
-                                 ((uint64_t)DESC_HI << 32) | (w2_lo + (uint32_t)((tap * W_BLK) >> 4) + 2 * k), idesc,
-                                 (tap | k) ? 1u : 0u, issue);
-                }
-                umma_commit_pred(&t_empty[b2], issue);
-                umma_commit_pred(&acc2_full[ab], issue);
-                ++j2;
-                if (++b2 == nb) { b2 = 0; ph2 ^= 1; }
-                if (++ab == cfg.nb2) { ab = 0; aph ^= 1; }
-            };
-            const int lag = nb - 1;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
                 mbar_wait(&acc1_empty[b1], ph1 ^ 1);
                 mbar_wait(&a_full[stage], phase);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_u + (uint32_t)(b1 * C);
                 const uint32_t a_lo = ((smem_u32(smA + stage * a_alloc) >> 4) & 0x3FFF) | (1u << 16);
+                if (!(cfg.dbg & 4))
 #pragma unroll
                 for (int tap = 0; tap < TAPS; ++tap) {
 #pragma unroll
@@ -192,16 +184,47 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 umma_commit_pred(&acc1_full[b1], issue);
                 if (++stage == cfg.a_stages) { stage = 0; phase ^= 1; }
                 if (++b1 == nb) { b1 = 0; ph1 ^= 1; }
-                if (it >= lag) conv2();
             }
-            while (j2 < it) conv2();
+        }
+    } else if (warp == 2) {
+        // ======================= conv2 issuer =======================
+        {
+            const uint32_t issue = 0;
+            const uint32_t tmem_u = make_uniform(tmem_base);
+            const uint32_t idesc = make_idesc(BM, C);
+            constexpr uint32_t tap_step2 = (uint32_t)(ROW_BYTES >> 4);
+            const uint32_t w2_lo = ((smem_u32(smW2) >> 4) & 0x3FFF) | (1u << 16);
+            mbar_wait(&w_full[0], 0);
+            tc_fence_after();
+            int b2 = 0; uint32_t ph2 = 0;                     // t-tile ring
+            int ab = 0; uint32_t aph = 0;                     // conv2 accumulator ring
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                mbar_wait(&t_full[b2], ph2);
+                mbar_wait(&acc2_empty[ab], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_u + (uint32_t)(RB_MAX_NB * C + ab * C);
+                const uint32_t t_lo = ((smem_u32(smT + b2 * T_ALLOC) >> 4) & 0x3FFF) | (1u << 16);
+                if (!(cfg.dbg & 4))
+#pragma unroll
+                for (int tap = 0; tap < TAPS; ++tap) {
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_f16_pred(d_tmem, ((uint64_t)DESC_HI << 32) | (t_lo + tap * tap_step2 + 2 * k),
+                                 ((uint64_t)DESC_HI << 32) | (w2_lo + (uint32_t)((tap * W_BLK) >> 4) + 2 * k), idesc,
+                                 (tap | k) ? 1u : 0u, issue);
+                }
+                umma_commit_pred(&t_empty[b2], issue);
+                umma_commit_pred(&acc2_full[ab], issue);
+                if (++b2 == nb) { b2 = 0; ph2 ^= 1; }
+                if (++ab == cfg.nb2) { ab = 0; aph ^= 1; }
+            }
         }
     } else {
         // ======================= epilogue warps =======================
-        const bool is_e1 = warp < 10;     // warps 2-9: epilogue 1 (conv1 -> t tile); warps 10-17: epilogue 2 (output)
+        const bool is_e1 = warp < 11;     // warps 3-10: epilogue 1 (conv1 -> t tile); warps 11-18: epilogue 2 (output)
         const int q = warp & 3;                                             // TMEM lane quarter
-        const int h = ((warp - 2) >> 2) & 1;                                // column half
-        const int ew = (warp - 2) & 7;                                      // index inside the group of eight
+        const int h = ((warp - 3) >> 2) & 1;                                // column half
+        const int ew = (warp - 3) & 7;                                      // index inside the group of eight
         const int row = q * 32 + lane;
         const int n_base = h * CH;
         const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
@@ -219,6 +242,7 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const bool inside = trow >= 0 && trow < p.L;
                 const uint32_t taddr = tmem_base + (uint32_t)(bb * C + n_base) + lane_addr;
                 uint8_t* trow_ptr = smT + bb * T_ALLOC + row * ROW_BYTES;
+                if (!(cfg.dbg & 2))
 #pragma unroll
                 for (int c = 0; c < CH / 16; ++c) {
                     uint32_t r[16];
@@ -260,16 +284,17 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             // residual lrelu(y) [+ MRF partial sum] of this thread's output row: global reads (L2-hot: the rows were
             // fetched by the tile's TMA a moment ago), software-pipelined ONE TILE AHEAD so that their latency never
             // sits between the accumulator wait and the stores
-            uint4 rnext[CH / 8], snext[HAS_SUM ? CH / 8 : 1];
+            constexpr bool PIPE_SUM = HAS_SUM && C == 32;     // C = 64: not enough registers to pipeline the sum too
+            uint4 rnext[CH / 8], snext[PIPE_SUM ? CH / 8 : 1];
             auto prefetch = [&](int tile_) {
                 const int mt_ = tile_ % cfg.m_tiles, b_ = tile_ / cfg.m_tiles;
                 const int o_ = mt_ * cfg.valid + row;
-                const bool ok = tile_ < tiles && row < cfg.valid && o_ < p.L;
+                const bool ok = tile_ < tiles && row < cfg.valid && o_ < p.L && !(cfg.dbg & 8);
                 const long long g_ = ((long long)b_ * p.L + o_) * C + n_base;
 #pragma unroll
                 for (int i = 0; i < CH / 8; ++i) {
                     rnext[i] = ok ? reinterpret_cast<const uint4*>(p.a + g_)[i] : make_uint4(0u, 0u, 0u, 0u);
-                    if constexpr (HAS_SUM) snext[i] = ok ? reinterpret_cast<const uint4*>(p.sum_h + g_)[i] : make_uint4(0u, 0u, 0u, 0u);
+                    if constexpr (PIPE_SUM) snext[i] = ok ? reinterpret_cast<const uint4*>(p.sum_h + g_)[i] : make_uint4(0u, 0u, 0u, 0u);
                 }
             };
             prefetch((int)blockIdx.x);
@@ -281,7 +306,11 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const long long goff = ((long long)b * p.L + o) * C + n_base;
                 uint4 rres[CH / 8], rsum[HAS_SUM ? CH / 8 : 1];
 #pragma unroll
-                for (int i = 0; i < CH / 8; ++i) { rres[i] = rnext[i]; if constexpr (HAS_SUM) rsum[i] = snext[i]; }
+                for (int i = 0; i < CH / 8; ++i) {
+                    rres[i] = rnext[i];
+                    if constexpr (PIPE_SUM) rsum[i] = snext[i];
+                    else if constexpr (HAS_SUM) rsum[i] = valid ? reinterpret_cast<const uint4*>(p.sum_h + goff)[i] : make_uint4(0u, 0u, 0u, 0u);
+                }
                 prefetch(tile + (int)gridDim.x);
                 mbar_wait(&acc2_full[bb], ph);
                 tc_fence_after();
@@ -290,6 +319,7 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     __syncwarp();
                 }
                 const uint32_t taddr = tmem_base + (uint32_t)(RB_MAX_NB * C + bb * C + n_base) + lane_addr;
+                if (!(cfg.dbg & 1))
 #pragma unroll
                 for (int c = 0; c < CH / 16; ++c) {
                     uint32_t r[16];
@@ -333,7 +363,7 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     if (TMA_STORE) {
                         *reinterpret_cast<uint4*>(slab + (((2 * c) ^ swo) << 4)) = u0;
                         *reinterpret_cast<uint4*>(slab + (((2 * c + 1) ^ swo) << 4)) = u1;
-                    } else if (valid) {
+                    } else if (valid && !(cfg.dbg & 16)) {
                         __half* op = p.out_h + goff + c * 16;
                         *reinterpret_cast<uint4*>(op) = u0;
                         *reinterpret_cast<uint4*>(op + 8) = u1;
@@ -344,7 +374,7 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(&acc2_empty[bb]);
-                    if (TMA_STORE) {
+                    if (TMA_STORE && !(cfg.dbg & 17)) {
                         // rows [q*32, q*32+32) of the tile; the last lane quarter only owns `valid - 96` rows
                         const int r0 = mt * cfg.valid + q * 32;
                         if (q < 3) tma_store_3d(&tmO, smO + ew * O_SLAB, n_base, r0, b);
@@ -400,6 +430,12 @@ int launch_rb_cfg(const UmmaResblockParams& p, cudaStream_t s) {
     static int nb2_env = -1;
     if (nb2_env < 0) { const char* e = getenv("CMTTS_RB_NB2"); nb2_env = e ? atoi(e) : 0; }
     cfg.nb2 = (nb2_env >= 2 && nb2_env <= RB_MAX_NB) ? nb2_env : RB_MAX_NB;
+    static int dbg_env = -1;
+    if (dbg_env < 0) { const char* e = getenv("CMTTS_RB_DBG"); dbg_env = e ? atoi(e) : 0; }
+    cfg.dbg = dbg_env;
+    static int pf_env = -1;
+    if (pf_env < 0) { const char* e = getenv("CMTTS_PF"); pf_env = e ? atoi(e) : 0; }
+    cfg.pf = pf_env;
     size_t st = (LIMIT - rest) / a_alloc;
     cfg.a_stages = (int)(st > RB_MAX_STAGES ? RB_MAX_STAGES : st);
     const size_t smem = rest + (size_t)cfg.a_stages * a_alloc;
