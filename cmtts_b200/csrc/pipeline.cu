@@ -559,18 +559,30 @@ extern "C" int cmtts_f32_to_f16(const float* x, void* hi, void* lo, int64_t rows
 }
 
 extern "C" size_t cmtts_denoiser_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t L) {
-    const size_t n = (size_t)B * L * d->res_channels;
-    return align_up(n * 4) * 3 + align_up(n * 2) * 4 + align_up((size_t)B * L * 128 * 2) * 2 +
-           align_up((size_t)B * d->res_layers * d->res_channels * 4);
+    const size_t R = (size_t)B * (L + 1);                       // flattened rows, one guard row per utterance
+    const size_t C = d->res_channels, H = d->hidden;
+    return align_up(R * C * 4) * 2 +                            // x, v (fp32)
+           align_up(R * (C + H) * 2) * 2 +                      // [y | cond] hi, lo
+           align_up(R * C * 2) * 2 * (size_t)d->res_layers +    // g hi, lo of every layer
+           align_up(R * C * 2) * 2 +                            // skip sum hi, lo
+           align_up(R * 128 * 2) * 2 +                          // x_t hi, lo (K padded to 128)
+           align_up((size_t)B * d->res_layers * C * 4);         // per-(utterance, layer) constants
 }
 
-// The residual stack as a recurrence in y_l = x_l + c_l, with c_l = Wc_l cond + bc_l + step_l[b] + spk_l[b]
-// (what the k=3 conv consumes, blocks.py:669-678).  With r = 1/sqrt(2) and x_{l+1} = r (Wo_l[:C] g_l + bo_l +
-// step_l[b] + x_l) (blocks.py:676, :683-686):
-//     y_{l+1} = [r Wo_l[:C] | Wc_{l+1} - r Wc_l] [g_l ; cond]  +  r y_l  +  const_l[b]
-// — ONE GEMM per layer (K = C + H, the "fused" weights of weights.py) instead of the output projection, a
-// separate conditioner projection and two passes over x.  x_l itself is never needed: the stack's result is
-// the skip sum (modules.py:629-637).  Same algebra as the reference, different rounding order (fp32-class).
+// The residual stack on tensor cores, restructured (same algebra as the reference, fp32-class rounding):
+//
+// * a recurrence in y_l = x_l + c_l, c_l = Wc_l cond + bc_l + step_l[b] + spk_l[b] (what the k=3 conv consumes,
+//   blocks.py:669-678).  With r = 1/sqrt(2), x_{l+1} = r (Wo_l[:C] g_l + bo_l + step_l[b] + x_l) (blocks.py:676,:683-686):
+//       y_{l+1} = [r Wo_l[:C] | r I | Wc_{l+1} - r Wc_l] [g_l ; y_l ; cond] + const_l[b]
+//   ONE GEMM per layer (weights.py: fused_recurrence_weights) instead of an output projection, a conditioner
+//   projection and two read-modify-write passes over x.  y_l enters through the operand pipeline (block-diagonal
+//   r I: a tile only loads its own 128 channels of y), so the epilogue reads nothing from global memory — with
+//   epilogue reads the kernel sat on exposed DRAM latency (ncu / tools/ablate.py).  x_l itself is never needed;
+// * the skip sum (modules.py:629-637) is ONE GEMM at the end over the stacked gate outputs, K = layers * C
+//   (weights.py: skip_stack_weights), instead of a fp32 read-modify-write of `skip` in every layer;
+// * utterances are FLATTENED into one row axis with a zero guard row after each (row b (L+1) + t): the k=3 conv's
+//   zero padding between neighbours is the guard row, tiles are 128 consecutive rows regardless of L (L = 793 would
+//   otherwise waste 11 % of every 7th tile and, worse, quantise 896 tiles onto 148 SMs as 7 rounds instead of 6).
 extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const* w, const void* const* w16,
                                          const float* x_t, const void* cond_hi, const void* cond_lo,
                                          const float* ds_all, const float* dsp_all, float c_in, float c_out,
@@ -580,96 +592,115 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
     const int B = (int)B_, L = (int)L_, C = d->res_channels, M = d->n_mels, H = d->hidden, NLY = d->res_layers;
     CMTTS_REQUIRE(ws_bytes >= cmtts_denoiser_tc_workspace_bytes(d, B_, L_), "denoiser_tc: workspace too small");
     CMTTS_REQUIRE(C % 128 == 0 && H % 64 == 0, "denoiser_tc: channel counts must suit the 128x128x64 UMMA tiling");
+    CMTTS_REQUIRE(M <= 128, "denoiser_tc: n_mels must be <= 128");
+    CMTTS_REQUIRE((long long)B * (L + 1) < (1ll << 31), "denoiser_tc: too many rows");
     if (B == 0 || L == 0) return CMTTS_OK;
+    const int Lp = L + 1, R = B * Lp, YC = C + H;
     Carver cv(ws, ws_bytes);
-    const size_t n = (size_t)B * L;
-    float* x = cv.take<float>(n * C);
-    float* skip = cv.take<float>(n * C);
-    float* v = cv.take<float>(n * C);
-    __half* y_hi = cv.take<__half>(n * C);
-    __half* y_lo = cv.take<__half>(n * C);
-    __half* g_hi = cv.take<__half>(n * C);
-    __half* g_lo = cv.take<__half>(n * C);
-    __half* xt_hi = cv.take<__half>(n * 128);
-    __half* xt_lo = cv.take<__half>(n * 128);
+    float* x = cv.take<float>((size_t)R * C);
+    float* v = cv.take<float>((size_t)R * C);
+    __half* yc_hi = cv.take<__half>((size_t)R * YC);          // row = [y (C) | cond (H)]
+    __half* yc_lo = cv.take<__half>((size_t)R * YC);
+    __half* g_hi = cv.take<__half>((size_t)R * C * NLY);      // [layer][row][C]
+    __half* g_lo = cv.take<__half>((size_t)R * C * NLY);
+    __half* sk_hi = cv.take<__half>((size_t)R * C);
+    __half* sk_lo = cv.take<__half>((size_t)R * C);
+    __half* xt_hi = cv.take<__half>((size_t)R * 128);
+    __half* xt_lo = cv.take<__half>((size_t)R * 128);
     float* yc = cv.take<float>((size_t)B * NLY * C);
     const long long NL = (long long)NLY * C;
-    const long long bs = (long long)L * C;
-    const void* const* wx = w16 + NLY * 7;              // {in_w hi, lo [C][128]; skip_w hi, lo [C][C]}
-    const void* const* wf = wx + 4;                     // per layer l < NLY-1: {fused_w hi, lo [2C][C+H]; fused_b [2C]}
+    const void* const* wx = w16 + NLY * 7;                    // {in_w hi, lo [C][128]; skip_w hi, lo [C][C]}
+    const void* const* wf = wx + 4;                           // per layer l < NLY-1: {y_w hi, lo [C][2C+H]; y_b [C]}
+    const void* const* wsk = wf + 3 * (NLY - 1);              // {skip-stack w hi, lo [NLY*C][C]; summed bias [C]}
     const float r = (float)(1.0 / sqrt(2.0));
-    CMTTS_REQUIRE(M <= 128, "denoiser_tc: n_mels must be <= 128");
+
+    // flattened single-"utterance" problem of R rows; guard rows are never written by the epilogues
+    auto flat = [&](UmmaConvParams& u) { u.B = 1; u.M = R; u.Lin = R; u.rows_per_utt = Lp; };
 
     CMTTS_TRY(launch_dn_fuse_steps(ds_all, dsp_all, yc, B, NLY, C, r, s));
+    // zero the y part of the guard rows (the conv's padding); everything else in guard rows is never consumed
+    cudaMemset2DAsync(yc_hi + (size_t)L * YC, (size_t)Lp * YC * 2, 0, (size_t)C * 2, B, s);
+    cudaMemset2DAsync(yc_lo + (size_t)L * YC, (size_t)Lp * YC * 2, 0, (size_t)C * 2, B, s);
+    CMTTS_TRY(launch_pack_rows_f16((const __half*)cond_hi, yc_hi, B, L, Lp, H, YC, C, s));
+    CMTTS_TRY(launch_pack_rows_f16((const __half*)cond_lo, yc_lo, B, L, Lp, H, YC, C, s));
     // input projection: relu(W (c_in x_t) + b), x_t zero-padded to 128 channels as an fp16 hi/lo pair
-    CMTTS_TRY(launch_f32_to_f16(x_t, xt_hi, xt_lo, (long long)n, M, 128, 1.f, s));
+    CMTTS_TRY(launch_f32_to_f16_rows(x_t, xt_hi, xt_lo, B, L, Lp, M, 128, 128, s));
     {
-        UmmaConvParams u = tc_same(HL{xt_hi, xt_lo}, B, L, 128, wx[0], wx[1], F(w, CMTTS_DN_IN_B), C, 1, 1);
+        UmmaConvParams u = tc_same(HL{xt_hi, xt_lo}, 1, R, 128, wx[0], wx[1], F(w, CMTTS_DN_IN_B), C, 1, 1);
+        flat(u);
         u.alpha = c_in * TC_W_SCALE_INV; u.act = ACT_RELU;
-        tc_out32(u, x, L, C);
+        tc_out32(u, x, R, C);
         CMTTS_TRY(launch_umma_conv(u, s));
     }
     {
         // y_0 = Wc_0 cond + bc_0 + (step + speaker)_0[b] + x_0                blocks.py:669-678
         UmmaConvParams u = umma_params_default();
-        u.B = B; u.M = L; u.Lin = L; u.N = C; u.Cin = H; u.taps = 1; u.shift[0] = 0; u.split = 1; u.epi = UEPI_DN_COND;
+        flat(u);
+        u.N = C; u.Cin = H; u.taps = 1; u.shift[0] = 0; u.split = 1; u.epi = UEPI_DN_COND;
         u.alpha = TC_W_SCALE_INV;
-        u.a_hi = (const __half*)cond_hi; u.a_lo = (const __half*)cond_lo; u.a_bstride = (long long)L * H; u.a_ld = H;
+        u.a_hi = yc_hi + C; u.a_lo = yc_lo + C; u.a_bstride = (long long)R * YC; u.a_ld = YC;
         u.w_hi = (const __half*)w16[0]; u.w_lo = (const __half*)w16[1];
         u.bias = F(w, CMTTS_DN_LAYER0 + 1);
         u.addvec = dsp_all; u.addvec_bstride = NL;
-        u.x_f32 = x; u.x_bstride = bs; u.x_ld = C;
-        u.out_h = y_hi; u.out_lo = y_lo; u.out_bstride = bs; u.out_ld = C;
+        u.x_f32 = x; u.x_bstride = (long long)R * C; u.x_ld = C;
+        u.out_h = yc_hi; u.out_lo = yc_lo; u.out_bstride = (long long)R * YC; u.out_ld = YC;
         CMTTS_TRY(launch_umma_conv(u, s));
     }
-    ConvParams p;
     for (int l = 0; l < NLY; ++l) {
         const void* const* wl = w16 + l * 7;
         const int o = CMTTS_DN_LAYER0 + l * CMTTS_DN_PER_LAYER;
-        // g = sigmoid(gate) * tanh(filter) of the k=3 conv of y_l              blocks.py:677-681
+        __half* gl_hi = g_hi + (size_t)l * R * C;
+        __half* gl_lo = g_lo + (size_t)l * R * C;
+        // g_l = sigmoid(gate) * tanh(filter) of the k=3 conv of y_l            blocks.py:677-681
         UmmaConvParams u = umma_params_default();
-        u.B = B; u.M = L; u.Lin = L; u.N = 2 * C; u.Cin = C; u.taps = 3; u.shift[0] = -1; u.shift[1] = 0; u.shift[2] = 1;
+        flat(u);
+        u.N = 2 * C; u.Cin = C; u.taps = 3; u.shift[0] = -1; u.shift[1] = 0; u.shift[2] = 1;
         u.split = 1; u.epi = UEPI_DN_GATE; u.alpha = TC_W_SCALE_INV;
-        u.a_hi = y_hi; u.a_lo = y_lo; u.a_bstride = bs; u.a_ld = C;
+        u.a_hi = yc_hi; u.a_lo = yc_lo; u.a_bstride = (long long)R * YC; u.a_ld = YC;
         u.w_hi = (const __half*)wl[2]; u.w_lo = (const __half*)wl[3];
         u.bias = F(w, o + 3);
-        u.out_h = g_hi; u.out_lo = g_lo; u.out_bstride = bs; u.out_ld = C;
+        u.out_h = gl_hi; u.out_lo = gl_lo; u.out_bstride = (long long)R * C; u.out_ld = C;
         CMTTS_TRY(launch_umma_conv(u, s));
         if (l + 1 < NLY) {
-            // y_{l+1} (in place) and skip (+)= Wo_l[C:] g + b : one launch, see the recurrence above
+            // y_{l+1}, in place: K = C (g_l) + own 128 channels of y_l + H (cond); see the recurrence above
             u = umma_params_default();
-            u.B = B; u.M = L; u.Lin = L; u.N = 2 * C; u.Cin = C; u.taps = 1; u.shift[0] = 0; u.split = 1; u.epi = UEPI_DN_OUTY;
+            flat(u);
+            u.N = C; u.Cin = C; u.taps = 1; u.shift[0] = 0; u.split = 1; u.epi = UEPI_DN_OUTY;
             u.alpha = TC_W_SCALE_INV;
-            u.a_hi = g_hi; u.a_lo = g_lo; u.a_bstride = bs; u.a_ld = C;
-            u.a2_hi = (const __half*)cond_hi; u.a2_lo = (const __half*)cond_lo; u.a2_bstride = (long long)L * H; u.a2_ld = H;
-            u.Cin2 = H; u.n_k2 = C;
+            u.a_hi = gl_hi; u.a_lo = gl_lo; u.a_bstride = (long long)R * C; u.a_ld = C;
+            u.a2_hi = yc_hi; u.a2_lo = yc_lo; u.a2_bstride = (long long)R * YC; u.a2_ld = YC;
+            u.Cin2 = YC; u.n_k2 = C; u.a2_diag = C;
             u.w_hi = (const __half*)wf[3 * l]; u.w_lo = (const __half*)wf[3 * l + 1];
             u.bias = (const float*)wf[3 * l + 2];
             u.addvec = yc + (long long)l * C; u.addvec_bstride = (long long)(NLY - 1) * C;
-            u.out_h = y_hi; u.out_lo = y_lo; u.out_bstride = bs; u.out_ld = C;
-            u.skip_f32 = skip; u.x_bstride = bs; u.x_ld = C; u.skip_accumulate = (l > 0);
-            u.out_scale = r;
-            CMTTS_TRY(launch_umma_conv(u, s));
-        } else {
-            // last layer: only the skip half of the output projection is used (modules.py:629-634)
-            u = tc_same(HL{g_hi, g_lo}, B, L, C, (const __half*)wl[4] + (size_t)C * C, (const __half*)wl[5] + (size_t)C * C,
-                        (const float*)wl[6] + C, C, 1, 1);
-            if (l > 0) tc_res(u, skip, L, C);
-            tc_out32(u, skip, L, C);
+            u.out_h = yc_hi; u.out_lo = yc_lo; u.out_bstride = (long long)R * YC; u.out_ld = YC;
             CMTTS_TRY(launch_umma_conv(u, s));
         }
     }
     const int o = CMTTS_DN_LAYER0 + NLY * CMTTS_DN_PER_LAYER;
-    // skip projection: relu(W (sum skip / sqrt(n_layers)) + b) on the hi/lo kernel (y/g buffers are free now)
-    CMTTS_TRY(to_hl(skip, HL{y_hi, y_lo}, (long long)n, C, s));
     {
-        UmmaConvParams u = tc_same(HL{y_hi, y_lo}, B, L, C, wx[2], wx[3], F(w, o + 1), C, 1, 1);
-        u.alpha = (float)(1.0 / sqrt((double)NLY)) * TC_W_SCALE_INV; u.act = ACT_RELU;
-        tc_out32(u, v, L, C);
+        // skip sum over all layers as one GEMM over the stacked gate outputs (K = NLY * C), written as hi/lo
+        UmmaConvParams u = umma_params_default();
+        flat(u);
+        u.N = C; u.Cin = C; u.taps = NLY; u.a_tap_dim = 1; u.split = 1; u.epi = UEPI_F32; u.n_valid = C;
+        u.alpha = TC_W_SCALE_INV;
+        u.a_hi = g_hi; u.a_lo = g_lo; u.a_bstride = (long long)R * C; u.a_ld = C;
+        u.w_hi = (const __half*)wsk[0]; u.w_lo = (const __half*)wsk[1];
+        u.bias = (const float*)wsk[2];
+        u.out_h = sk_hi; u.out_lo = sk_lo; u.out_bstride = (long long)R * C; u.out_ld = C;
         CMTTS_TRY(launch_umma_conv(u, s));
     }
-    // output projection (N = 80) + Karras combination stay on the fp32 kernel
-    p = conv_same(v, B, L, C, F(w, o + 2), F(w, o + 3), M, 1, 1, out);
+    {
+        // skip projection: relu(W (sum skip / sqrt(n_layers)) + b)              modules.py:635-636
+        UmmaConvParams u = tc_same(HL{sk_hi, sk_lo}, 1, R, C, wx[2], wx[3], F(w, o + 1), C, 1, 1);
+        flat(u);
+        u.alpha = (float)(1.0 / sqrt((double)NLY)) * TC_W_SCALE_INV; u.act = ACT_RELU;
+        tc_out32(u, v, R, C);
+        CMTTS_TRY(launch_umma_conv(u, s));
+    }
+    // output projection (N = 80) + Karras combination stay on the fp32 kernel; it reads v through the guarded layout
+    ConvParams p = conv_same(v, B, L, C, F(w, o + 2), F(w, o + 3), M, 1, 1, out);
+    p.x_bstride = (long long)Lp * C;
     p.beta = c_out;
     if (model_out) { p.aux_out = model_out; p.aux_bstride = (long long)L * M; p.aux_ld = M; }
     if (c_skip != 0.f) { p.res1 = x_t; p.res1_bstride = (long long)L * M; p.res1_ld = M; p.res1_scale = c_skip; }

@@ -49,7 +49,7 @@ struct TileSched {
         H = rows * heavy_n; Lt = rows * (n_tiles - heavy_n);
         h_next = c;
         if (heavy_n == 0) { l_next = 0; l_end = 0; x_next = c; return; }
-        const int wl = p.Cin / BK, wh = wl + p.Cin2 / BK;
+        const int wl = p.Cin / BK, wh = wl + p.Cin2 / BK - (p.a2_diag ? (p.a2_diag - BN) / BK : 0);
         const long long total = (long long)H * wh + (long long)Lt * wl;
         const int T = (int)((total + G - 1) / G);
         const int q = H / G, rem = H % G;
@@ -109,7 +109,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cblocks = p.Cin / BK;
     const int kblocks1 = p.taps * cblocks;                // k-blocks over the first operand
-    const int kblocks2 = SPLIT ? p.Cin2 / BK : 0;         // extra k-blocks of heavy tiles (second operand)
+    // extra k-blocks of heavy tiles (second operand); of a block-diagonal leading segment only the tile's own blocks
+    const int diag_blocks = SPLIT ? p.a2_diag / BK : 0;
+    const int kblocks2 = SPLIT ? (p.Cin2 / BK - diag_blocks + (diag_blocks ? BN / BK : 0)) : 0;
 
     if (threadIdx.x == 0) {
         // SPLIT: two issuing warps (main products / cross terms) each commit to `empty` and `tfull`
@@ -138,26 +140,6 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             int nt, mt, b; bool heavy;
             while (ts.next(nt, mt, b, heavy)) {
                 const int kblocks = kblocks1 + (heavy ? kblocks2 : 0);
-                {
-                    // pull the NEXT tile's activation boxes into L2 now: the real loads can only be issued as stages
-                    // free up, and for operands that come from DRAM (conditioner, a just-written g) a 3-stage ring
-                    // does not hold enough bytes in flight to hide that latency
-                    TileSched ahead = ts;
-                    int nt2, mt2, b2; bool heavy2;
-                    if ((p.dbg & 128) && ahead.next(nt2, mt2, b2, heavy2) && (mt2 != mt || b2 != b)) {
-                        for (int kb = 0; kb < kblocks1; ++kb) {
-                            const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * BK;
-                            if (tap > 0) break;                       // the taps of a conv re-read the same rows (+-halo)
-                            tma_prefetch_3d_elect(&tmA0, c0, mt2 * BM + p.shift[0], b2);
-                            if (SPLIT) tma_prefetch_3d_elect(&tmA1, c0, mt2 * BM + p.shift[0], b2);
-                        }
-                        if (SPLIT && heavy2)
-                            for (int kb = 0; kb < kblocks2; ++kb) {
-                                tma_prefetch_3d_elect(&tmA2, kb * BK, mt2 * BM, b2);
-                                tma_prefetch_3d_elect(&tmA3, kb * BK, mt2 * BM, b2);
-                            }
-                    }
-                }
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx_elect(&full[stage], STAGE_BYTES);
@@ -165,14 +147,18 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     uint8_t* sb = sa + NOP * A_BYTES;
                     if (!SPLIT || kb < kblocks1) {
                         const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * BK;
-                        const int row = mt * BM + p.shift[tap];
-                        tma_load_3d_elect(sa, &tmA0, &full[stage], c0, row, b);
-                        if (SPLIT) tma_load_3d_elect(sa + A_BYTES, &tmA1, &full[stage], c0, row, b);
+                        // conv taps shift rows; in a_tap_dim mode they select a slice of the stacked A tensor
+                        const int row = mt * BM + (p.a_tap_dim ? 0 : p.shift[tap]);
+                        const int z = p.a_tap_dim ? tap : b;
+                        tma_load_3d_elect(sa, &tmA0, &full[stage], c0, row, z);
+                        if (SPLIT) tma_load_3d_elect(sa + A_BYTES, &tmA1, &full[stage], c0, row, z);
                         // weights [taps*N][Cin (+ Cin2)]: with a second operand taps == 1 and c0 is also the W column
                         tma_load_2d_elect(sb, &tmB0, &full[stage], c0, tap * p.N + nt * BN);
                         if (SPLIT) tma_load_2d_elect(sb + B_BYTES, &tmB1, &full[stage], c0, tap * p.N + nt * BN);
                     } else {
-                        const int c0 = (kb - kblocks1) * BK;
+                        int blk = kb - kblocks1;
+                        if (diag_blocks) blk = blk < BN / BK ? nt * (BN / BK) + blk : diag_blocks + (blk - BN / BK);
+                        const int c0 = blk * BK;
                         tma_load_3d_elect(sa, &tmA2, &full[stage], c0, mt * BM, b);
                         tma_load_3d_elect(sa + A_BYTES, &tmA3, &full[stage], c0, mt * BM, b);
                         tma_load_2d_elect(sb, &tmB0, &full[stage], p.Cin + c0, nt * BN);
@@ -245,7 +231,12 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         int nt, mt, b; bool heavy;
         while (ts.next(nt, mt, b, heavy)) {
             const int t = mt * BM + row;
-            const bool valid = t < p.M;
+            bool valid = t < p.M;
+            int ub = b;                                       // utterance index (addvec row)
+            if (p.rows_per_utt > 0) {                         // flattened layout: skip the guard row of every utterance
+                ub = t / p.rows_per_utt;
+                valid = valid && (t - ub * p.rows_per_utt) < p.rows_per_utt - 1;
+            }
             const int n0 = nt * BN + h * BNH;                 // first output column of this thread
             uint4 pre[16];
             bool have_pre = false;
@@ -257,23 +248,11 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     const int half_n = p.N >> 1;
                     if (n0 < half_n) src = p.x_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + n0;
                     else if (p.skip_accumulate) src = p.skip_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + (n0 - half_n);
-                } else if (p.epi == UEPI_DN_OUTY) {
-                    if (n0 >= p.n_k2 && p.skip_accumulate)
-                        src = p.skip_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + (n0 - p.n_k2);
                 }
                 if (src && valid && !(p.dbg & 8)) {
                     have_pre = true;
 #pragma unroll
                     for (int i = 0; i < BNH / 4; ++i) pre[i] = reinterpret_cast<const uint4*>(src)[i];
-                }
-                if (p.epi == UEPI_DN_OUTY && n0 < p.n_k2 && valid && !(p.dbg & 8)) {
-                    // y (fp16 hi/lo, updated in place): hi halves in pre[0, BNH/8), lo halves in pre[BNH/8, BNH/4)
-                    have_pre = true;
-                    const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n0;
-                    const uint4* yh = reinterpret_cast<const uint4*>(p.out_h + o);
-                    const uint4* yl = reinterpret_cast<const uint4*>(p.out_lo + o);
-#pragma unroll
-                    for (int i = 0; i < BNH / 8; ++i) { pre[i] = yh[i]; pre[BNH / 8 + i] = yl[i]; }
                 }
             } else {
                 if (p.res_h && valid) {
@@ -362,27 +341,11 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         store16h(p.out_h + o, v);
                     } else {
                         float x[16];
-                        if (p.epi == UEPI_DN_OUTY && n < p.n_k2) {
-                            // old y = hi + lo of this thread's 16 columns
 #pragma unroll
-                            for (int i = 0; i < 2; ++i) {
-                                const uint4 uh = have_pre ? pre[2 * c + i] : make_uint4(0u, 0u, 0u, 0u);
-                                const uint4 ul = have_pre ? pre[BNH / 8 + 2 * c + i] : make_uint4(0u, 0u, 0u, 0u);
-                                const __half2* hh = reinterpret_cast<const __half2*>(&uh);
-                                const __half2* hl = reinterpret_cast<const __half2*>(&ul);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float2 a = __half22float2(hh[j]), bq = __half22float2(hl[j]);
-                                    x[8 * i + 2 * j] = a.x + bq.x; x[8 * i + 2 * j + 1] = a.y + bq.y;
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const uint4 u = have_pre ? pre[4 * c + i] : make_uint4(0u, 0u, 0u, 0u);
-                                x[4 * i] = __uint_as_float(u.x); x[4 * i + 1] = __uint_as_float(u.y);
-                                x[4 * i + 2] = __uint_as_float(u.z); x[4 * i + 3] = __uint_as_float(u.w);
-                            }
+                        for (int i = 0; i < 4; ++i) {
+                            const uint4 u = have_pre ? pre[4 * c + i] : make_uint4(0u, 0u, 0u, 0u);
+                            x[4 * i] = __uint_as_float(u.x); x[4 * i + 1] = __uint_as_float(u.y);
+                            x[4 * i + 2] = __uint_as_float(u.z); x[4 * i + 3] = __uint_as_float(u.w);
                         }
                         if (p.epi == UEPI_F32) {
                             if (n >= p.n_valid) continue;
@@ -398,7 +361,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             }
                             if (p.addvec) {
                                 float a[16];
-                                load16f(p.addvec + (long long)b * p.addvec_bstride + n, a);
+                                load16f(p.addvec + (long long)ub * p.addvec_bstride + n, a);
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) v[j] += a[j];
                             }
@@ -412,29 +375,23 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             }
                         } else if (p.epi == UEPI_DN_COND) {
                             float a[16];
-                            load16f(p.addvec + (long long)b * p.addvec_bstride + n, a);
+                            load16f(p.addvec + (long long)ub * p.addvec_bstride + n, a);
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] += a[j] + x[j];
                             const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
                             store16_hilo(p.out_h + o, p.out_lo + o, v);
                         } else if (p.epi == UEPI_DN_OUTY) {
-                            if (n < p.n_k2) {
-                                float a[16];
-                                load16f(p.addvec + (long long)b * p.addvec_bstride + n, a);
+                            float a[16];
+                            load16f(p.addvec + (long long)ub * p.addvec_bstride + n, a);
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) v[j] = fmaf(x[j], p.out_scale, v[j] + a[j]);
-                                const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
-                                store16_hilo(p.out_h + o, p.out_lo + o, v);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) v[j] += x[j];     // x[] holds the old skip (or zeros)
-                                store16f(p.skip_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + (n - p.n_k2), v);
-                            }
+                            for (int j = 0; j < 16; ++j) v[j] += a[j];
+                            const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
+                            store16_hilo(p.out_h + o, p.out_lo + o, v);
                         } else {  // UEPI_DN_OUT
                             const int half_n = p.N >> 1;
                             if (n < half_n) {
                                 float a[16];
-                                load16f(p.addvec + (long long)b * p.addvec_bstride + n, a);
+                                load16f(p.addvec + (long long)ub * p.addvec_bstride + n, a);
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) v[j] = (v[j] + a[j] + x[j]) * p.out_scale;
                                 store16f(p.x_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + n, v);
@@ -484,7 +441,7 @@ int launch_cfg(const UmmaConvParams& p, cudaStream_t s) {
         attr_done = true;
     }
     CUtensorMap a0, a1, b0, b1;
-    if (!make_act_map(&a0, p.a_hi, p.Cin, p.Lin, p.B, p.a_ld, p.a_bstride, BK) ||
+    if (!make_act_map(&a0, p.a_hi, p.Cin, p.Lin, p.a_tap_dim ? p.taps : p.B, p.a_ld, p.a_bstride, BK) ||
         !make_w_map(&b0, p.w_hi, p.Cin, p.taps * p.N, BK, BN)) {
         cmtts_set_error("umma_conv: cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
         return CMTTS_ERR_CUDA;
@@ -493,7 +450,7 @@ int launch_cfg(const UmmaConvParams& p, cudaStream_t s) {
     CUtensorMap a2 = a0, a3 = a0;
     if (SPLIT) {
         const int wk = p.Cin + (p.a2_hi ? p.Cin2 : 0);     // weight row length
-        if (!make_act_map(&a1, p.a_lo, p.Cin, p.Lin, p.B, p.a_ld, p.a_bstride, BK) ||
+        if (!make_act_map(&a1, p.a_lo, p.Cin, p.Lin, p.a_tap_dim ? p.taps : p.B, p.a_ld, p.a_bstride, BK) ||
             !make_w_map(&b0, p.w_hi, wk, p.taps * p.N, BK, BN) || !make_w_map(&b1, p.w_lo, wk, p.taps * p.N, BK, BN)) {
             cmtts_set_error("umma_conv: cuTensorMapEncodeTiled failed (lo operands)", __FILE__, __LINE__);
             return CMTTS_ERR_CUDA;
@@ -519,7 +476,7 @@ int launch_umma_conv(const UmmaConvParams& p_in, cudaStream_t s) {
     UmmaConvParams p = p_in;
     p.dbg = dbg_env;
     CMTTS_REQUIRE(p.a_hi && p.w_hi, "umma_conv: null operand");
-    CMTTS_REQUIRE(p.taps >= 1 && p.taps <= CMTTS_MAX_TAPS, "umma_conv: taps out of range");
+    CMTTS_REQUIRE(p.taps >= 1 && (p.taps <= CMTTS_MAX_TAPS || p.a_tap_dim), "umma_conv: taps out of range");
     CMTTS_REQUIRE(p.Cin % 32 == 0, "umma_conv: Cin must be a multiple of 32");
     CMTTS_REQUIRE(p.a_ld % 8 == 0 && p.a_bstride % 8 == 0, "umma_conv: activation strides must be multiples of 16 bytes");
     CMTTS_REQUIRE(((uintptr_t)p.a_hi % 16 == 0) && ((uintptr_t)p.w_hi % 16 == 0), "umma_conv: operands must be 16-byte aligned");
@@ -534,8 +491,12 @@ int launch_umma_conv(const UmmaConvParams& p_in, cudaStream_t s) {
                           ((uintptr_t)p.a2_hi % 16 == 0) && ((uintptr_t)p.a2_lo % 16 == 0),
                           "umma_conv: second operand needs taps == 1, Cin2 % 64 == 0, n_k2 % 128 == 0, 16-byte alignment");
         }
-        CMTTS_REQUIRE(p.epi != UEPI_DN_OUTY || (p.a2_hi && p.out_h && p.out_lo && p.addvec && p.skip_f32),
-                      "umma_conv: UEPI_DN_OUTY needs the second operand, y hi/lo, addvec and skip");
+        CMTTS_REQUIRE(p.epi != UEPI_DN_OUTY || (p.a2_hi && p.out_h && p.out_lo && p.addvec),
+                      "umma_conv: UEPI_DN_OUTY needs the second operand, y hi/lo and addvec");
+        CMTTS_REQUIRE(p.a2_diag == 0 || (p.a2_hi && p.a2_diag == p.N && p.n_k2 == p.N && p.a2_diag <= p.Cin2),
+                      "umma_conv: a block-diagonal A2 segment must span exactly the N output columns");
+        CMTTS_REQUIRE(p.rows_per_utt == 0 || (p.B == 1 && p.rows_per_utt >= 2), "umma_conv: flattened layout needs B == 1");
+        CMTTS_REQUIRE(!p.a_tap_dim || (p.B == 1 && !p.a2_hi), "umma_conv: a_tap_dim needs B == 1 and no second operand");
         return launch_cfg<128, 64, 1>(p, s);
     }
     CMTTS_REQUIRE(p.epi == UEPI_VOC, "umma_conv: denoiser epilogues need split mode");
@@ -585,6 +546,44 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ x, __half* __restric
     }
     *reinterpret_cast<uint4*>(hi + r * Cpad + c) = uh;
     if (lo) *reinterpret_cast<uint4*>(lo + r * Cpad + c) = ul;
+}
+
+// Flattened-utterance layout helpers (denoiser): row b*L + t of a (B, L, *) tensor goes to row b*Lp + t (Lp = L + 1:
+// one guard row per utterance) of a matrix with row pitch `out_ld` elements, at column `col_off`.
+__global__ void f32_to_f16_rows_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
+                                       long long rows, int L, int Lp, int C, int Cpad, int out_ld) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 8 output channels
+    const int per_row = Cpad >> 3;
+    if (i >= rows * per_row) return;
+    const long long r = i / per_row;
+    const int c = (int)(i - r * per_row) << 3;
+    const long long ro = (r / L) * Lp + (r % L);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c + j < C) ? x[r * C + c + j] : 0.f;
+    uint4 uh, ul;
+    __half2* ph = reinterpret_cast<__half2*>(&uh);
+    __half2* pl = reinterpret_cast<__half2*>(&ul);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+        const float2 hf = __half22float2(h);
+        ph[j] = h;
+        pl[j] = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+    }
+    *reinterpret_cast<uint4*>(hi + ro * out_ld + c) = uh;
+    *reinterpret_cast<uint4*>(lo + ro * out_ld + c) = ul;
+}
+
+__global__ void pack_rows_f16_kernel(const __half* __restrict__ src, __half* __restrict__ dst, long long rows, int L, int Lp,
+                                     int W, int out_ld, int col_off) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 8 halves
+    const int per_row = W >> 3;
+    if (i >= rows * per_row) return;
+    const long long r = i / per_row;
+    const int c = (int)(i - r * per_row) << 3;
+    const long long ro = (r / L) * Lp + (r % L);
+    *reinterpret_cast<uint4*>(dst + ro * out_ld + col_off + c) = *reinterpret_cast<const uint4*>(src + r * W + c);
 }
 
 // conv_post on fp16 "activated" input a = lrelu(xs, 0.01): tanh(sum w * (a / pre_div) + b); leaky-ReLU is
@@ -645,6 +644,27 @@ int launch_f32_to_f16(const float* x, __half* hi, __half* lo, long long rows, in
     CMTTS_REQUIRE(Cpad % 8 == 0 && Cpad >= C, "f32_to_f16: Cpad must be a multiple of 8 and >= C");
     const long long n = rows * (Cpad / 8);
     f32_to_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, hi, lo, rows, C, Cpad, slope);
+    CMTTS_CHECK_LAUNCH();
+    return CMTTS_OK;
+}
+
+int launch_f32_to_f16_rows(const float* x, __half* hi, __half* lo, int B, int L, int Lp, int C, int Cpad, int out_ld,
+                           cudaStream_t s) {
+    const long long rows = (long long)B * L;
+    if (rows == 0) return CMTTS_OK;
+    CMTTS_REQUIRE(Cpad % 8 == 0 && Cpad >= C && out_ld % 8 == 0 && Lp >= L, "f32_to_f16_rows: shape");
+    const long long n = rows * (Cpad / 8);
+    f32_to_f16_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, hi, lo, rows, L, Lp, C, Cpad, out_ld);
+    CMTTS_CHECK_LAUNCH();
+    return CMTTS_OK;
+}
+
+int launch_pack_rows_f16(const __half* src, __half* dst, int B, int L, int Lp, int W, int out_ld, int col_off, cudaStream_t s) {
+    const long long rows = (long long)B * L;
+    if (rows == 0) return CMTTS_OK;
+    CMTTS_REQUIRE(W % 8 == 0 && out_ld % 8 == 0 && col_off % 8 == 0 && Lp >= L, "pack_rows_f16: shape");
+    const long long n = rows * (W / 8);
+    pack_rows_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, dst, rows, L, Lp, W, out_ld, col_off);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }

@@ -9,9 +9,8 @@ enum UmmaEpi {
     UEPI_DN_GATE = 2,  // sigmoid(gate + b) * tanh(filter + b)          -> fp16 hi/lo   (BN = 128: 64 gates | 64 filters)
     UEPI_DN_OUT = 3,   // cols <  N/2: x = (acc + b + addvec[b] + x) * out_scale (fp32, in place)
                        // cols >= N/2: skip (+)= acc + b                 (fp32)
-    UEPI_DN_OUTY = 5,  // fused "output projection + next layer's conditioner" of the y-recurrence (see pipeline.cu):
-                       // cols <  n_k2: y = acc + bias + addvec[b] + y * out_scale  (fp16 hi/lo, in place in out_h/out_lo)
-                       // cols >= n_k2: skip (+)= acc + bias                        (fp32)
+    UEPI_DN_OUTY = 5,  // y-recurrence of the residual stack (see pipeline.cu): y = acc + bias + addvec[utterance]
+                       // -> fp16 hi/lo, written in place over the y operand (out_h/out_lo)
     UEPI_F32 = 4,      // generic: v = act((acc*alpha + bias) * beta) + addvec[b] + res*res_scale ; v *= out_scale ;
                        // rows >= lens[b] -> 0 ; written as fp32 (out_f32) and/or fp16 hi/lo ; cols >= n_valid dropped
 };
@@ -28,6 +27,16 @@ struct UmmaConvParams {
     // optional SECOND activation operand (split mode, taps == 1): the contraction runs over [A | A2], i.e.
     // K = Cin + Cin2 with weights [N][Cin + Cin2]; output columns >= n_k2 contract over the first Cin only
     const __half* a2_hi; const __half* a2_lo; long long a2_bstride; int a2_ld; int Cin2; int n_k2;
+    // the first `a2_diag` channels of A2 meet BLOCK-DIAGONAL weights (an identity-like term): a tile whose output
+    // columns are [n0, n0 + BN) only loads the A2 channel blocks [n0, n0 + BN) of that range (requires a2_diag == N)
+    int a2_diag;
+    // taps index the THIRD coordinate of the A tensor map (a stack of `taps` tensors, e.g. one per layer) instead of
+    // shifting rows: K = taps * Cin over [tap][row][channel]
+    int a_tap_dim;
+    // flattened-utterance layout: B == 1, M == utterances * rows_per_utt rows, the last row of every utterance is a
+    // zero guard row (the conv's padding between neighbours); the epilogue never writes guard rows and indexes
+    // addvec by row / rows_per_utt.  0 = off (3-D tensor maps, one utterance per batch index).
+    int rows_per_utt;
     // epilogue
     const float* bias; float alpha;
     // UEPI_VOC: v = acc*alpha + bias + inv_lrelu(res) + sum ; out = lrelu(v, out_slope) as fp16
@@ -69,6 +78,11 @@ int launch_umma_resblock(const UmmaResblockParams& p, cudaStream_t s);
 
 // fp32 -> fp16 (optionally hi/lo pair, optional leaky-ReLU, optional channel zero-padding)
 int launch_f32_to_f16(const float* x, __half* hi, __half* lo, long long rows, int C, int Cpad, float slope, cudaStream_t s);
+// flattened-utterance layout (one guard row per utterance): (B, L, C) fp32 -> rows b*Lp + t of an fp16 hi/lo matrix;
+// and the same row mapping for an existing fp16 (B, L, W) tensor, placed at a column offset
+int launch_f32_to_f16_rows(const float* x, __half* hi, __half* lo, int B, int L, int Lp, int C, int Cpad, int out_ld,
+                           cudaStream_t s);
+int launch_pack_rows_f16(const __half* src, __half* dst, int B, int L, int Lp, int W, int out_ld, int col_off, cudaStream_t s);
 // HiFi-GAN output stage on fp16 activated input
 int launch_conv_post_f16(const __half* x, const float* w, const float* bias, float pre_div, float* wav, short* wav_i16,
                          float max_wav, int B, int L, int C, int K, cudaStream_t s);

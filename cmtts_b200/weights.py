@@ -104,11 +104,11 @@ def split_f16(w: torch.Tensor, scale: float = TC_W_SCALE):
 
 
 def fused_recurrence_weights(sd: Dict[str, torch.Tensor], l: int, C: int, H: int):
-    """Operands of layer l of the denoiser's y-recurrence (fp64): weights (2C, C + H) and bias (2C,).
+    """Operands of layer l of the denoiser's y-recurrence (fp64): weights (C, C + C + H) and bias (C,).
 
     With y_l = x_l + Wc_l cond + bc_l + step_l + spk_l (the k=3 conv's input, model/blocks.py:669-678) and
-    r = 1/sqrt(2): y_{l+1} = [r Wo_l[:C] | Wc_{l+1} - r Wc_l] [g_l ; cond] + r y_l + const, so the rows < C are
-    that block matrix, the rows >= C the skip half [Wo_l[C:] | 0] of the output projection (:683-686)."""
+    r = 1/sqrt(2) (:683-686):  y_{l+1} = [r Wo_l[:C] | r I | Wc_{l+1} - r Wc_l] [g_l ; y_l ; cond] + const.
+    The identity block lets y_l flow through the GEMM's operand pipeline instead of being read by the epilogue."""
     r = 1.0 / math.sqrt(2.0)
     p, pn = f"net.residual_layers.{l}.", f"net.residual_layers.{l + 1}."
     wo = sd[p + "output_projection.conv.weight"][:, :, 0].double()
@@ -117,12 +117,23 @@ def fused_recurrence_weights(sd: Dict[str, torch.Tensor], l: int, C: int, H: int
     bc = sd[p + "conditioner_projection.conv.bias"].double()
     wcn = sd[pn + "conditioner_projection.conv.weight"][:, :, 0].double()
     bcn = sd[pn + "conditioner_projection.conv.bias"].double()
-    wf = torch.zeros(2 * C, C + H, dtype=torch.float64)
-    wf[:C, :C] = r * wo[:C]
-    wf[:C, C:] = wcn - r * wc
-    wf[C:, :C] = wo[C:]
-    bf = torch.cat([r * bo[:C] + bcn - r * bc, bo[C:]])
+    wf = torch.zeros(C, 2 * C + H, dtype=torch.float64)
+    wf[:, :C] = r * wo[:C]
+    wf[:, C:2 * C] = r * torch.eye(C, dtype=torch.float64)
+    wf[:, 2 * C:] = wcn - r * wc
+    bf = r * bo[:C] + bcn - r * bc
     return wf, bf
+
+
+def skip_stack_weights(sd: Dict[str, torch.Tensor], n_layers: int, C: int):
+    """sum_l (Wo_l[C:] g_l + bo_l[C:]) (model/modules.py:629-634, blocks.py:683-686) as ONE GEMM over the stacked
+    gate outputs: weights (n_layers * C, C) with row l*C + n = Wo_l[C + n], and the summed bias (C,)  (fp64)."""
+    ws, b = [], torch.zeros(C, dtype=torch.float64)
+    for l in range(n_layers):
+        p = f"net.residual_layers.{l}.output_projection.conv."
+        ws.append(sd[p + "weight"][C:, :, 0].double())
+        b = b + sd[p + "bias"][C:].double()
+    return torch.cat(ws, dim=0), b
 
 
 class _Table:
@@ -291,14 +302,16 @@ class PackedAcoustic:
         for w in (w_in, sd["net.skip_projection.conv.weight"][:, :, 0].contiguous()):
             hi, lo = split_f16(w)
             dn16.add(hi); dn16.add(lo)
-        # y-recurrence of the residual stack (csrc/pipeline.cu, cmtts_denoiser_forward_tc): per layer l < last,
-        #   [ r Wo_l[:C] | Wc_{l+1} - r Wc_l ]   rows < C  : y_{l+1}  (K = C + H)
-        #   [   Wo_l[C:] |         0         ]   rows >= C : skip     (the kernel only contracts these over K = C)
+        # y-recurrence of the residual stack (csrc/pipeline.cu, cmtts_denoiser_forward_tc): per layer l < last the
+        # (C, 2C + H) operand of fused_recurrence_weights, then the stacked skip projection of skip_stack_weights;
         # derived in fp64, then split into fp16 hi/lo like every other operand
         for l in range(s.res_layers - 1):
             wf, bf = fused_recurrence_weights(sd, l, C, s.hidden)
             hi, lo = split_f16(wf)
             dn16.add(hi); dn16.add(lo); dn16.add(bf.to(torch.float32))
+        wsk, bsk = skip_stack_weights(sd, s.res_layers, C)
+        hi, lo = split_f16(wsk)
+        dn16.add(hi); dn16.add(lo); dn16.add(bsk.to(torch.float32))
         self.dn16 = dn16.finish()
 
         def add_pair(tab, w):

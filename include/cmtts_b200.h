@@ -192,8 +192,9 @@ int cmtts_f32_to_f16(const float* x, void* hi, void* lo, int64_t rows, int64_t C
 /* D1/D3 + S4 on tensor cores: same contract as cmtts_denoiser_forward; `w16` holds per layer
  * {cond_w hi, lo [C][H]; k3_w hi, lo [3*2C][C] (gate/filter interleaved per 64); out_w hi, lo [2C][C];
  *  out_b fp32 [2C]}, then {in_w hi, lo [C][128] (K zero-padded); skip_w hi, lo [C][C]}, then per layer
- * l < res_layers-1 the y-recurrence operands {fused_w hi, lo [2C][C+H]; fused_b fp32 [2C]} with
- * fused_w = [[r Wo_l[:C] | Wc_{l+1} - r Wc_l], [Wo_l[C:] | 0]], r = 1/sqrt(2) (cmtts_b200/weights.py);
+ * l < res_layers-1 the y-recurrence operands {y_w hi, lo [C][2C+H]; y_b fp32 [C]} with
+ * y_w = [r Wo_l[:C] | r I | Wc_{l+1} - r Wc_l], r = 1/sqrt(2), then the stacked skip projection
+ * {skip_stack_w hi, lo [res_layers*C][C] (row l*C+n = Wo_l[C+n]); summed bias fp32 [C]} (cmtts_b200/weights.py);
  * cond_hi/cond_lo are the fp16 split of the conditioner (cmtts_f32_to_f16). */
 size_t cmtts_denoiser_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t L);
 int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const* w, const void* const* w16,

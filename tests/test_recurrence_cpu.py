@@ -8,7 +8,7 @@ import torch.nn.functional as F
 
 from cmtts_b200 import synthetic
 from cmtts_b200.config import ModelSpec
-from cmtts_b200.weights import TC_W_SCALE, fused_recurrence_weights, split_f16
+from cmtts_b200.weights import TC_W_SCALE, fused_recurrence_weights, skip_stack_weights, split_f16
 
 
 def _k3(sd, y, l, C):
@@ -48,18 +48,20 @@ def test_y_recurrence_matches_residual_stack():
     wc, bc = wb(0, "conditioner_projection")
     y = x0 + cond @ wc.t() + bc + dsp[:, 0][:, None]
     yc = r * ds[:, :-1] + dsp[:, 1:] - r * dsp[:, :-1]                       # rowops.cu: dn_fuse_steps_kernel
-    skip2 = 0
+    gs = []
     for l in range(NL):
         gg = _k3(sd, y, l, C)
+        gs.append(gg)
         if l + 1 < NL:
             wf, bf = fused_recurrence_weights(sd, l, C, H)
-            assert float(wf[C:, C:].abs().max()) == 0.0
+            assert torch.equal(wf[:, C:2 * C], r * torch.eye(C, dtype=torch.float64))   # block-diagonal y segment
             hi, lo = split_f16(wf)
             wf = (hi.double() + lo.double()) / TC_W_SCALE
-            skip2 = skip2 + gg @ wf[C:, :C].t() + bf[C:]
-            y = torch.cat([gg, cond], -1) @ wf[:C].t() + bf[:C] + yc[:, l][:, None] + r * y
-        else:
-            wo, bo = wb(l, "output_projection")
-            skip2 = skip2 + gg @ wo[C:].t() + bo[C:]
+            y = torch.cat([gg, y, cond], -1) @ wf.t() + bf + yc[:, l][:, None]
+    # the skip sum as one GEMM over the stacked gate outputs
+    wsk, bsk = skip_stack_weights(sd, NL, C)
+    hi, lo = split_f16(wsk)
+    wsk = (hi.double() + lo.double()) / TC_W_SCALE
+    skip2 = torch.cat(gs, -1) @ wsk.reshape(NL, C, C).permute(1, 0, 2).reshape(C, NL * C).t() + bsk
     err = float((skip - skip2).abs().max())
     assert err <= 1e-5 * float(skip.abs().max()), err
