@@ -127,7 +127,7 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 tma_load_2d_elect(smW2 + tap * W_BLK, &tmW2, &w_full[0], 0, tap * C);
             }
             int stage = 0; uint32_t phase = 0;
-            const uint32_t bytes = (uint32_t)(cfg.box_rows * ROW_BYTES);
+            const uint32_t bytes = (uint32_t)(((cfg.dbg & 32) ? 16 : cfg.box_rows) * ROW_BYTES);   // 32: 16-row boxes (timing)
             // L2 prefetch distance (tiles): the smem ring alone (2-8 stages of 9-20 KB) holds too few bytes in flight
             // to cover the DRAM latency at this kernel's per-SM bandwidth share (ncu: producer stalled on a_empty,
             // DRAM 25-30 % busy), so the halo tiles are pulled into L2 well ahead of the ring
@@ -451,7 +451,7 @@ int launch_rb_cfg(const UmmaResblockParams& p, cudaStream_t s) {
     }
     CUtensorMap a_map, w1_map, w2_map, o_map, ot_map;
     const long long bs = (long long)p.L * C;
-    if (!make_act_map(&a_map, p.a, C, p.L, p.B, C, bs, BK, cfg.box_rows) ||
+    if (!make_act_map(&a_map, p.a, C, p.L, p.B, C, bs, BK, (cfg.dbg & 32) ? 16 : cfg.box_rows) ||
         !make_w_map(&w1_map, p.w1, C, TAPS * C, BK, C) || !make_w_map(&w2_map, p.w2, C, TAPS * C, BK, C) ||
         !make_act_map(&o_map, p.out_h, C, p.L, p.B, C, bs, 32, 32) ||              // per-warp box: C/2 (<= 32) channels
         !make_act_map(&ot_map, p.out_h, C, p.L, p.B, C, bs, 32, cfg.valid - 96)) {

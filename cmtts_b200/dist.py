@@ -102,7 +102,7 @@ class ShardedSynthesizer:
 
     def dtype_label(self) -> str:
         if self.pipe.precision == "tc":
-            return "f16 operands / f32 accumulate (tcgen05); denoiser f16 hi+lo pairs; encoder + variance adaptor f32"
+            return "f16 operands / f32 accumulate (tcgen05); vocoder plain f16, denoiser + encoder + variance adaptor f16 hi+lo pairs (fp32-class products)"
         return "f32"
 
     def dominant_kernel(self) -> str:

@@ -55,6 +55,19 @@ def main():
                          ("noStore", {"CMTTS_RB_DBG": "16"}), ("pf8", {"CMTTS_PF": "8"})]:
             res[tag] = run("vocoder_only.py", env, "voc_" + tag)
         table("vocoder", res)
+    if which == "ring":
+        res = OrderedDict()
+        for tag, env in [("base", {}), ("nb2", {"CMTTS_RB_NB": "2"}), ("skel", {"CMTTS_RB_DBG": "7"}),
+                         ("skel+pf8", {"CMTTS_RB_DBG": "7", "CMTTS_PF": "8"}), ("skel+nb2", {"CMTTS_RB_DBG": "7", "CMTTS_RB_NB": "2"}),
+                         ("noMMA+nb2", {"CMTTS_RB_DBG": "4", "CMTTS_RB_NB": "2"})]:
+            res[tag] = run("vocoder_only.py", env, "ring_" + tag)
+        table("vocoder input-ring experiments", res)
+    if which == "tma":
+        res = OrderedDict()
+        for tag, env in [("skel", {"CMTTS_RB_DBG": "7"}), ("skel16rows", {"CMTTS_RB_DBG": "39"}),
+                         ("skelNoRes", {"CMTTS_RB_DBG": "15"}), ("skel16NoRes", {"CMTTS_RB_DBG": "47"})]:
+            res[tag] = run("vocoder_only.py", env, "tma_" + tag)
+        table("TMA row-rate experiment (fused ResBlock kernel, all roles but the producer switched off)", res)
     if which in ("all", "dn"):
         res = OrderedDict()
         for tag, env in [("base", {}), ("noEpiLd", {"CMTTS_UMMA_DBG": "8"}), ("noMMA", {"CMTTS_UMMA_DBG": "32"}),
