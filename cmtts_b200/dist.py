@@ -53,9 +53,13 @@ def gather_rows(dist_mod, t: torch.Tensor) -> torch.Tensor:
     """all_gather along dim 0 (equal shapes on every rank thanks to the global paddings)."""
     if dist_mod is None or dist_mod.get_world_size() == 1:
         return t
-    parts = [torch.empty_like(t) for _ in range(dist_mod.get_world_size())]
-    dist_mod.all_gather(parts, t.contiguous())
-    return torch.cat(parts, dim=0)
+    t = t.contiguous()
+    # NCCL has no 16-bit integer type: int16 wavs travel as raw bytes
+    wire = t.view(torch.uint8) if t.dtype == torch.int16 else t
+    parts = [torch.empty_like(wire) for _ in range(dist_mod.get_world_size())]
+    dist_mod.all_gather(parts, wire)
+    out = torch.cat(parts, dim=0)
+    return out.view(torch.int16) if t.dtype == torch.int16 else out
 
 
 class ShardedSynthesizer:
