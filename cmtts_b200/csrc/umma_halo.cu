@@ -11,9 +11,9 @@
 // * RESIDENT WEIGHTS: all taps of the layer's weights (<= 96 KB) are loaded into shared memory
 //   once per CTA and reused for every tile of the persistent loop; when they do not fit (C = 128,
 //   k = 7/11) they stream through their own mbarrier ring.
-// * DEEP RINGS: as many activation stages as shared memory allows (up to 8 tiles in flight per SM)
-//   and the residual tile of the epilogue is ALSO fetched by TMA into its own ring, so the
-//   HBM-bound levels keep tens of KB in flight per SM instead of one row per thread.
+// * DEEP RING: as many activation stages as shared memory allows (up to 8 tiles in flight per SM); the
+//   residual rows of the epilogue are read from global memory (L2) into registers before the
+//   accumulator wait.
 //
 // * WIDE EPILOGUE: 8 epilogue warps (lane quarter x column half).  A single warp per SM sub-partition
 //   issues its ~12 instructions per output element back to back at the ALU dependency latency, which
@@ -22,7 +22,7 @@
 //   staging slab and TMA store (column half = one channel block, or half of one), the bias sits in
 //   shared memory, and leaky-ReLU is max(v, s v) / min(v, s v).
 //
-// Roles: warp 0 = activation TMA producer (+ resident weights), warp 3 = residual + streamed-weight
+// Roles: warp 0 = activation TMA producer (+ resident weights), warp 3 = streamed-weight
 // TMA producer, warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator (+ second issuer when the weights
 // are resident), warps 4-11 = epilogue.
 #include "umma_common.cuh"
@@ -35,7 +35,7 @@ using namespace umma;
 constexpr int MAX_STAGES = 8;
 
 struct HaloCfg {
-    int a_stages, r_stages, w_stages;   // ring depths (w_stages = 0: weights resident)
+    int a_stages, w_stages;             // ring depths (w_stages = 0: weights resident)
     int rows_alloc;                     // rows reserved per activation block (>= 128 + span)
     int box_rows;                       // 128 + span
     int pf;                             // L2 prefetch distance in tiles (0 = off; CMTTS_PF)
@@ -48,13 +48,11 @@ __device__ __forceinline__ float lrelu_inv(float v, float inv_slope) { return fm
 template <int BN, int BK, int CB, int TAPS>
 __global__ void __launch_bounds__(384, 1)
 umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                 const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
+                 const __grid_constant__ CUtensorMap tmO,
                  const UmmaConvParams p, const HaloCfg cfg) {
     constexpr int BM = 128;
     constexpr int ROW_BYTES = BK * 2;
     constexpr int W_BLK = BN * ROW_BYTES;
-    constexpr int R_BLK = BM * ROW_BYTES;          // one channel block of the residual tile
-    constexpr int R_STAGE = CB * R_BLK;
     constexpr int BNH = BN / 2;                    // output columns per epilogue warp
     constexpr int OROW = BNH * 2;                  // bytes per staged output row of one warp (128 / 64 / 32)
     constexpr int O_SLAB = 32 * OROW;              // one epilogue warp's 32 rows x BNH columns
@@ -70,17 +68,14 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smA = smem;
-    uint8_t* smR = smA + cfg.a_stages * a_stage;
-    uint8_t* smO = smR + cfg.r_stages * R_STAGE;
+    uint8_t* smO = smA + cfg.a_stages * a_stage;
     uint8_t* smW = smO + O_BYTES;
     const int w_blocks = wres ? p.taps * CB : cfg.w_stages;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smW + (size_t)w_blocks * W_BLK);
     uint64_t* a_empty = a_full + MAX_STAGES;
     uint64_t* w_full = a_empty + MAX_STAGES;
     uint64_t* w_empty = w_full + MAX_STAGES;
-    uint64_t* r_full = w_empty + MAX_STAGES;
-    uint64_t* r_empty = r_full + MAX_STAGES;
-    uint64_t* tfull = r_empty + MAX_STAGES;
+    uint64_t* tfull = w_empty + MAX_STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // float4 reads
@@ -94,7 +89,6 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < MAX_STAGES; ++i) {
             mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
             mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
-            mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 8);
         }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -139,36 +133,17 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else if (warp == 3) {
-        // ======================= residual + streamed-weight producer =======================
-        if (has_res || !wres) {
-            if (has_res) prefetch_tmap(&tmR);
+        // ======================= streamed-weight producer =======================
+        if (!wres) {
             int ws = 0; uint32_t wphase = 0;
-            int rs = 0; uint32_t rphase = 0;
-            const int PF = cfg.pf;
-            auto prefetch_res = [&](int tl) {
-                if (PF > 0 && has_res && tl < tiles)
-                    for (int cb = 0; cb < CB; ++cb) tma_prefetch_3d_elect(&tmR, cb * BK, (tl % m_tiles) * BM, tl / m_tiles);
-            };
-            for (int i = 0; i < PF; ++i) prefetch_res(blockIdx.x + i * gridDim.x);
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                const int mt = tile % m_tiles, b = tile / m_tiles;
-                prefetch_res(tile + PF * gridDim.x);
-                if (has_res) {
-                    mbar_wait(&r_empty[rs], rphase ^ 1);
-                    mbar_expect_tx_elect(&r_full[rs], R_STAGE);
-                    for (int cb = 0; cb < CB; ++cb)
-                        tma_load_3d_elect(smR + rs * R_STAGE + cb * R_BLK, &tmR, &r_full[rs], cb * BK, mt * BM, b);
-                    if (++rs == cfg.r_stages) { rs = 0; rphase ^= 1; }
-                }
-                if (!wres) {
-                    for (int tap = 0; tap < p.taps; ++tap)
-                        for (int cb = 0; cb < CB; ++cb) {
-                            mbar_wait(&w_empty[ws], wphase ^ 1);
-                            mbar_expect_tx_elect(&w_full[ws], W_BLK);
-                            tma_load_2d_elect(smW + ws * W_BLK, &tmW, &w_full[ws], cb * BK, tap * p.N);
-                            if (++ws == cfg.w_stages) { ws = 0; wphase ^= 1; }
-                        }
-                }
+                for (int tap = 0; tap < p.taps; ++tap)
+                    for (int cb = 0; cb < CB; ++cb) {
+                        mbar_wait(&w_empty[ws], wphase ^ 1);
+                        mbar_expect_tx_elect(&w_full[ws], W_BLK);
+                        tma_load_2d_elect(smW + ws * W_BLK, &tmW, &w_full[ws], cb * BK, tap * p.N);
+                        if (++ws == cfg.w_stages) { ws = 0; wphase ^= 1; }
+                    }
             }
         }
     } else if (warp == 1 || (warp == 2 && wres)) {
@@ -243,32 +218,22 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int q = warp & 3;                    // TMEM lane quarter
         const int h = (warp - 4) >> 2;             // column half
         const int row = q * 32 + lane;
-        constexpr int CHUNKS = ROW_BYTES / 16;     // 16-byte chunks per channel-block row of the residual tile: 8 or 4
-        // 16-byte chunk swizzle of the TMA-written residual tile (same pattern as the operands)
-        const int swz = (BK == 64) ? (row & 7) : ((row >> 1) & 3);
         // staging slab of this warp: rows of OROW bytes in the TMA box layout (128B / 64B swizzle by row pitch)
         const int swz_o = (OROW == 128) ? (lane & 7) : ((lane >> 1) & 3);
         uint8_t* slab = smO + (warp - 4) * O_SLAB + lane * OROW;
         const int n_base = h * BNH;
         int abuf = 0; uint32_t aphase = 0;
-        int rs = 0; uint32_t rphase = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             const int mt = tile % m_tiles, b = tile / m_tiles;
             const int t = mt * BM + row;
             const bool valid = t < p.M;
+            // residual lrelu(y) of this thread's row segment: global reads issued before the accumulator wait (the tensor
+            // was written by the previous launch, most of it is still in L2)
             uint4 rres[BNH / 8];
             if (has_res) {
-                mbar_wait(&r_full[rs], rphase);
-                const uint8_t* rb = smR + rs * R_STAGE + row * ROW_BYTES;
+                const uint4* rp = reinterpret_cast<const uint4*>(p.res_h + (long long)b * p.res_bstride + (long long)t * p.res_ld + n_base);
 #pragma unroll
-                for (int i = 0; i < BNH / 8; ++i) {
-                    const int gi = n_base / 8 + i;
-                    const int cb = gi / CHUNKS, j = gi % CHUNKS;
-                    rres[i] = *reinterpret_cast<const uint4*>(rb + cb * R_BLK + ((j ^ swz) << 4));
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&r_empty[rs]);
-                if (++rs == cfg.r_stages) { rs = 0; rphase ^= 1; }
+                for (int i = 0; i < BNH / 8; ++i) rres[i] = valid ? rp[i] : make_uint4(0u, 0u, 0u, 0u);
             }
             // MRF partial sum (last iteration of a resblock): global reads issued before the accumulator wait
             uint4 rsum[BNH / 8];
@@ -365,11 +330,10 @@ template <int BN, int BK, int CB, int TAPS>
 int launch_halo_cfg(const UmmaConvParams& p, cudaStream_t s) {
     constexpr int ROW_BYTES = BK * 2;
     constexpr int W_BLK = BN * ROW_BYTES;
-    constexpr int R_STAGE = CB * 128 * ROW_BYTES;
     constexpr int ROW_ALIGN = 1024 / ROW_BYTES;        // rows per 1024-byte swizzle-aligned unit
     constexpr size_t LIMIT = 227 * 1024;
     constexpr size_t O_BYTES = (size_t)8 * 32 * BN;        // 8 warps x 32 rows x BN/2 fp16
-    constexpr size_t FIXED = (6 * MAX_STAGES + 4) * 8 + 32 + BN * 4 + 1024 + O_BYTES;
+    constexpr size_t FIXED = (4 * MAX_STAGES + 4) * 8 + 32 + BN * 4 + 1024 + O_BYTES;
 
     HaloCfg cfg{};
     const int span = p.shift[p.taps - 1] - p.shift[0];
@@ -377,26 +341,17 @@ int launch_halo_cfg(const UmmaConvParams& p, cudaStream_t s) {
     cfg.rows_alloc = (cfg.box_rows + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
     const size_t a_stage = (size_t)CB * cfg.rows_alloc * ROW_BYTES;
     const size_t w_res = (size_t)p.taps * CB * W_BLK;
-    const bool has_res = p.res_h != nullptr;
-    // weights stay resident when that leaves room for >= 3 activation stages (+ 2 residual stages)
+    // weights stay resident when that leaves room for >= 3 activation stages
     size_t budget = LIMIT - FIXED;
-    const size_t need_min = 3 * a_stage + (has_res ? 2 * R_STAGE : 0);
     size_t w_bytes;
-    if (w_res + need_min <= budget) { cfg.w_stages = 0; w_bytes = w_res; }
+    if (w_res + 3 * a_stage <= budget) { cfg.w_stages = 0; w_bytes = w_res; }
     else { cfg.w_stages = 4; w_bytes = (size_t)cfg.w_stages * W_BLK; }
-    if (w_bytes + 2 * a_stage + (has_res ? R_STAGE : 0) > budget) return CMTTS_ERR_UNSUPPORTED;
+    if (w_bytes + 2 * a_stage > budget) return CMTTS_ERR_UNSUPPORTED;
     budget -= w_bytes;
-    // split the rest: residual ring gets ~1/3 of the bytes in flight when present
-    cfg.r_stages = 0;
-    if (has_res) {
-        size_t r = budget / 3 / R_STAGE;
-        cfg.r_stages = (int)(r < 1 ? 1 : (r > MAX_STAGES ? MAX_STAGES : r));
-        budget -= (size_t)cfg.r_stages * R_STAGE;
-    }
     size_t a = budget / a_stage;
     cfg.a_stages = (int)(a > MAX_STAGES ? MAX_STAGES : a);
     if (cfg.a_stages < 2) return CMTTS_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)cfg.a_stages * a_stage + (size_t)cfg.r_stages * R_STAGE + w_bytes + FIXED;
+    const size_t smem = (size_t)cfg.a_stages * a_stage + w_bytes + FIXED;
 
     static int pf_env = -1;
     if (pf_env < 0) { const char* e = getenv("CMTTS_PF"); pf_env = e ? atoi(e) : 0; }
@@ -410,15 +365,10 @@ int launch_halo_cfg(const UmmaConvParams& p, cudaStream_t s) {
         }
         attr_done = true;
     }
-    CUtensorMap a_map, w_map, r_map, o_map;
+    CUtensorMap a_map, w_map, o_map;
     if (!make_act_map(&a_map, p.a_hi, p.Cin, p.Lin, p.B, p.a_ld, p.a_bstride, BK, cfg.box_rows) ||
         !make_w_map(&w_map, p.w_hi, p.Cin, p.taps * p.N, BK, BN)) {
         cmtts_set_error("umma_halo: cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
-        return CMTTS_ERR_CUDA;
-    }
-    r_map = a_map;
-    if (has_res && !make_act_map(&r_map, p.res_h, p.N, p.M, p.B, p.res_ld, p.res_bstride, BK, 128)) {
-        cmtts_set_error("umma_halo: cuTensorMapEncodeTiled failed (residual)", __FILE__, __LINE__);
         return CMTTS_ERR_CUDA;
     }
     // output boxes: one per epilogue warp, BN/2 channels x 32 rows (128B swizzle for 64 channels, 64B for 32)
@@ -428,7 +378,7 @@ int launch_halo_cfg(const UmmaConvParams& p, cudaStream_t s) {
     }
     const int tiles = p.B * ((p.M + 127) / 128);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, 384, smem, s>>>(a_map, w_map, r_map, o_map, p, cfg);
+    kern<<<grid, 384, smem, s>>>(a_map, w_map, o_map, p, cfg);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }

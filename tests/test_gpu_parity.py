@@ -286,3 +286,27 @@ def test_edge_cases():
     with pytest.raises(ValueError):
         from cmtts_b200.sampler import sampler_plan
         sampler_plan(3)
+
+
+def test_acoustic_path_is_batch_invariant_under_global_padding():
+    """Utterances are independent once Tsrc_max and L_max are fixed: a sub-batch padded like the full batch
+    must reproduce its rows of the batched run BIT FOR BIT — the property the multi-GPU sharding relies on."""
+    from cmtts_b200.synthesize import Pipeline
+    spec = ModelSpec.preset("VCTK")
+    sd = synthetic.make_acoustic_state_dict(spec, seed=4)
+    ck = synthetic.make_hifigan_checkpoint(spec.hifigan, seed=7)
+    pipe = Pipeline(spec, sd, ck["generator"], DEV)
+    B, T = 6, 4
+    batch = synthetic.make_batch(spec, B, 10, 40, seed=12)
+    pre = pipe.model.dpen(batch["texts"], batch["src_lens"], batch["spker_embeds"], None)
+    L = pre["cond"].shape[1]
+    noise = draw_noise(9, (B, 1, L, 80), T + 1)
+    full = pipe(batch["texts"], batch["src_lens"], batch["spker_embeds"], T=T, generator=Replay(noise))
+    for rows in (slice(0, 2), slice(2, 6)):
+        sub = pipe(batch["texts"][rows].contiguous(), batch["src_lens"][rows].contiguous(),
+                   batch["spker_embeds"][rows].contiguous(), T=T, generator=Replay([n[rows].contiguous() for n in noise]),
+                   l_max_hook=lambda local_max: L)
+        torch.cuda.synchronize()
+        assert torch.equal(sub["mel_lens"], full["mel_lens"][rows])
+        assert torch.equal(sub["mel"], full["mel"][rows])
+        assert torch.equal(sub["wav_i16"], full["wav_i16"][rows])
