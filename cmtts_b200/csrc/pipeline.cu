@@ -690,15 +690,30 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
         u.out_h = sk_hi; u.out_lo = sk_lo; u.out_bstride = (long long)R * C; u.out_ld = C;
         CMTTS_TRY(launch_umma_conv(u, s));
     }
+    const void* const* wo = wsk + 3;                          // {out_w hi, lo [128][C] (rows >= n_mels zero); out_b [128]}
+    const bool tc_out = (model_out == nullptr) && (M % 16 == 0);
     {
         // skip projection: relu(W (sum skip / sqrt(n_layers)) + b)              modules.py:635-636
+        // (as a hi/lo pair in layer 0's g slot — free again after the skip GEMM — when the output projection runs on tensor cores)
         UmmaConvParams u = tc_same(HL{sk_hi, sk_lo}, 1, R, C, wx[2], wx[3], F(w, o + 1), C, 1, 1);
         flat(u);
         u.alpha = (float)(1.0 / sqrt((double)NLY)) * TC_W_SCALE_INV; u.act = ACT_RELU;
-        tc_out32(u, v, R, C);
+        if (tc_out) { u.out_h = g_hi; u.out_lo = g_lo; u.out_bstride = (long long)R * C; u.out_ld = C; }
+        else tc_out32(u, v, R, C);
         CMTTS_TRY(launch_umma_conv(u, s));
     }
-    // output projection (N = 80) + Karras combination stay on the fp32 kernel; it reads v through the guarded layout
+    if (tc_out) {
+        // F = W v + b ; out = c_out F + c_skip x_t  (modules.py:637, karras_diffusion.py:406) on the hi/lo kernel:
+        // N = n_mels zero-padded to 128; x_t / out are ordinary (B, L, n_mels) tensors (io_unguard)
+        UmmaConvParams u = tc_same(HL{g_hi, g_lo}, 1, R, C, wo[0], wo[1], (const float*)wo[2], 128, 1, 1);
+        flat(u);
+        u.n_valid = M; u.beta = c_out; u.io_unguard = 1;
+        u.out_f32 = out; u.out32_bstride = 0; u.out32_ld = M;
+        if (c_skip != 0.f) { u.x_f32 = const_cast<float*>(x_t); u.x_bstride = 0; u.x_ld = M; u.res_scale = c_skip; }
+        CMTTS_TRY(launch_umma_conv(u, s));
+        return CMTTS_OK;
+    }
+    // fp32 FFMA output projection (also produces the raw model output F when asked for); reads v through the guarded layout
     ConvParams p = conv_same(v, B, L, C, F(w, o + 2), F(w, o + 3), M, 1, 1, out);
     p.x_bstride = (long long)Lp * C;
     p.beta = c_out;

@@ -242,8 +242,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             bool have_pre = false;
             if constexpr (SPLIT) {
                 const float* src = nullptr;
+                const long long t_io = p.io_unguard ? (long long)(t - ub) : (long long)t;   // row in un-guarded fp32 tensors
                 if (p.epi == UEPI_DN_COND || (p.epi == UEPI_F32 && p.x_f32 != nullptr && n0 < p.n_valid))
-                    src = p.x_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + n0;
+                    src = p.x_f32 + (long long)b * p.x_bstride + t_io * p.x_ld + n0;
                 else if (p.epi == UEPI_DN_OUT) {
                     const int half_n = p.N >> 1;
                     if (n0 < half_n) src = p.x_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + n0;
@@ -251,8 +252,11 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 }
                 if (src && valid && !(p.dbg & 8)) {
                     have_pre = true;
+                    // UEPI_F32: never read past column n_valid (the row may be shorter than the tile is wide)
+                    const int lim = (p.epi == UEPI_F32) ? (p.n_valid - n0) : BNH;
 #pragma unroll
-                    for (int i = 0; i < BNH / 4; ++i) pre[i] = reinterpret_cast<const uint4*>(src)[i];
+                    for (int i = 0; i < BNH / 4; ++i)
+                        pre[i] = (4 * i + 4 <= lim) ? reinterpret_cast<const uint4*>(src)[i] : make_uint4(0u, 0u, 0u, 0u);
                 }
             } else {
                 if (p.res_h && valid) {
@@ -367,7 +371,10 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             }
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = keep ? fmaf(x[j], p.res_scale, v[j]) * p.out_scale : 0.f;
-                            if (p.out_f32) store16f(p.out_f32 + (long long)b * p.out32_bstride + (long long)t * p.out32_ld + n, v);
+                            if (p.out_f32) {
+                                const long long t_o = p.io_unguard ? (long long)(t - ub) : (long long)t;
+                                store16f(p.out_f32 + (long long)b * p.out32_bstride + t_o * p.out32_ld + n, v);
+                            }
                             if (p.out_h) {
                                 const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
                                 if (p.out_lo) store16_hilo(p.out_h + o, p.out_lo + o, v);
@@ -497,6 +504,8 @@ int launch_umma_conv(const UmmaConvParams& p_in, cudaStream_t s) {
                       "umma_conv: a block-diagonal A2 segment must span exactly the N output columns");
         CMTTS_REQUIRE(p.rows_per_utt == 0 || (p.B == 1 && p.rows_per_utt >= 2), "umma_conv: flattened layout needs B == 1");
         CMTTS_REQUIRE(!p.a_tap_dim || (p.B == 1 && !p.a2_hi), "umma_conv: a_tap_dim needs B == 1 and no second operand");
+        CMTTS_REQUIRE(!p.io_unguard || (p.rows_per_utt > 0 && p.epi == UEPI_F32 && p.n_valid % 16 == 0),
+                      "umma_conv: io_unguard needs the flattened layout, the generic epilogue and n_valid % 16 == 0");
         return launch_cfg<128, 64, 1>(p, s);
     }
     CMTTS_REQUIRE(p.epi == UEPI_VOC, "umma_conv: denoiser epilogues need split mode");

@@ -37,6 +37,9 @@ struct UmmaConvParams {
     // zero guard row (the conv's padding between neighbours); the epilogue never writes guard rows and indexes
     // addvec by row / rows_per_utt.  0 = off (3-D tensor maps, one utterance per batch index).
     int rows_per_utt;
+    // UEPI_F32 with rows_per_utt: the fp32 residual / output tensors (x_f32, out_f32) are ordinary (B, L, *) tensors
+    // WITHOUT guard rows: their row index is (flattened row - utterance index)
+    int io_unguard;
     // epilogue
     const float* bias; float alpha;
     // UEPI_VOC: v = acc*alpha + bias + inv_lrelu(res) + sum ; out = lrelu(v, out_slope) as fp16

@@ -79,12 +79,13 @@ class ShardedSynthesizer:
 
     def stage_times(self, texts, src_lens, spker_embeds, T: int, reps: int = 3) -> Dict[str, float]:
         """Instrumented passes of the same step: CUDA events on the launching stream around each
-        stage.  Returns average milliseconds per stage."""
+        stage.  Returns the MEDIAN milliseconds per stage over `reps` passes (one pass may absorb an allocator
+        or clock hiccup that a mean would smear over the stage numbers)."""
         from .sampler import karras_sample_tts, sampler_plan
 
         pipe, dev = self.pipe, self.pipe.device
         names = ["dpen", "sampler", "vocoder"]
-        acc = {n: 0.0 for n in names}
+        acc = {n: [] for n in names}
         for _ in range(reps):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
@@ -101,8 +102,8 @@ class ShardedSynthesizer:
             ev[3].record()
             torch.cuda.synchronize(dev)
             for i, n in enumerate(names):
-                acc[n] += ev[i].elapsed_time(ev[i + 1])
-        return {n: v / reps for n, v in acc.items()}
+                acc[n].append(ev[i].elapsed_time(ev[i + 1]))
+        return {n: sorted(v)[len(v) // 2] for n, v in acc.items()}
 
     def dtype_label(self) -> str:
         if self.pipe.precision == "tc":

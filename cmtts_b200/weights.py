@@ -312,6 +312,13 @@ class PackedAcoustic:
         wsk, bsk = skip_stack_weights(sd, s.res_layers, C)
         hi, lo = split_f16(wsk)
         dn16.add(hi); dn16.add(lo); dn16.add(bsk.to(torch.float32))
+        # output projection (C -> n_mels) on the hi/lo kernel: rows zero-padded to one 128-wide N tile
+        w_out = torch.zeros(128, C)
+        w_out[:s.n_mels] = sd["net.output_projection.conv.weight"][:, :, 0]
+        b_out = torch.zeros(128)
+        b_out[:s.n_mels] = sd["net.output_projection.conv.bias"]
+        hi, lo = split_f16(w_out)
+        dn16.add(hi); dn16.add(lo); dn16.add(b_out)
         self.dn16 = dn16.finish()
 
         def add_pair(tab, w):

@@ -194,7 +194,8 @@ int cmtts_f32_to_f16(const float* x, void* hi, void* lo, int64_t rows, int64_t C
  *  out_b fp32 [2C]}, then {in_w hi, lo [C][128] (K zero-padded); skip_w hi, lo [C][C]}, then per layer
  * l < res_layers-1 the y-recurrence operands {y_w hi, lo [C][2C+H]; y_b fp32 [C]} with
  * y_w = [r Wo_l[:C] | r I | Wc_{l+1} - r Wc_l], r = 1/sqrt(2), then the stacked skip projection
- * {skip_stack_w hi, lo [res_layers*C][C] (row l*C+n = Wo_l[C+n]); summed bias fp32 [C]} (cmtts_b200/weights.py);
+ * {skip_stack_w hi, lo [res_layers*C][C] (row l*C+n = Wo_l[C+n]); summed bias fp32 [C]}, then the output
+ * projection {out_w hi, lo [128][C] (rows >= n_mels zero); out_b fp32 [128]} (cmtts_b200/weights.py);
  * cond_hi/cond_lo are the fp16 split of the conditioner (cmtts_f32_to_f16). */
 size_t cmtts_denoiser_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t L);
 int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const* w, const void* const* w16,

@@ -241,6 +241,24 @@ def test_hifigan_vs_oracle_ragged_batch(precision):
         assert (wav.cpu() - ref).abs().max().item() <= WAV_TOL[precision]
 
 
+def test_hifigan_vs_oracle_bench_length():
+    """A bench-length utterance pair (L = 801 frames -> 205k samples): every CTA of the persistent vocoder kernels runs
+    many tiles, which short fixtures never exercise.  Checked against the CPU oracle (max-abs and SNR)."""
+    from cmtts_b200.vocoder import Generator
+    ck = synthetic.make_hifigan_checkpoint(HifiGanSpec(), seed=3)
+    voc = Generator(hspec=HifiGanSpec(), precision="tc").load_state_dict(ck["generator"]).to(DEV)
+    Wf = O.Weights(synthetic.fold_weight_norm(ck["generator"]))
+    mel = synthetic.make_mels(2, 80, 801, seed=11)
+    with torch.no_grad():
+        ref = O.hifigan(Wf, HifiGanSpec(), mel)
+    wav = voc(mel.to(DEV)).cpu()
+    assert wav.shape == ref.shape
+    err = (wav - ref).abs()
+    assert err.max().item() <= WAV_TOL["tc"]
+    snr = 10 * torch.log10((ref ** 2).mean() / (err ** 2).mean()).item()
+    assert snr >= 48.0, snr
+
+
 def test_whole_pipeline_int16_vs_oracle():
     from cmtts_b200.synthesize import Pipeline
     spec = ModelSpec.preset("VCTK")
@@ -288,24 +306,30 @@ def test_edge_cases():
         sampler_plan(3)
 
 
-def test_acoustic_path_is_batch_invariant_under_global_padding():
+@pytest.mark.parametrize("ds,B,lo,hi,T,parts", [("VCTK", 6, 10, 40, 4, (slice(0, 2), slice(2, 6))),
+                                                  # BASELINE.json configs[1] at full size (C2): B=32, L~800, T=4
+                                                  ("LJSpeech", 32, 80, 115, 4, (slice(0, 8), slice(24, 32)))])
+def test_acoustic_path_is_batch_invariant_under_global_padding(ds, B, lo, hi, T, parts):
     """Utterances are independent once Tsrc_max and L_max are fixed: a sub-batch padded like the full batch
-    must reproduce its rows of the batched run BIT FOR BIT — the property the multi-GPU sharding relies on."""
+    must reproduce its rows of the batched run BIT FOR BIT (mels and int16 wavs) — the property the multi-GPU sharding
+    relies on, and a size-independent check of the whole path at the bench size."""
     from cmtts_b200.synthesize import Pipeline
-    spec = ModelSpec.preset("VCTK")
+    spec = ModelSpec.preset(ds)
     sd = synthetic.make_acoustic_state_dict(spec, seed=4)
     ck = synthetic.make_hifigan_checkpoint(spec.hifigan, seed=7)
     pipe = Pipeline(spec, sd, ck["generator"], DEV)
-    B, T = 6, 4
-    batch = synthetic.make_batch(spec, B, 10, 40, seed=12)
+    batch = synthetic.make_batch(spec, B, lo, hi, seed=12)
     pre = pipe.model.dpen(batch["texts"], batch["src_lens"], batch["spker_embeds"], None)
     L = pre["cond"].shape[1]
     noise = draw_noise(9, (B, 1, L, 80), T + 1)
     full = pipe(batch["texts"], batch["src_lens"], batch["spker_embeds"], T=T, generator=Replay(noise))
-    for rows in (slice(0, 2), slice(2, 6)):
-        sub = pipe(batch["texts"][rows].contiguous(), batch["src_lens"][rows].contiguous(),
-                   batch["spker_embeds"][rows].contiguous(), T=T, generator=Replay([n[rows].contiguous() for n in noise]),
-                   l_max_hook=lambda local_max: L)
+    full = {k: full[k].clone() for k in ("mel", "mel_lens", "wav_i16")}
+    again = pipe(batch["texts"], batch["src_lens"], batch["spker_embeds"], T=T, generator=Replay(noise))
+    assert torch.equal(again["mel"], full["mel"]) and torch.equal(again["wav_i16"], full["wav_i16"])      # repeatable
+    for rows in parts:
+        spk = None if batch["spker_embeds"] is None else batch["spker_embeds"][rows].contiguous()
+        sub = pipe(batch["texts"][rows].contiguous(), batch["src_lens"][rows].contiguous(), spk, T=T,
+                   generator=Replay([n[rows].contiguous() for n in noise]), l_max_hook=lambda local_max: L)
         torch.cuda.synchronize()
         assert torch.equal(sub["mel_lens"], full["mel_lens"][rows])
         assert torch.equal(sub["mel"], full["mel"][rows])
