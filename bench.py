@@ -127,6 +127,80 @@ class ClockSampler:
                 "samples": len(rows), "window": window, "power_w_max": max(float(r[3]) for r in rows)}
 
 
+# ------------------------------------------------------------------------------------------------
+# live single-kernel probes for the roofline block: the dominant conv shapes at bench size, launched
+# through the C ABI (cmtts_umma_conv1d) and timed with CUDA events on the launching stream
+# ------------------------------------------------------------------------------------------------
+def _probe(lib, desc, ptrs, reps=10):
+    import ctypes as C
+    from cmtts_b200 import _lib
+    p = _lib.ptr
+    args = [p(t) for t in ptrs]
+
+    def launch():
+        _lib.check(lib.cmtts_umma_conv1d(C.byref(desc), *args, _lib.stream_ptr()), "umma_conv1d")
+    for _ in range(3):
+        launch()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3          # seconds per launch
+
+
+def kernel_probes(lib, dev, B, L):
+    """(a) HiFi-GAN level-1 ResBlock conv, C=128 k=11 dilation 5 with residual (largest FLOP consumer of the vocoder):
+    plain fp16 operands, algorithmic FLOPs == executed FLOPs.  (b) the denoiser's k=3 gate conv (K=768, N=512) on
+    fp16 hi/lo pairs: 3 MMAs per algorithmic MAC.  Inputs are far larger than L2 (0.4 GB / 26 MB x 2 operands re-read
+    from L2 by design), launches back to back."""
+    from cmtts_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(3)
+    out = {}
+    # (a)
+    Cc, k, dil, rows = 128, 11, 5, L * 64
+    a = torch.randn(B, rows, Cc, generator=g).half().to(dev)
+    w = (torch.randn(k * Cc, Cc, generator=g) / (Cc * k) ** 0.5).half().to(dev)
+    bias = torch.randn(Cc, generator=g).to(dev)
+    res = a.clone()
+    o = torch.empty_like(a)
+    d = _lib.UmmaDesc(B=B, M=rows, Lin=rows, N=Cc, Cin=Cc, taps=k, split=0, epi=0, a_ld=Cc, res_ld=Cc, out_ld=Cc, x_ld=0,
+                      a_bstride=rows * Cc, res_bstride=rows * Cc, out_bstride=rows * Cc, x_bstride=0, addvec_bstride=0,
+                      alpha=1.0, res_inv_slope=10.0, out_slope=0.1, out_scale=1.0, skip_accumulate=0)
+    for i in range(k):
+        d.shift[i] = (i - (k - 1) // 2) * dil
+    t = _probe(lib, d, [a, None, w, None, bias, res, None, o, None, None, None, None])
+    out["vocoder_c128_k11"] = {"seconds": t, "flops": 2.0 * B * rows * Cc * Cc * k,
+                               "algorithmic_bytes": float(B * rows * Cc * 2 * 3)}
+    del a, res, o
+    # (b)
+    Cd, R = 256, B * (L + 1)
+    y = torch.randn(1, R, Cd, generator=g)
+    yh = y.half(); yl = (y - yh.float()).half()
+    wk = torch.randn(3 * 2 * Cd, Cd, generator=g) / (3 * Cd) ** 0.5 * 1024.0
+    wh = wk.half(); wl = (wk - wh.float()).half()
+    bias2 = (torch.randn(2 * Cd, generator=g) * 0.1).to(dev)
+    gh = torch.empty(1, R, Cd, dtype=torch.float16, device=dev); gl = torch.empty_like(gh)
+    d2 = _lib.UmmaDesc(B=1, M=R, Lin=R, N=2 * Cd, Cin=Cd, taps=3, split=1, epi=2, a_ld=Cd, res_ld=Cd, out_ld=Cd, x_ld=0,
+                       a_bstride=R * Cd, res_bstride=0, out_bstride=R * Cd, x_bstride=0, addvec_bstride=0,
+                       alpha=1.0 / 1024.0, res_inv_slope=1.0, out_slope=1.0, out_scale=1.0, skip_accumulate=0)
+    d2.shift[0], d2.shift[1], d2.shift[2] = -1, 0, 1
+    t2 = _probe(lib, d2, [yh.to(dev), yl.to(dev), wh.to(dev), wl.to(dev), bias2, None, None, gh, gl, None, None, None])
+    out["denoiser_gate_k3"] = {"seconds": t2, "flops": 2.0 * R * 3 * Cd * 2 * Cd, "mma_flops": 3 * 2.0 * R * 3 * Cd * 2 * Cd}
+    return out
+
+
+def profile_traffic():
+    """DRAM bytes per launch of the probed kernels from the committed `ncu --set full` capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic_r1.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
