@@ -367,11 +367,12 @@ extern "C" int cmtts_renoise(const float* x0, const float* noise, float s1, floa
 namespace {
 struct HifiCfg {
     int n_levels, C0, n_kernels, n_dil, pre_k, post_k;
-    const int32_t *rates, *up_taps, *up_shift0, *ksize, *dil;
+    const int32_t *rates, *up_taps, *up_shift0, *ksize, *dil, *split_ok;
     explicit HifiCfg(const int32_t* c) {
         n_levels = c[0]; C0 = c[1]; n_kernels = c[2]; n_dil = c[3]; pre_k = c[4]; post_k = c[5];
         rates = c + 6; up_taps = rates + n_levels; up_shift0 = up_taps + n_levels;
         ksize = up_shift0 + n_levels; dil = ksize + n_kernels;
+        split_ok = dil + n_kernels * n_dil;          // per level: first / last packed tap only feed the first / second half of N
     }
     long long max_level_elems_per_frame() const {
         long long best = C0, rate = 1; int ch = C0;
@@ -781,6 +782,9 @@ extern "C" int cmtts_hifigan_forward_tc(const int32_t* cfg, const void* const* w
         u.w_hi = (const __half*)w[wi]; u.bias = F(w, wi + 1);
         u.alpha = (i > 0) ? inv_nk : 1.f;
         u.out_h = up; u.out_ld = r * cout; u.out_bstride = (long long)len * r * cout; u.out_slope = 0.1f;
+        // k = 2 stride, 3 packed taps starting at shift -1: phases [0, r/2) read inputs {t-1, t}, phases [r/2, r) read
+        // {t, t+1} (weights.py: pack_conv_transpose) -> each n-tile skips its all-zero tap
+        if (c.split_ok[i] && u.taps == 3 && ((r / 2) * cout) % 256 == 0) u.tap_split_n = (r / 2) * cout;
         wi += 2;
         CMTTS_TRY(launch_umma_conv(u, s));
         len *= r; ch = cout;

@@ -139,8 +139,12 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             TileSched ts(p, BN, BK);
             int nt, mt, b; bool heavy;
             while (ts.next(nt, mt, b, heavy)) {
-                const int kblocks = kblocks1 + (heavy ? kblocks2 : 0);
-                for (int kb = 0; kb < kblocks; ++kb) {
+                int kb0 = 0, kblocks = kblocks1 + (heavy ? kblocks2 : 0);
+                if (p.tap_split_n > 0) {                      // skip the tile's all-zero tap
+                    kb0 = (nt * BN < p.tap_split_n) ? 0 : cblocks;
+                    kblocks = kb0 + (p.taps - 1) * cblocks;
+                }
+                for (int kb = kb0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx_elect(&full[stage], STAGE_BYTES);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -183,11 +187,15 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             TileSched ts(p, BN, BK);
             int nt, mt, b; bool heavy;
             while (ts.next(nt, mt, b, heavy)) {
-                const int kblocks = kblocks1 + (heavy ? kblocks2 : 0);
+                int kb0 = 0, kblocks = kblocks1 + (heavy ? kblocks2 : 0);
+                if (p.tap_split_n > 0) {
+                    kb0 = (nt * BN < p.tap_split_n) ? 0 : cblocks;
+                    kblocks = kb0 + (p.taps - 1) * cblocks;
+                }
                 mbar_wait(&tempty[abuf], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_u + (uint32_t)(abuf * ACC_COLS);
-                for (int kb = 0; kb < kblocks; ++kb) {
+                for (int kb = kb0; kb < kblocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
@@ -200,13 +208,13 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 x 16B units along K
-                            umma_f16_pred(d_tmem, a0 + adv, b0 + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u, 0u);
+                            umma_f16_pred(d_tmem, a0 + adv, b0 + adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u, 0u);
                         }
                     } else {
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             const uint64_t adv = (uint64_t)(k * 2);
-                            umma_f16_pred(d_tmem + BN, a0 + adv, b1 + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u, 0u);
+                            umma_f16_pred(d_tmem + BN, a0 + adv, b1 + adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u, 0u);
                             umma_f16_pred(d_tmem + BN, a1 + adv, b0 + adv, idesc, 1u, 0u);
                         }
                     }
@@ -485,6 +493,8 @@ int launch_umma_conv(const UmmaConvParams& p_in, cudaStream_t s) {
     CMTTS_REQUIRE(p.a_hi && p.w_hi, "umma_conv: null operand");
     CMTTS_REQUIRE(p.taps >= 1 && (p.taps <= CMTTS_MAX_TAPS || p.a_tap_dim), "umma_conv: taps out of range");
     CMTTS_REQUIRE(p.Cin % 32 == 0, "umma_conv: Cin must be a multiple of 32");
+    CMTTS_REQUIRE(p.tap_split_n == 0 || (p.taps >= 2 && !p.split && p.tap_split_n % 256 == 0 && !p.a_tap_dim),
+                  "umma_conv: tap_split_n needs >= 2 taps, plain fp16 operands and a multiple of 256");
     CMTTS_REQUIRE(p.a_ld % 8 == 0 && p.a_bstride % 8 == 0, "umma_conv: activation strides must be multiples of 16 bytes");
     CMTTS_REQUIRE(((uintptr_t)p.a_hi % 16 == 0) && ((uintptr_t)p.w_hi % 16 == 0), "umma_conv: operands must be 16-byte aligned");
     if (p.B == 0 || p.M == 0 || p.N == 0) return CMTTS_OK;

@@ -52,6 +52,10 @@ struct UmmaConvParams {
     float* skip_f32; int skip_accumulate; float out_scale;
     // UEPI_F32 extras (res = x_f32 with x_bstride / x_ld)
     int act; float beta; float res_scale; const long long* lens; float* out_f32; long long out32_bstride; int out32_ld; int n_valid;
+    // transposed convs packed as 3-tap convs (weights.py: pack_conv_transpose): output columns < tap_split_n only have
+    // non-zero weights in taps [0, taps-1), columns >= tap_split_n only in taps [1, taps) -> the all-zero tap of a tile
+    // is skipped (identical results: it would add exact zeros).  0 = off.
+    int tap_split_n;
     int dbg;              // experiment bits (CMTTS_UMMA_DBG): 1 = descriptor base_offset, 2 = disable the halo kernel
 };
 

@@ -229,6 +229,18 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const bool valid = t < p.M;
             // residual lrelu(y) of this thread's row segment: global reads issued before the accumulator wait (the tensor
             // was written by the previous launch, most of it is still in L2)
+            {
+                // pull the NEXT tile's residual / partial-sum segment of this thread into L2 (one 64-128 byte line each):
+                // by the time the register loads below are issued for that tile they no longer pay a DRAM round trip
+                const int tn = tile + gridDim.x;
+                if (tn < tiles) {
+                    const int t2 = (tn % m_tiles) * BM + row, b2 = tn / m_tiles;
+                    if (t2 < p.M) {
+                        if (has_res) prefetch_l2(p.res_h + (long long)b2 * p.res_bstride + (long long)t2 * p.res_ld + n_base);
+                        if (p.sum_h) prefetch_l2(p.sum_h + (long long)b2 * p.out_bstride + (long long)t2 * p.out_ld + n_base);
+                    }
+                }
+            }
             uint4 rres[BNH / 8];
             if (has_res) {
                 const uint4* rp = reinterpret_cast<const uint4*>(p.res_h + (long long)b * p.res_bstride + (long long)t * p.res_ld + n_base);

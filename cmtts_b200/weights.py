@@ -401,7 +401,17 @@ class PackedHifiGan:
         t16.add(hi); t16.add(lo)
         self.table16 = t16.finish()
         dil = [d for ds in hspec.resblock_dilation_sizes for d in ds]
+        # per level: may a tile skip its all-zero tap?  True when the packed transposed conv has 3 taps of which the
+        # first only feeds output phases [0, u/2) and the last only phases [u/2, u) (k = 2 u, padding u/2) — checked on
+        # the actual packed weights, not assumed
+        split_ok = []
+        for i, (u, k) in enumerate(zip(hspec.upsample_rates, hspec.upsample_kernel_sizes)):
+            w, _, d0 = pack_conv_transpose(sd[f"ups.{i}.weight"], sd[f"ups.{i}.bias"], u, (k - u) // 2)   # [taps][Cin][u*Cout]
+            half = w.shape[2] // 2
+            ok = w.shape[0] == 3 and d0 == -1 and u % 2 == 0 and float(w[0][:, half:].abs().max()) == 0.0 \
+                and float(w[2][:, :half].abs().max()) == 0.0
+            split_ok.append(1 if ok else 0)
         cfg = [len(hspec.upsample_rates), C0, nk, nd, 7, wp.shape[2]] + list(hspec.upsample_rates) + taps + shift0 \
-            + list(hspec.resblock_kernel_sizes) + dil
+            + list(hspec.resblock_kernel_sizes) + dil + split_ok
         self.cfg = (C.c_int32 * len(cfg))(*cfg)
         self.hop = hspec.hop

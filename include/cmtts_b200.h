@@ -87,7 +87,9 @@ enum { CMTTS_DN_IN_W = 0, CMTTS_DN_IN_B, CMTTS_DN_FREQ, CMTTS_DN_MLP0, CMTTS_DN_
        CMTTS_DN_SPROJ, CMTTS_DN_LAYER0, CMTTS_DN_PER_LAYER = 8 };
 
 /* hifigan config: ints {n_levels, C0, n_kernels, n_dil, pre_k, post_k, rates[n_levels],
- *                       up_taps[n_levels], up_shift0[n_levels], ksize[n_kernels], dil[n_kernels*n_dil]} */
+ *                       up_taps[n_levels], up_shift0[n_levels], ksize[n_kernels], dil[n_kernels*n_dil],
+ *                       split_ok[n_levels]}   (split_ok[i] = 1: the packed transposed conv of level i has 3 taps, the
+ *                       first feeding only the first half of its s*Cout columns, the last only the second half) */
 /* hifigan weights: pre_w[k][80][C0], pre_b, then per level { up_w[taps][Cin][s*Cout], up_b[s*Cout],
  *                  per MRF resblock j of that level, per dilation m: {c1_w, c1_b, c2_w, c2_b} },
  *                  post_w[k][C], post_b */
