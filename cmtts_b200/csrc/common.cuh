@@ -59,6 +59,9 @@ struct ConvParams {
     int accumulate;
     // optional fp16 copy of the result with leaky-ReLU applied (operand of a following tensor-core conv)
     __half* out_h; float out_h_slope;
+    // opt-in for the few-rows kernel (B == 1, M <= 32, one tap): the 128-row tile kernel runs such a GEMM on 1-8 CTAs.
+    // The summation order differs from the tile kernel's, so only call sites that do not feed a quantiser set it.
+    int few_rows_ok;
 };
 
 static inline ConvParams conv_params_default() {

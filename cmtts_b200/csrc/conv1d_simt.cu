@@ -222,7 +222,66 @@ int launch_bn(const ConvParams& p, cudaStream_t s) {
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------
+// few-rows linear layer: out[m, n] = epi( sum_k x[m, k] w[k, n] ), M <= 32 (per-utterance vectors: step embedding MLP,
+// per-layer step / speaker projections).  One CTA per 32 output columns, 8 k-slices per column, x staged in shared
+// memory in 64-wide k chunks, fixed-order reduction of the slices (deterministic and independent of M).
+// ------------------------------------------------------------------------------------------
+namespace {
+constexpr int FR_ROWS = 32, FR_COLS = 32, FR_SLICES = 8, FR_KC = 64;
+
+__global__ void __launch_bounds__(FR_COLS * FR_SLICES)
+few_rows_linear_kernel(const ConvParams p) {
+    __shared__ float s_x[FR_ROWS][FR_KC + 1];
+    __shared__ float s_red[FR_ROWS][FR_COLS + 1];
+    const int tx = threadIdx.x & 31, ky = threadIdx.x >> 5;
+    const int n = blockIdx.x * FR_COLS + tx;
+    const bool n_ok = n < p.N;
+    float acc[FR_ROWS];
+#pragma unroll
+    for (int m = 0; m < FR_ROWS; ++m) acc[m] = 0.f;
+    for (int k0 = 0; k0 < p.Cin; k0 += FR_KC) {
+        for (int i = threadIdx.x; i < FR_ROWS * FR_KC; i += blockDim.x) {
+            const int m = i / FR_KC, kk = i - m * FR_KC;
+            s_x[m][kk] = (m < p.M && k0 + kk < p.Cin) ? p.x[(long long)m * p.x_ld + k0 + kk] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < FR_KC / FR_SLICES; ++j) {
+            const int kk = ky * (FR_KC / FR_SLICES) + j;
+            const float wv = (n_ok && k0 + kk < p.Cin) ? p.w[(long long)(k0 + kk) * p.N + n] : 0.f;
+#pragma unroll
+            for (int m = 0; m < FR_ROWS; ++m) acc[m] = fmaf(s_x[m][kk], wv, acc[m]);
+        }
+        __syncthreads();
+    }
+    for (int r = 0; r < FR_SLICES; ++r) {            // fixed-order reduction of the k slices
+        if (ky == r) {
+#pragma unroll
+            for (int m = 0; m < FR_ROWS; ++m) s_red[m][tx] = (r == 0 ? 0.f : s_red[m][tx]) + acc[m];
+        }
+        __syncthreads();
+    }
+    if (ky == 0 && n_ok) {
+        for (int m = 0; m < p.M; ++m) {
+            float v = fmaf(s_red[m][tx], p.alpha, p.bias ? p.bias[n] : 0.f);
+            v *= p.beta;
+            if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
+            if (p.res1) v = fmaf(p.res1[(long long)m * p.res1_ld + n], p.res1_scale, v);
+            p.out[(long long)m * p.out_ld + n] = v * p.out_scale;
+        }
+    }
+}
+}  // namespace
+
 int launch_conv1d_simt(const ConvParams& p, cudaStream_t s) {
+    if (p.few_rows_ok && p.B == 1 && p.M >= 1 && p.M <= FR_ROWS && p.taps == 1 && p.shift[0] == 0 && !p.pre_lrelu &&
+        (p.act == ACT_NONE || p.act == ACT_RELU) && !p.aux_out && !p.addvec && !p.lens && !p.accumulate && !p.out_h &&
+        p.x && p.w && p.out && p.N > 0) {
+        few_rows_linear_kernel<<<(p.N + FR_COLS - 1) / FR_COLS, FR_COLS * FR_SLICES, 0, s>>>(p);
+        CMTTS_CHECK_LAUNCH();
+        return CMTTS_OK;
+    }
     CMTTS_REQUIRE(p.x && p.w && p.out, "conv1d: null pointer");
     CMTTS_REQUIRE(p.Cin % BK == 0, "conv1d: Cin must be a multiple of 16");
     CMTTS_REQUIRE(p.N % 4 == 0 && p.x_ld % 4 == 0 && p.out_ld % 4 == 0, "conv1d: N, x_ld, out_ld must be multiples of 4");

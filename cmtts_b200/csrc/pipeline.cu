@@ -279,16 +279,20 @@ extern "C" int cmtts_denoiser_prepare(const cmtts_dims* d, const void* const* w,
     float* h = cv.take<float>((size_t)B * 4 * C);
     CMTTS_TRY(cmtts_step_sinusoid_impl(t, F(w, CMTTS_DN_FREQ), e, B, C, s));
     ConvParams p = conv_same(e, 1, B, C, F(w, CMTTS_DN_MLP0), nullptr, 4 * C, 1, 1, h);
+    p.few_rows_ok = 1;
     CMTTS_TRY(launch_conv1d_simt(p, s));
     CMTTS_TRY(launch_mish(h, (long long)B * 4 * C, s));
     p = conv_same(h, 1, B, 4 * C, F(w, CMTTS_DN_MLP2), nullptr, C, 1, 1, sv);
+    p.few_rows_ok = 1;
     CMTTS_TRY(launch_conv1d_simt(p, s));
     p = conv_same(sv, 1, B, C, F(w, CMTTS_DN_DPROJ), nullptr, NL, 1, 1, ds_all);
+    p.few_rows_ok = 1;
     CMTTS_TRY(launch_conv1d_simt(p, s));
     if (d->multi_speaker) {
         CMTTS_REQUIRE(spk_emb != nullptr && dsp_all != ds_all, "denoiser_prepare: multi-speaker needs spk_emb and a separate dsp_all");
         p = conv_same(spk_emb, 1, B, d->hidden, F(w, CMTTS_DN_SPROJ), nullptr, NL, 1, 1, dsp_all);
         p.res1 = ds_all; p.res1_bstride = 0; p.res1_ld = NL;
+        p.few_rows_ok = 1;
         CMTTS_TRY(launch_conv1d_simt(p, s));
     } else if (dsp_all != ds_all) {
         cudaMemcpyAsync(dsp_all, ds_all, (size_t)B * NL * sizeof(float), cudaMemcpyDeviceToDevice, s);
