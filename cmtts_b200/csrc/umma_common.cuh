@@ -118,8 +118,8 @@ __device__ __forceinline__ void tma_load_2d_elect(void* dst, const CUtensorMap* 
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
-// L2 prefetch of a TMA box (no shared memory, no barrier): issued several tiles ahead so that the real load, which can
-// only be issued once a shared-memory stage frees up, finds its data in L2 instead of paying a DRAM round trip
+// L2 prefetch of a TMA box (no shared memory, no barrier).  Experiment knob (CMTTS_PF): the vocoder kernels turned out
+// not to be bound by the latency of their input loads, so it is off by default.
 __device__ __forceinline__ void tma_prefetch_3d_elect(const CUtensorMap* map, int c0, int c1, int c2) {
     asm volatile(
         "{\n\t.reg .pred e;\n\t"

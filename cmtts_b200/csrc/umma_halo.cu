@@ -115,7 +115,7 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             int stage = 0; uint32_t phase = 0;
             const uint32_t bytes = (uint32_t)(CB * cfg.box_rows * ROW_BYTES);
-            // L2 prefetch of the halo tiles PF tiles ahead of the shared-memory ring (see tma_prefetch_3d_elect)
+            // optional L2 prefetch of the halo tiles PF tiles ahead of the ring (CMTTS_PF, off by default: measured no gain)
             const int PF = cfg.pf;
             auto prefetch_tile = [&](int tl) {
                 if (PF > 0 && tl < tiles)

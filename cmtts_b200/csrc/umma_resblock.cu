@@ -128,9 +128,8 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
             int stage = 0; uint32_t phase = 0;
             const uint32_t bytes = (uint32_t)(((cfg.dbg & 32) ? 16 : cfg.box_rows) * ROW_BYTES);   // 32: 16-row boxes (timing)
-            // L2 prefetch distance (tiles): the smem ring alone (2-8 stages of 9-20 KB) holds too few bytes in flight
-            // to cover the DRAM latency at this kernel's per-SM bandwidth share (ncu: producer stalled on a_empty,
-            // DRAM 25-30 % busy), so the halo tiles are pulled into L2 well ahead of the ring
+            // optional L2 prefetch of the halo tiles PF tiles ahead of the ring (CMTTS_PF, off by default: measured no gain,
+            // profiles/ablation_r1_ring.txt — the kernel is not bound by the latency of its input loads)
             const int PF = cfg.pf;
             for (int i = 0; i < PF; ++i) {
                 const int tl = blockIdx.x + i * gridDim.x;
