@@ -11,6 +11,8 @@
 #define CMTTS_ERR_UNSUPPORTED (-4)
 
 extern unsigned long long g_cmtts_launches;   // kernels launched by this library (bench evidence)
+extern int g_cmtts_umma_dbg;                  // CMTTS_UMMA_DBG experiment bits (-1: not read yet)
+extern int g_cmtts_pdl;                       // CMTTS_PDL: programmatic dependent launch on (1, default) / off (0)
 
 #define CMTTS_CHECK_LAUNCH()                                  \
     do {                                                      \

@@ -27,6 +27,10 @@ extern "C" const char* cmtts_last_error(void) { return g_err; }
 extern "C" int cmtts_abi_version(void) { return CMTTS_ABI_VERSION; }
 unsigned long long g_cmtts_launches = 0;
 extern "C" uint64_t cmtts_launch_count(void) { return g_cmtts_launches; }
+// experiment switches (tools/ab_switch.py): -1 = read the environment (CMTTS_UMMA_DBG / CMTTS_PDL) on first use
+int g_cmtts_umma_dbg = -1;
+int g_cmtts_pdl = -1;
+extern "C" void cmtts_debug_set(int32_t umma_dbg, int32_t pdl) { g_cmtts_umma_dbg = umma_dbg; g_cmtts_pdl = pdl; }
 
 namespace {
 

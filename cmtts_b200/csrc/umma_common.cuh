@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace umma {
 
@@ -61,6 +62,14 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// Programmatic dependent launch (PDL).  Every tcgen05 kernel here is launched with the programmatic-stream-serialization
+// attribute (launch_pdl below): its CTAs may become resident — and run their prologue: barrier init, TMEM allocation,
+// tensor-map prefetch, loads of constant weights — while the previous kernel of the stream is still draining its last
+// tiles.  pdl_wait() blocks until that kernel has completed and its writes are visible; it precedes every access to
+// memory another kernel produces.  pdl_trigger() lets the NEXT kernel's CTAs be scheduled as soon as this grid's
+// CTAs are all running (they take an SM only once its current CTA has exited: shared memory does not fit twice).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -71,6 +80,17 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
+}
+// One elected lane of a converged warp.  `if (elect_one()) { tcgen05.mma ...; tcgen05.commit ...; }` is the form ptxas
+// turns into bare warp-level UTCHMMA / UTCBAR instructions — PROVIDED every operand is derived from warp-uniform values
+// only (make_uniform() of the shared-memory / TMEM bases, compile-time ring indices, kernel parameters): then descriptors
+// live in uniform registers and a K = 64 block is 4 back-to-back UTCHMMA plus a few UIADD3.  With operands built from
+// ring indices in vector registers the same source costs 13-17 SASS instructions per MMA (ELECT / VOTEU / five R2UR),
+// which made the issuing warp — not the tensor pipe — the limiter of the hi/lo kernels (profiles/ncu_r1_gate_*.txt).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}" : "=r"(p));
+    return p != 0;
 }
 // Warp-convergent variants: the WHOLE warp executes these with identical operands and `issue` true in
 // exactly one lane; the instruction itself is predicated in PTX.  Keeping the surrounding control flow
@@ -253,6 +273,23 @@ static inline bool make_w_map(CUtensorMap* m, const __half* base, int Cin, int r
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// kernel launch with the PDL attribute (CMTTS_PDL=0 turns the attribute off: plain stream order)
+static inline bool pdl_enabled() {
+    if (g_cmtts_pdl < 0) { const char* e = getenv("CMTTS_PDL"); g_cmtts_pdl = e ? (atoi(e) != 0) : 1; }
+    return g_cmtts_pdl != 0;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 static inline int num_sms() {

@@ -106,7 +106,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: warp index provably uniform for ptxas
     const int cblocks = p.Cin / BK;
     const int kblocks1 = p.taps * cblocks;                // k-blocks over the first operand
     // extra k-blocks of heavy tiles (second operand); of a block-diagonal leading segment only the tile's own blocks
@@ -127,6 +127,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();      // everything below reads / writes tensors of earlier kernels
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -179,9 +181,14 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // (~60-70 cycles) against 64 tensor-pipe cycles for 128x128x16, so a single issuer kept the pipe ~65 % busy;
         // the accumulators are disjoint, so the two instruction streams need no ordering between them.
         {
+            // Issue form: `if (elect_one())` blocks whose operands all derive from warp-uniform values (make_uniform()'d
+            // bases, scalar ring counters) -> bare UTCHMMA runs with descriptors in uniform registers (umma_common.cuh).
             const bool cross = SPLIT && warp == 3;
             const uint32_t tmem_u = make_uniform(tmem_base);
             const uint32_t idesc = make_idesc(BM, BN);
+            constexpr uint64_t HI = (uint64_t)((uint32_t)((8 * BK * 2) >> 4) | (1u << 14) | ((BK == 64 ? 2u : 4u) << 29)) << 32;
+            const uint32_t s_base = make_uniform(((smem_u32(smem) >> 4) & 0x3FFF) | (1u << 16));
+            const uint32_t bar_base = make_uniform(smem_u32(full));
             int stage = 0; uint32_t phase = 0;
             int abuf = 0; uint32_t aphase = 0;
             TileSched ts(p, BN, BK);
@@ -194,36 +201,36 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 }
                 mbar_wait(&tempty[abuf], aphase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_u + (uint32_t)(abuf * ACC_COLS);
+                const uint32_t d_tmem = make_uniform(tmem_u + (uint32_t)(abuf * ACC_COLS) + (cross ? (uint32_t)BN : 0u));
                 for (int kb = kb0; kb < kblocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint32_t sb = sa + NOP * A_BYTES;
-                    const uint64_t a0 = make_smem_desc<BK>(sa), b0 = make_smem_desc<BK>(sb);
-                    const uint64_t a1 = make_smem_desc<BK>(sa + A_BYTES), b1 = make_smem_desc<BK>(sb + B_BYTES);
-                    if (p.dbg & 32) {
-                        // timing ablation: no MMAs
-                    } else if (!cross) {
+                    const uint32_t a0 = make_uniform(s_base + (uint32_t)stage * (uint32_t)(STAGE_BYTES >> 4));
+                    const uint32_t b0 = a0 + (uint32_t)((NOP * A_BYTES) >> 4);
+                    const uint32_t first = make_uniform(kb > kb0 ? 1u : 0u);
+                    if ((p.dbg & 32) == 0 && elect_one()) {      // dbg 32 = timing ablation: no MMAs
+                        if (!cross) {
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 x 16B units along K
-                            umma_f16_pred(d_tmem, a0 + adv, b0 + adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u, 0u);
-                        }
-                    } else {
+                            for (int k = 0; k < BK / 16; ++k)
+                                umma_f16(d_tmem, HI | (a0 + 2 * k), HI | (b0 + 2 * k), idesc, k > 0 ? 1u : first);
+                        } else {
+                            const uint32_t a1 = a0 + (uint32_t)(A_BYTES >> 4), b1 = b0 + (uint32_t)(B_BYTES >> 4);
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            const uint64_t adv = (uint64_t)(k * 2);
-                            umma_f16_pred(d_tmem + BN, a0 + adv, b1 + adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u, 0u);
-                            umma_f16_pred(d_tmem + BN, a1 + adv, b0 + adv, idesc, 1u, 0u);
+                            for (int k = 0; k < BK / 16; ++k)                          // A_hi W_lo
+                                umma_f16(d_tmem, HI | (a0 + 2 * k), HI | (b1 + 2 * k), idesc, k > 0 ? 1u : first);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)                          // A_lo W_hi
+                                umma_f16(d_tmem, HI | (a1 + 2 * k), HI | (b0 + 2 * k), idesc, 1u);
                         }
                     }
+                    __syncwarp();
                     umma_commit_pred(&empty[stage], 0u);   // frees the smem slot once these MMAs have read it
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit_pred(&tfull[abuf], 0u);        // accumulator complete -> epilogue
                 abuf ^= 1; if (abuf == 0) aphase ^= 1;
             }
+            (void)bar_base;
         }
     } else if (warp >= 4) {
         // ================================ epilogue ================================
@@ -362,14 +369,23 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         if (p.epi == UEPI_F32) {
                             if (n >= p.n_valid) continue;
                             const bool keep = p.lens == nullptr || (long long)t < p.lens[b];
+                            // the activation switch sits OUTSIDE the element loops: with it inside, the 16 outputs of a
+                            // chunk were evaluated one after the other behind a branch each (ncu: a K = 128 projection took
+                            // 44 us at 6 % tensor-pipe activity, every other role parked at the final barrier)
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                float u = v[j] * p.beta;
-                                if (p.act == ACT_RELU) u = fmaxf(u, 0.f);
-                                else if (p.act == ACT_GELU) u = 0.5f * u * (1.f + erff(u * 0.70710678118654752440f));
-                                else if (p.act == ACT_SWISH) u = u / (1.f + expf(-u));
-                                else if (p.act == ACT_LRELU) u = u > 0.f ? u : u * p.out_slope;
-                                v[j] = u;
+                            for (int j = 0; j < 16; ++j) v[j] *= p.beta;
+                            if (p.act == ACT_RELU) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                            } else if (p.act == ACT_GELU) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752440f));
+                            } else if (p.act == ACT_SWISH) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] = v[j] / (1.f + expf(-v[j]));
+                            } else if (p.act == ACT_LRELU) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f) + fminf(v[j], 0.f) * p.out_slope;
                             }
                             if (p.addvec) {
                                 float a[16];
@@ -478,7 +494,7 @@ int launch_cfg(const UmmaConvParams& p, cudaStream_t s) {
     }
     const int tiles = p.B * ((p.M + 127) / 128) * (p.N / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, 384, SMEM, s>>>(a0, a1, b0, b1, a2, a3, p);
+    launch_pdl(kern, grid, 384, SMEM, s, a0, a1, b0, b1, a2, a3, p);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }
@@ -486,10 +502,9 @@ int launch_cfg(const UmmaConvParams& p, cudaStream_t s) {
 }  // namespace
 
 int launch_umma_conv(const UmmaConvParams& p_in, cudaStream_t s) {
-    static int dbg_env = -1;
-    if (dbg_env < 0) { const char* e = getenv("CMTTS_UMMA_DBG"); dbg_env = e ? atoi(e) : 0; }
+    if (g_cmtts_umma_dbg < 0) { const char* e = getenv("CMTTS_UMMA_DBG"); g_cmtts_umma_dbg = e ? atoi(e) : 0; }
     UmmaConvParams p = p_in;
-    p.dbg = dbg_env;
+    p.dbg = g_cmtts_umma_dbg;
     CMTTS_REQUIRE(p.a_hi && p.w_hi, "umma_conv: null operand");
     CMTTS_REQUIRE(p.taps >= 1 && (p.taps <= CMTTS_MAX_TAPS || p.a_tap_dim), "umma_conv: taps out of range");
     CMTTS_REQUIRE(p.Cin % 32 == 0, "umma_conv: Cin must be a multiple of 32");
@@ -516,6 +531,10 @@ int launch_umma_conv(const UmmaConvParams& p_in, cudaStream_t s) {
         CMTTS_REQUIRE(!p.a_tap_dim || (p.B == 1 && !p.a2_hi), "umma_conv: a_tap_dim needs B == 1 and no second operand");
         CMTTS_REQUIRE(!p.io_unguard || (p.rows_per_utt > 0 && p.epi == UEPI_F32 && p.n_valid % 16 == 0),
                       "umma_conv: io_unguard needs the flattened layout, the generic epilogue and n_valid % 16 == 0");
+        if (p.epi == UEPI_DN_GATE && !(p.dbg & 128)) {      // halo-A variant for the denoiser's k=3 gate conv (umma_gate.cu)
+            const int rc = launch_umma_gate(p, s);
+            if (rc != CMTTS_ERR_UNSUPPORTED) return rc;
+        }
         return launch_cfg<128, 64, 1>(p, s);
     }
     CMTTS_REQUIRE(p.epi == UEPI_VOC, "umma_conv: denoiser epilogues need split mode");

@@ -56,7 +56,7 @@ struct UmmaConvParams {
     // non-zero weights in taps [0, taps-1), columns >= tap_split_n only in taps [1, taps) -> the all-zero tap of a tile
     // is skipped (identical results: it would add exact zeros).  0 = off.
     int tap_split_n;
-    int dbg;              // experiment bits (CMTTS_UMMA_DBG): 1 = descriptor base_offset, 2 = disable the halo kernel
+    int dbg;              // experiment bits (CMTTS_UMMA_DBG): 1 = descriptor base_offset, 2 = disable the halo kernel, 128 = disable the gate kernel
 };
 
 static inline UmmaConvParams umma_params_default() {
@@ -68,6 +68,9 @@ static inline UmmaConvParams umma_params_default() {
 int launch_umma_conv(const UmmaConvParams& p, cudaStream_t s);
 // halo-tile / resident-weight variant for Cin == N in {32, 64, 128}; CMTTS_ERR_UNSUPPORTED if not applicable
 int launch_umma_halo(const UmmaConvParams& p, cudaStream_t s);
+// halo-A variant of the split (hi/lo) kernel for the denoiser's gate conv (UEPI_DN_GATE, 3 taps, Cin == 256);
+// CMTTS_ERR_UNSUPPORTED if not applicable
+int launch_umma_gate(const UmmaConvParams& p, cudaStream_t s);
 
 // Fused ResBlock iteration y' = c2(lrelu(c1(a) + b1)) + b2 + inv_lrelu(a) on fp16 activated storage
 // (all tensors [B][L][C] contiguous; weights [k][C][C] fp16); see umma_resblock.cu

@@ -1,0 +1,323 @@
+// tcgen05 k-tap conv + gated activation for the denoiser's residual layers (blocks.py:677-681), fp16 hi/lo operands
+// (3 MMAs per K step, see umma_conv.cu) — the general kernel's SPLIT path restructured around what bounded it on
+// this shape: the L2 -> SM operand stream.  umma_conv_kernel<128,64,1> fetches one 128-row A tile PER TAP, i.e.
+// 3 x (hi + lo) x 16 KB per 64-channel block next to 3 x 32 KB of weights: 786 KB per 128 x 128 output tile, which
+// at the ~11 TB/s the L2 delivers to 148 SMs is 10.6 us per tile against 8.0 us of tensor-pipe time (measured:
+// 62 us per launch = 6 tiles x 10.3 us).  Here:
+//
+// * HALO A TILE: the (128 + span)-row activation tile of a channel block is fetched ONCE (hi and lo) and every tap's
+//   A operand is that tile at a row offset in the UMMA descriptor (same trick as umma_halo.cu: the 128B swizzle is a
+//   function of the absolute shared-memory address, identical for the TMA write and the UMMA read).  The K loop runs
+//   channel-block-major, tap-minor; A traffic drops 3x (786 -> 532 KB per tile);
+// * two rings: A halo tiles (2 stages x 34 KB) and weight blocks (4 stages x 32 KB), each with its own producer warp;
+// * two tcgen05.mma issuing warps as in the general kernel (main products / cross terms, separate TMEM accumulators),
+//   issued from `if (elect_one())` blocks with warp-uniform operands only (compile-time ring indices, make_uniform()'d
+//   bases): bare UTCHMMA runs, ~2 SASS instructions per MMA instead of ~15 (see issue_tiles);
+// * the DN_GATE epilogue of umma_conv.cu (8 warps, fp16 hi/lo store) with cheaper sigmoid x tanh math (gate_fast).
+//
+// Roles: warp 0 = A producer, warp 2 = TMEM allocator + weight producer, warps 1 / 3 = MMA issuers, warps 4-11 =
+// epilogue.  Summation order differs from the general kernel's (channel-block-major), results agree to fp32 rounding.
+#include "umma_common.cuh"
+#include <stdlib.h>
+
+namespace {
+
+using namespace umma;
+
+constexpr int G_BM = 128, G_BN = 128, G_BK = 64;
+constexpr int G_ROW_BYTES = G_BK * 2;                 // 128
+constexpr int G_A_STAGES = 2, G_B_STAGES = 4;
+constexpr int G_B_BYTES = G_BN * G_ROW_BYTES;         // one weight block (hi or lo)
+constexpr int G_B_STAGE = 2 * G_B_BYTES;              // hi + lo
+
+// sigmoid(g) * tanh(f) = (1 - e^{-2f}) / ((1 + e^{-g}) (1 + e^{-2f})) with two MUFU.EX2 and one MUFU.RCP, BRANCH-FREE.
+// expf / tanhf / IEEE division each carry a slow-path branch, so with them the compiler evaluated the 16 outputs of a
+// chunk strictly one after the other — ~25 dependent instructions each, no overlap — and the 8 epilogue warps were
+// ~95 % busy (ncu), i.e. the epilogue, not the tensor pipe, bounded the kernel (the same is true of the DN_GATE path
+// of umma_conv.cu).  Straight-line math lets the 16 chains interleave.  Arguments are clamped so that no intermediate
+// overflows or goes subnormal (sigmoid(-30) = 9e-14, 1 - tanh(15) = 2e-13: below fp32 resolution of the result), which
+// is what makes the .ftz approximations safe; absolute error <= ~2e-7 (ex2.approx is good to 2 ulp, the 1 - e^{-2f}
+// cancellation costs one ulp of 1) — the size of the hi/lo operands' own 2^-22 truncation.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float gate_fast(float g, float f) {
+    const float a = fminf(fmaxf(g, -30.f), 30.f) * -1.4426950408889634f;      // -g log2(e)
+    const float b = fminf(fmaxf(f, -15.f), 15.f) * -2.8853900817779268f;      // -2 f log2(e)
+    const float eg = ex2_approx(a), ef = ex2_approx(b);
+    return (1.f - ef) * rcp_approx((1.f + eg) * (1.f + ef));
+}
+
+// MMA issue loop of one warp (CROSS = false: main products into accumulator 0; true: the two cross terms into
+// accumulator 1).  ncu on the first version of this kernel (and on umma_conv_kernel's SPLIT path) showed the warp
+// issuing the cross terms busy ~100 % of the time at ~17 SASS instructions per tcgen05.mma (ELECT / VOTEU and five
+// R2UR per MMA: descriptors were built from ring indices held in vector registers) while the tensor pipe idled 40 %.
+// Here every operand of UTCHMMA is derived from warp-uniform values only: ring stage indices and phases are
+// COMPILE-TIME (the rings' depths divide the per-tile stage counts, so every tile starts at stage 0), the shared-memory
+// bases go through make_uniform() once, and the MMAs sit in `if (elect_one())` blocks (umma_common.cuh).
+template <int TAPS, int CB, bool CROSS>
+__device__ __forceinline__ void issue_tiles(const UmmaConvParams& p, uint8_t* smA, uint8_t* smB, int a_stage, int a_half,
+                                            uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full, uint64_t* b_empty,
+                                            uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base, int tiles) {
+    constexpr int BN = G_BN, ACC_COLS = 2 * G_BN;
+    static_assert(CB % G_A_STAGES == 0 && (CB * TAPS) % G_B_STAGES == 0, "every tile must start at ring stage 0");
+    constexpr int A_USES = CB / G_A_STAGES, B_USES = CB * TAPS / G_B_STAGES;   // uses of one ring stage per tile
+    const uint32_t tmem_u = make_uniform(tmem_base);
+    const uint32_t idesc = make_idesc(G_BM, BN);
+    constexpr uint32_t DESC_HI = (uint32_t)((8 * G_ROW_BYTES) >> 4) | (1u << 14) | (2u << 29);   // SBO | version | SWIZZLE_128B
+    const uint32_t tap_step = make_uniform((uint32_t)(((TAPS > 1 ? p.shift[1] - p.shift[0] : 0) * G_ROW_BYTES) >> 4));
+    const uint32_t a_half16 = make_uniform((uint32_t)(a_half >> 4));
+    const uint32_t a_stage16 = make_uniform((uint32_t)(a_stage >> 4));
+    const uint32_t a_base = make_uniform(((smem_u32(smA) >> 4) & 0x3FFF) | (1u << 16));
+    const uint32_t b_base = make_uniform(((smem_u32(smB) >> 4) & 0x3FFF) | (1u << 16));
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const uint32_t abuf = it & 1u, tphase = (it >> 1) & 1u;
+        mbar_wait(&tempty[abuf], tphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = make_uniform(tmem_u + abuf * (uint32_t)ACC_COLS + (CROSS ? (uint32_t)BN : 0u));
+#pragma unroll
+        for (int cb = 0; cb < CB; ++cb) {
+            constexpr int dummy = 0; (void)dummy;
+            const int as = cb % G_A_STAGES;
+            const uint32_t aphase = (uint32_t)((it * A_USES + cb / G_A_STAGES) & 1u);
+            mbar_wait(&a_full[as], aphase);
+            tc_fence_after();
+            const uint32_t a0 = a_base + (uint32_t)as * a_stage16;
+#pragma unroll
+            for (int tap = 0; tap < TAPS; ++tap) {
+                const int idx = cb * TAPS + tap;
+                const int bs = idx % G_B_STAGES;
+                const uint32_t bphase = (uint32_t)((it * B_USES + idx / G_B_STAGES) & 1u);
+                mbar_wait(&b_full[bs], bphase);
+                tc_fence_after();
+                const uint32_t ah = a0 + (uint32_t)tap * tap_step;     // hi halo tile at this tap's row offset
+                const uint32_t wh = b_base + (uint32_t)((bs * G_B_STAGE) >> 4);
+                if (elect_one()) {
+                    constexpr uint64_t HI = (uint64_t)DESC_HI << 32;
+                    if (!CROSS) {
+#pragma unroll
+                        for (int k = 0; k < G_BK / 16; ++k)
+                            umma_f16(d_tmem, HI | (ah + 2 * k), HI | (wh + 2 * k), idesc, (cb | tap | k) ? 1u : 0u);
+                    } else {
+                        const uint32_t wl = wh + (uint32_t)(G_B_BYTES >> 4), al = ah + a_half16;
+#pragma unroll
+                        for (int k = 0; k < G_BK / 16; ++k)                                  // A_hi W_lo
+                            umma_f16(d_tmem, HI | (ah + 2 * k), HI | (wl + 2 * k), idesc, (cb | tap | k) ? 1u : 0u);
+#pragma unroll
+                        for (int k = 0; k < G_BK / 16; ++k)                                  // A_lo W_hi
+                            umma_f16(d_tmem, HI | (al + 2 * k), HI | (wh + 2 * k), idesc, 1u);
+                    }
+                    umma_commit(&b_empty[bs]);                  // frees the weight stage once these MMAs have read it
+                    if (tap == TAPS - 1) umma_commit(&a_empty[as]);
+                    if (tap == TAPS - 1 && cb == CB - 1) umma_commit(&tfull[abuf]);   // accumulator complete -> epilogue
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+template <int TAPS, int CB>
+__global__ void __launch_bounds__(384, 1)
+umma_gate_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                 const UmmaConvParams p, const int rows_alloc, const int box_rows) {
+    constexpr int BM = G_BM, BN = G_BN;
+    constexpr int ACC_COLS = 2 * BN;                  // main | cross-term accumulator
+    constexpr int TMEM_COLS = 2 * ACC_COLS;           // double-buffered: 512 columns
+
+    const int a_half = rows_alloc * G_ROW_BYTES;      // hi (or lo) halo tile, 1024-byte multiple
+    const int a_stage = 2 * a_half;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smA = smem;
+    uint8_t* smB = smA + G_A_STAGES * a_stage;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smB + G_B_STAGES * G_B_STAGE);
+    uint64_t* a_empty = a_full + G_A_STAGES;
+    uint64_t* b_full = a_empty + G_A_STAGES;
+    uint64_t* b_empty = b_full + G_B_STAGES;
+    uint64_t* tfull = b_empty + G_B_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: warp index provably uniform for ptxas
+    const int m_tiles = (p.M + BM - 1) / BM;
+    const int n_tiles = p.N / BN;
+    const int tiles = p.B * m_tiles * n_tiles;        // n-tile fastest: the n-tiles of one row block run side by side
+    const int shift0 = p.shift[0];
+
+    if (threadIdx.x == 0) {
+        // both issuing warps commit to the ring-empty and accumulator-full barriers
+        for (int i = 0; i < G_A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }
+        for (int i = 0; i < G_B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 2); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 2); mbar_init(&tempty[i], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    if (warp != 2) pdl_wait();      // the weight producer reads constants only: it runs ahead of the previous kernel's tail
+
+    if (warp == 0) {
+        // ================================ A producer: one halo tile (hi + lo) per channel block ================================
+        prefetch_tmap(&tmA0); prefetch_tmap(&tmA1);
+        int stage = 0; uint32_t phase = 0;
+        const uint32_t bytes = (uint32_t)(2 * box_rows * G_ROW_BYTES);
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int rest = tile / n_tiles;
+            const int mt = rest % m_tiles, b = rest / m_tiles;
+#pragma unroll 1
+            for (int cb = 0; cb < CB; ++cb) {
+                mbar_wait(&a_empty[stage], phase ^ 1);
+                mbar_expect_tx_elect(&a_full[stage], bytes);
+                uint8_t* sa = smA + stage * a_stage;
+                tma_load_3d_elect(sa, &tmA0, &a_full[stage], cb * G_BK, mt * BM + shift0, b);
+                tma_load_3d_elect(sa + a_half, &tmA1, &a_full[stage], cb * G_BK, mt * BM + shift0, b);
+                if (++stage == G_A_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 2) {
+        // ================================ weight producer: (channel block, tap) blocks, hi + lo ================================
+        prefetch_tmap(&tmB0); prefetch_tmap(&tmB1);
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int nt = tile % n_tiles;
+#pragma unroll 1
+            for (int cb = 0; cb < CB; ++cb) {
+#pragma unroll 1
+                for (int tap = 0; tap < TAPS; ++tap) {
+                    mbar_wait(&b_empty[stage], phase ^ 1);
+                    mbar_expect_tx_elect(&b_full[stage], G_B_STAGE);
+                    uint8_t* sb = smB + stage * G_B_STAGE;
+                    tma_load_2d_elect(sb, &tmB0, &b_full[stage], cb * G_BK, tap * p.N + nt * BN);
+                    tma_load_2d_elect(sb + G_B_BYTES, &tmB1, &b_full[stage], cb * G_BK, tap * p.N + nt * BN);
+                    if (++stage == G_B_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1 || warp == 3) {
+        // ================================ MMA issuers ================================
+        // warp 1: A_hi W_hi -> accumulator 0; warp 3: A_hi W_lo + A_lo W_hi -> accumulator 1 (disjoint, no ordering needed)
+        if (warp == 1) issue_tiles<TAPS, CB, false>(p, smA, smB, a_stage, a_half, a_full, a_empty, b_full, b_empty, tfull, tempty, tmem_base, tiles);
+        else issue_tiles<TAPS, CB, true>(p, smA, smB, a_stage, a_half, a_full, a_empty, b_full, b_empty, tfull, tempty, tmem_base, tiles);
+    } else if (warp >= 4) {
+        // ================================ epilogue (UEPI_DN_GATE) ================================
+        // tile columns [0, BN/2) are gates, [BN/2, BN) the matching filters (weights.py gate_permutation); warp w reads
+        // TMEM lane quarter (w & 3) and one half of the gate / filter columns
+        constexpr int GH = BN / 4;
+        const int q = warp & 3;
+        const int h = (warp - 4) >> 2;
+        const int row = q * 32 + lane;
+        int abuf = 0; uint32_t tphase = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int nt = tile % n_tiles, rest = tile / n_tiles;
+            const int mt = rest % m_tiles, b = rest / m_tiles;
+            const int t = mt * BM + row;
+            bool valid = t < p.M;
+            if (p.rows_per_utt > 0) {                         // flattened layout: never write the guard row of an utterance
+                const int ub = t / p.rows_per_utt;
+                valid = valid && (t - ub * p.rows_per_utt) < p.rows_per_utt - 1;
+            }
+            // this thread's 2 x GH bias values, fetched before the accumulator wait
+            float bg[GH], bf[GH];
+            {
+                const float4* pg = reinterpret_cast<const float4*>(p.bias + nt * BN + h * GH);
+                const float4* pf = reinterpret_cast<const float4*>(p.bias + nt * BN + BN / 2 + h * GH);
+#pragma unroll
+                for (int i = 0; i < GH / 4; ++i) {
+                    const float4 x = __ldg(pg + i), y = __ldg(pf + i);
+                    bg[4 * i] = x.x; bg[4 * i + 1] = x.y; bg[4 * i + 2] = x.z; bg[4 * i + 3] = x.w;
+                    bf[4 * i] = y.x; bf[4 * i + 1] = y.y; bf[4 * i + 2] = y.z; bf[4 * i + 3] = y.w;
+                }
+            }
+            mbar_wait(&tfull[abuf], tphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t)(abuf * ACC_COLS) + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+            for (int c = 0; c < GH / 16; ++c) {
+                uint32_t rg[16], rf[16], rg2[16], rf2[16];
+                const int g0 = h * GH + c * 16;
+                tmem_ld16(taddr + g0, rg);
+                tmem_ld16(taddr + BN / 2 + g0, rf);
+                tmem_ld16(taddr + BN + g0, rg2);               // cross-term accumulator
+                tmem_ld16(taddr + BN + BN / 2 + g0, rf2);
+                tmem_ld_wait();
+                if (valid) {
+                    const int ch = nt * (BN / 2) + g0;
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float g = fmaf(__uint_as_float(rg[j]) + __uint_as_float(rg2[j]), p.alpha, bg[c * 16 + j]);
+                        const float f = fmaf(__uint_as_float(rf[j]) + __uint_as_float(rf2[j]), p.alpha, bf[c * 16 + j]);
+                        v[j] = gate_fast(g, f);
+                    }
+                    const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + ch;
+                    store16_hilo(p.out_h + o, p.out_lo + o, v);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[abuf]);
+            abuf ^= 1; if (abuf == 0) tphase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+template <int TAPS, int CB>
+int launch_gate_cfg(const UmmaConvParams& p, cudaStream_t s) {
+    const int span = p.shift[p.taps - 1] - p.shift[0];
+    const int box_rows = 128 + span;
+    const int rows_alloc = (box_rows + 7) / 8 * 8;                          // 8 rows x 128 B = one swizzle atom
+    const size_t smem = (size_t)G_A_STAGES * 2 * rows_alloc * G_ROW_BYTES + (size_t)G_B_STAGES * G_B_STAGE +
+                        (2 * G_A_STAGES + 2 * G_B_STAGES + 4) * 8 + 16 + 1024;
+    if (smem > 227 * 1024 || box_rows > 256) return CMTTS_ERR_UNSUPPORTED;
+    auto kern = umma_gate_kernel<TAPS, CB>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+            cmtts_set_error("umma_gate: cannot set dynamic shared memory size", __FILE__, __LINE__);
+            return CMTTS_ERR_CUDA;
+        }
+        attr_done = true;
+    }
+    CUtensorMap a0, a1, b0, b1;
+    if (!make_act_map(&a0, p.a_hi, p.Cin, p.Lin, p.B, p.a_ld, p.a_bstride, G_BK, box_rows) ||
+        !make_act_map(&a1, p.a_lo, p.Cin, p.Lin, p.B, p.a_ld, p.a_bstride, G_BK, box_rows) ||
+        !make_w_map(&b0, p.w_hi, p.Cin, p.taps * p.N, G_BK, G_BN) ||
+        !make_w_map(&b1, p.w_lo, p.Cin, p.taps * p.N, G_BK, G_BN)) {
+        cmtts_set_error("umma_gate: cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
+        return CMTTS_ERR_CUDA;
+    }
+    const int tiles = p.B * ((p.M + 127) / 128) * (p.N / G_BN);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    launch_pdl(kern, grid, 384, smem, s, a0, a1, b0, b1, p, rows_alloc, box_rows);
+    CMTTS_CHECK_LAUNCH();
+    return CMTTS_OK;
+}
+
+}  // namespace
+
+// Returns CMTTS_ERR_UNSUPPORTED (without setting an error) when the shape is not covered, so the caller can use the
+// general kernel.  Covered: split operands, UEPI_DN_GATE, 3 uniformly spaced taps, Cin == 256, N % 128 == 0.
+int launch_umma_gate(const UmmaConvParams& p, cudaStream_t s) {
+    if (!p.split || p.epi != UEPI_DN_GATE || p.a2_hi || p.a_tap_dim || p.tap_split_n) return CMTTS_ERR_UNSUPPORTED;
+    if (p.taps != 3 || p.Cin != 256 || p.N % G_BN != 0 || !p.bias || !p.a_lo || !p.w_lo) return CMTTS_ERR_UNSUPPORTED;
+    if (p.shift[1] - p.shift[0] != p.shift[2] - p.shift[1] || p.shift[1] <= p.shift[0]) return CMTTS_ERR_UNSUPPORTED;
+    if (((uintptr_t)p.bias % 16) != 0) return CMTTS_ERR_UNSUPPORTED;      // float4 bias loads
+    if (p.B == 0 || p.M == 0) return CMTTS_OK;
+    return launch_gate_cfg<3, 4>(p, s);
+}

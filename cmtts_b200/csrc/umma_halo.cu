@@ -80,7 +80,7 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // float4 reads
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: warp index provably uniform for ptxas
     const int m_tiles = (p.M + BM - 1) / BM;
     const int tiles = p.B * m_tiles;
     const int shift0 = p.shift[0];
@@ -102,6 +102,10 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    // PDL: weights are constants — warp 0 issues the resident weights before waiting for the previous kernel, the
+    // streamed-weight producer (warp 3) never waits; every other role touches activations and waits here
+    if (warp != 0 && warp != 3) pdl_wait();
 
     if (warp == 0) {
         // ======================= activation producer (+ resident weights) =======================
@@ -113,6 +117,7 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int cb = 0; cb < CB; ++cb)
                         tma_load_2d_elect(smW + (size_t)(tap * CB + cb) * W_BLK, &tmW, &w_full[0], cb * BK, tap * p.N);
             }
+            pdl_wait();
             int stage = 0; uint32_t phase = 0;
             const uint32_t bytes = (uint32_t)(CB * cfg.box_rows * ROW_BYTES);
             // optional L2 prefetch of the halo tiles PF tiles ahead of the ring (CMTTS_PF, off by default: measured no gain)
@@ -163,7 +168,13 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             constexpr uint32_t DESC_HI = (uint32_t)((8 * ROW_BYTES) >> 4) | (1u << 14) | ((BK == 64 ? 2u : 4u) << 29);
             const uint32_t tap_step = (uint32_t)(((p.taps > 1 ? p.shift[1] - p.shift[0] : 0) * ROW_BYTES) >> 4);
             const uint32_t cb_step = (uint32_t)(a_alloc >> 4);
-            const uint32_t w_lo0 = ((smem_u32(smW) >> 4) & 0x3FFF) | (1u << 16);
+            // Issue form: `if (elect_one())` blocks whose operands all derive from warp-uniform values (make_uniform()'d
+            // bases, scalar ring counters) -> bare UTCHMMA runs with descriptors in uniform registers (umma_common.cuh).
+            constexpr uint64_t HI = (uint64_t)DESC_HI << 32;
+            const uint32_t w_lo0 = make_uniform(((smem_u32(smW) >> 4) & 0x3FFF) | (1u << 16));
+            const uint32_t a_base = make_uniform(((smem_u32(smA) >> 4) & 0x3FFF) | (1u << 16));
+            const uint32_t a_stage16 = make_uniform((uint32_t)(a_stage >> 4));
+            const uint32_t tap_step_u = make_uniform(tap_step), cb_step_u = make_uniform(cb_step);
             const int ntaps = TAPS > 0 ? TAPS : p.taps;
             int stage = first % cfg.a_stages; uint32_t phase = (uint32_t)((first / cfg.a_stages) & 1);
             int ws = 0; uint32_t wphase = 0;
@@ -174,21 +185,25 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&tempty[abuf], aphase ^ 1);
                 mbar_wait(&a_full[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_u + (uint32_t)(abuf * BN);
-                const uint32_t a_lo0 = ((smem_u32(smA + stage * a_stage) >> 4) & 0x3FFF) | (1u << 16);
+                const uint32_t d_tmem = make_uniform(tmem_u + (uint32_t)(abuf * BN));
+                const uint32_t a_lo0 = make_uniform(a_base + (uint32_t)stage * a_stage16);
                 if (wres) {
+                    if (elect_one()) {
 #pragma unroll
-                    for (int tap = 0; tap < ntaps; ++tap) {
+                        for (int tap = 0; tap < ntaps; ++tap) {
 #pragma unroll
-                        for (int cb = 0; cb < CB; ++cb) {
-                            const uint32_t a_lo = a_lo0 + tap * tap_step + cb * cb_step;
-                            const uint32_t w_lo = w_lo0 + (uint32_t)(((tap * CB + cb) * W_BLK) >> 4);
+                            for (int cb = 0; cb < CB; ++cb) {
+                                const uint32_t a_lo = a_lo0 + tap * tap_step_u + cb * cb_step_u;
+                                const uint32_t w_lo = w_lo0 + (uint32_t)(((tap * CB + cb) * W_BLK) >> 4);
 #pragma unroll
-                            for (int k = 0; k < BK / 16; ++k)
-                                umma_f16_pred(d_tmem, ((uint64_t)DESC_HI << 32) | (a_lo + 2 * k), ((uint64_t)DESC_HI << 32) | (w_lo + 2 * k),
-                                         idesc, (tap | cb | k) ? 1u : 0u, 0u);
+                                for (int k = 0; k < BK / 16; ++k)
+                                    umma_f16(d_tmem, HI | (a_lo + 2 * k), HI | (w_lo + 2 * k), idesc, (tap | cb | k) ? 1u : 0u);
+                            }
                         }
+                        umma_commit(&a_empty[stage]);
+                        umma_commit(&tfull[abuf]);
                     }
+                    __syncwarp();
                 } else {
 #pragma unroll
                     for (int tap = 0; tap < ntaps; ++tap) {
@@ -196,19 +211,21 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int cb = 0; cb < CB; ++cb) {
                             mbar_wait(&w_full[ws], wphase);
                             tc_fence_after();
-                            const uint32_t a_lo = a_lo0 + tap * tap_step + cb * cb_step;
-                            const uint32_t w_lo = w_lo0 + (uint32_t)((ws * W_BLK) >> 4);
+                            const uint32_t a_lo = a_lo0 + tap * tap_step_u + cb * cb_step_u;
+                            const uint32_t w_lo = make_uniform(w_lo0 + (uint32_t)((ws * W_BLK) >> 4));
+                            if (elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < BK / 16; ++k)
-                                umma_f16_pred(d_tmem, ((uint64_t)DESC_HI << 32) | (a_lo + 2 * k), ((uint64_t)DESC_HI << 32) | (w_lo + 2 * k),
-                                         idesc, (tap | cb | k) ? 1u : 0u, 0u);
-                            umma_commit_pred(&w_empty[ws], 0u);
+                                for (int k = 0; k < BK / 16; ++k)
+                                    umma_f16(d_tmem, HI | (a_lo + 2 * k), HI | (w_lo + 2 * k), idesc, (tap | cb | k) ? 1u : 0u);
+                                umma_commit(&w_empty[ws]);
+                            }
+                            __syncwarp();
                             if (++ws == cfg.w_stages) { ws = 0; wphase ^= 1; }
                         }
                     }
+                    umma_commit_pred(&a_empty[stage], 0u);
+                    umma_commit_pred(&tfull[abuf], 0u);
                 }
-                umma_commit_pred(&a_empty[stage], 0u);
-                umma_commit_pred(&tfull[abuf], 0u);
                 stage += step;
                 if (stage >= cfg.a_stages) { stage -= cfg.a_stages; phase ^= 1; }
             }
@@ -390,7 +407,7 @@ int launch_halo_cfg(const UmmaConvParams& p, cudaStream_t s) {
     }
     const int tiles = p.B * ((p.M + 127) / 128);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, 384, smem, s>>>(a_map, w_map, o_map, p, cfg);
+    launch_pdl(kern, grid, 384, smem, s, a_map, w_map, o_map, p, cfg);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }

@@ -91,7 +91,7 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     float* s_b1 = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // float4 reads
     float* s_b2 = s_b1 + C;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: warp index provably uniform for ptxas
     const int tiles = p.B * cfg.m_tiles;
     const int p1d = ((TAPS - 1) / 2) * p.dil;      // conv1 half-span in rows
 
@@ -114,6 +114,8 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    if (warp != 0) pdl_wait();      // PDL: warp 0 issues the (constant) resident weights first, see below
     // TMEM columns: acc1[b] at b*C (b < nb), acc2[b] at RB_MAX_NB*C + b*C
     const int nb = cfg.nb;
 
@@ -126,6 +128,7 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 tma_load_2d_elect(smW1 + tap * W_BLK, &tmW1, &w_full[0], 0, tap * C);
                 tma_load_2d_elect(smW2 + tap * W_BLK, &tmW2, &w_full[0], 0, tap * C);
             }
+            pdl_wait();
             int stage = 0; uint32_t phase = 0;
             const uint32_t bytes = (uint32_t)(((cfg.dbg & 32) ? 16 : cfg.box_rows) * ROW_BYTES);   // 32: 16-row boxes (timing)
             // optional L2 prefetch of the halo tiles PF tiles ahead of the ring (CMTTS_PF, off by default: measured no gain,
@@ -155,11 +158,13 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // a 128 x C x 16 MMA occupies the tensor pipe for C <= 64, so conv1 and conv2 are issued by TWO warps:
         // a single issuer left the pipe idle ~45 % of the time with every other role waiting on it (ncu).
         {
-            const uint32_t issue = 0;
+            // Issue form: `if (elect_one())` blocks, operands derived from warp-uniform values only (umma_common.cuh)
             const uint32_t tmem_u = make_uniform(tmem_base);
             const uint32_t idesc = make_idesc(BM, C);
-            const uint32_t tap_step1 = (uint32_t)((p.dil * ROW_BYTES) >> 4);
-            const uint32_t w1_lo = ((smem_u32(smW1) >> 4) & 0x3FFF) | (1u << 16);
+            const uint32_t tap_step1 = make_uniform((uint32_t)((p.dil * ROW_BYTES) >> 4));
+            const uint32_t w1_lo = make_uniform(((smem_u32(smW1) >> 4) & 0x3FFF) | (1u << 16));
+            const uint32_t a_base = make_uniform(((smem_u32(smA) >> 4) & 0x3FFF) | (1u << 16));
+            const uint32_t a_alloc16 = make_uniform((uint32_t)(a_alloc >> 4));
             mbar_wait(&w_full[0], 0);
             tc_fence_after();
             int stage = 0; uint32_t phase = 0;
@@ -168,19 +173,22 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 mbar_wait(&acc1_empty[b1], ph1 ^ 1);
                 mbar_wait(&a_full[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_u + (uint32_t)(b1 * C);
-                const uint32_t a_lo = ((smem_u32(smA + stage * a_alloc) >> 4) & 0x3FFF) | (1u << 16);
-                if (!(cfg.dbg & 4))
+                const uint32_t d_tmem = make_uniform(tmem_u + (uint32_t)(b1 * C));
+                const uint32_t a_lo = make_uniform(a_base + (uint32_t)stage * a_alloc16);
+                if (elect_one()) {
+                    if (!(cfg.dbg & 4))
 #pragma unroll
-                for (int tap = 0; tap < TAPS; ++tap) {
+                    for (int tap = 0; tap < TAPS; ++tap) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_f16_pred(d_tmem, ((uint64_t)DESC_HI << 32) | (a_lo + tap * tap_step1 + 2 * k),
-                                 ((uint64_t)DESC_HI << 32) | (w1_lo + (uint32_t)((tap * W_BLK) >> 4) + 2 * k), idesc,
-                                 (tap | k) ? 1u : 0u, issue);
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | (a_lo + tap * tap_step1 + 2 * k),
+                                     ((uint64_t)DESC_HI << 32) | (w1_lo + (uint32_t)((tap * W_BLK) >> 4) + 2 * k), idesc,
+                                     (tap | k) ? 1u : 0u);
+                    }
+                    umma_commit(&a_empty[stage]);      // input stage free once conv1 has read it
+                    umma_commit(&acc1_full[b1]);
                 }
-                umma_commit_pred(&a_empty[stage], issue);      // input stage free once conv1 has read it
-                umma_commit_pred(&acc1_full[b1], issue);
+                __syncwarp();
                 if (++stage == cfg.a_stages) { stage = 0; phase ^= 1; }
                 if (++b1 == nb) { b1 = 0; ph1 ^= 1; }
             }
@@ -188,11 +196,11 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     } else if (warp == 2) {
         // ======================= conv2 issuer =======================
         {
-            const uint32_t issue = 0;
             const uint32_t tmem_u = make_uniform(tmem_base);
             const uint32_t idesc = make_idesc(BM, C);
             constexpr uint32_t tap_step2 = (uint32_t)(ROW_BYTES >> 4);
-            const uint32_t w2_lo = ((smem_u32(smW2) >> 4) & 0x3FFF) | (1u << 16);
+            const uint32_t w2_lo = make_uniform(((smem_u32(smW2) >> 4) & 0x3FFF) | (1u << 16));
+            const uint32_t t_base = make_uniform(((smem_u32(smT) >> 4) & 0x3FFF) | (1u << 16));
             mbar_wait(&w_full[0], 0);
             tc_fence_after();
             int b2 = 0; uint32_t ph2 = 0;                     // t-tile ring
@@ -201,19 +209,22 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 mbar_wait(&t_full[b2], ph2);
                 mbar_wait(&acc2_empty[ab], aph ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_u + (uint32_t)(RB_MAX_NB * C + ab * C);
-                const uint32_t t_lo = ((smem_u32(smT + b2 * T_ALLOC) >> 4) & 0x3FFF) | (1u << 16);
-                if (!(cfg.dbg & 4))
+                const uint32_t d_tmem = make_uniform(tmem_u + (uint32_t)(RB_MAX_NB * C + ab * C));
+                const uint32_t t_lo = make_uniform(t_base + (uint32_t)b2 * (uint32_t)(T_ALLOC >> 4));
+                if (elect_one()) {
+                    if (!(cfg.dbg & 4))
 #pragma unroll
-                for (int tap = 0; tap < TAPS; ++tap) {
+                    for (int tap = 0; tap < TAPS; ++tap) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_f16_pred(d_tmem, ((uint64_t)DESC_HI << 32) | (t_lo + tap * tap_step2 + 2 * k),
-                                 ((uint64_t)DESC_HI << 32) | (w2_lo + (uint32_t)((tap * W_BLK) >> 4) + 2 * k), idesc,
-                                 (tap | k) ? 1u : 0u, issue);
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | (t_lo + tap * tap_step2 + 2 * k),
+                                     ((uint64_t)DESC_HI << 32) | (w2_lo + (uint32_t)((tap * W_BLK) >> 4) + 2 * k), idesc,
+                                     (tap | k) ? 1u : 0u);
+                    }
+                    umma_commit(&t_empty[b2]);
+                    umma_commit(&acc2_full[ab]);
                 }
-                umma_commit_pred(&t_empty[b2], issue);
-                umma_commit_pred(&acc2_full[ab], issue);
+                __syncwarp();
                 if (++b2 == nb) { b2 = 0; ph2 ^= 1; }
                 if (++ab == cfg.nb2) { ab = 0; aph ^= 1; }
             }
@@ -459,7 +470,7 @@ int launch_rb_cfg(const UmmaResblockParams& p, cudaStream_t s) {
     }
     const int tiles = p.B * cfg.m_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, RB_THREADS, smem, s>>>(a_map, w1_map, w2_map, o_map, ot_map, p, cfg);
+    launch_pdl(kern, grid, RB_THREADS, smem, s, a_map, w1_map, w2_map, o_map, ot_map, p, cfg);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }

@@ -36,6 +36,10 @@ int cmtts_abi_version(void);
 const char* cmtts_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 uint64_t cmtts_launch_count(void);
+/* experiment switches for A/B timing in one process (tools/ab_switch.py); production code never calls it.
+ * umma_dbg: bit field of CMTTS_UMMA_DBG (2 = no halo kernel, 128 = no gate kernel, ...); pdl: 1/0 = programmatic
+ * dependent launch on/off; -1 = take the value from the environment */
+void cmtts_debug_set(int32_t umma_dbg, int32_t pdl);
 
 /* ---- model dimensions shared by the acoustic entry points ---- */
 typedef struct cmtts_dims {
