@@ -419,12 +419,12 @@ def main():
                     "note": "timed live with CUDA events (10 back-to-back launches through the C ABI at bench size); "
                             "traffic = dram__bytes_read+write of the committed ncu --set full capture (profiles/)"}
         roofline_other = [
-            {"kernel": "umma_conv_kernel<128,64,SPLIT> (denoiser k=3 gate conv, K=768 N=512, fp16 hi/lo: 3 MMAs per MAC; "
+            {"kernel": "umma_gate_kernel<3,4> (denoiser k=3 gate conv, K=768 N=512, fp16 hi/lo: 3 MMAs per MAC; "
                        "80 launches per step)", "bound": "tensor", "unit": "TFLOP/s", "peak": peaks["tflops"],
              "achieved": dn["flops"] / dn["seconds"] / 1e12, "frac": dn["flops"] / dn["seconds"] / 1e12 / peaks["tflops"],
              "achieved_mma": dn["mma_flops"] / dn["seconds"] / 1e12, "frac_mma": dn["mma_flops"] / dn["seconds"] / 1e12 / peaks["tflops"],
              "us_per_launch": dn["seconds"] * 1e6,
-             "traffic": tr.get("umma_conv_kernel<128,64,1> gate", {}).get("dram_bytes_per_launch")},
+             "traffic": tr.get("umma_gate_kernel<3,4>", {}).get("dram_bytes_per_launch")},
             {"kernel": "HiFi-GAN stage (all vocoder launches of one step)", "bound": "tensor", "unit": "TFLOP/s",
              "peak": peaks["tflops"], "achieved": achieved, "frac": achieved / peaks["tflops"], "stage_ms": stage_ms["vocoder"],
              "algorithmic_flops": voc_flops,

@@ -80,7 +80,10 @@ struct TileSched {
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-template <int BN, int BK, int SPLIT, int STAGES>
+// EPI is a template parameter: one instantiation carries ONE epilogue.  With all of them inlined behind run-time
+// switches the epilogue section alone was 135 KB of SASS and the epilogue warps spent 28 % of their time on
+// instruction-cache misses (ncu "no_inst", profiles/ncu_r1_gate_rec_summary.txt).
+template <int BN, int BK, int SPLIT, int STAGES, int EPI>
 __global__ void __launch_bounds__(384, 1)
 umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -258,9 +261,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if constexpr (SPLIT) {
                 const float* src = nullptr;
                 const long long t_io = p.io_unguard ? (long long)(t - ub) : (long long)t;   // row in un-guarded fp32 tensors
-                if (p.epi == UEPI_DN_COND || (p.epi == UEPI_F32 && p.x_f32 != nullptr && n0 < p.n_valid))
+                if (EPI == UEPI_DN_COND || (EPI == UEPI_F32 && p.x_f32 != nullptr && n0 < p.n_valid))
                     src = p.x_f32 + (long long)b * p.x_bstride + t_io * p.x_ld + n0;
-                else if (p.epi == UEPI_DN_OUT) {
+                else if (EPI == UEPI_DN_OUT) {
                     const int half_n = p.N >> 1;
                     if (n0 < half_n) src = p.x_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + n0;
                     else if (p.skip_accumulate) src = p.skip_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + (n0 - half_n);
@@ -268,7 +271,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 if (src && valid && !(p.dbg & 8)) {
                     have_pre = true;
                     // UEPI_F32: never read past column n_valid (the row may be shorter than the tile is wide)
-                    const int lim = (p.epi == UEPI_F32) ? (p.n_valid - n0) : BNH;
+                    const int lim = (EPI == UEPI_F32) ? (p.n_valid - n0) : BNH;
 #pragma unroll
                     for (int i = 0; i < BNH / 4; ++i)
                         pre[i] = (4 * i + 4 <= lim) ? reinterpret_cast<const uint4*>(src)[i] : make_uint4(0u, 0u, 0u, 0u);
@@ -287,7 +290,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
             if (p.dbg & 64) {
                 // timing ablation: the epilogue does nothing
-            } else if (SPLIT && p.epi == UEPI_DN_GATE) {
+            } else if (SPLIT && EPI == UEPI_DN_GATE) {
                 // tile columns [0, BN/2) are gates, [BN/2, BN) the matching filters (weights.py gate_permutation)
                 constexpr int GH = BN / 4;                        // gate columns per column-half
 #pragma unroll
@@ -321,6 +324,23 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             } else {
 #pragma unroll
                 for (int c = 0; c < BNH / 16; ++c) {
+                    const int n = n0 + c * 16;
+                    // bias / per-utterance vector of this chunk: issued BEFORE the TMEM loads so the two latencies overlap
+                    float bia[16], av[16];
+                    const bool n_ok = (EPI != UEPI_F32) || n < p.n_valid;
+                    const bool want_av = valid && n_ok && p.addvec != nullptr &&
+                                         (EPI == UEPI_DN_COND || EPI == UEPI_DN_OUTY || EPI == UEPI_F32 ||
+                                          (EPI == UEPI_DN_OUT && n < (p.N >> 1)));
+                    if (p.bias && n_ok) load16f(p.bias + n, bia);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) bia[j] = 0.f;
+                    }
+                    if (want_av) load16f(p.addvec + (long long)ub * p.addvec_bstride + n, av);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) av[j] = 0.f;
+                    }
                     uint32_t r[16];
                     tmem_ld16(taddr + h * BNH + c * 16, r);
                     if constexpr (SPLIT) {
@@ -333,10 +353,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         tmem_ld_wait();
                     }
                     if (!valid) continue;
-                    const int n = n0 + c * 16;
                     float v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, p.bias ? p.bias[n + j] : 0.f);
+                    for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, bia[j]);
                     if constexpr (!SPLIT) {   // UEPI_VOC
                         const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
                         if (have_pre) {
@@ -366,7 +385,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             x[4 * i] = __uint_as_float(u.x); x[4 * i + 1] = __uint_as_float(u.y);
                             x[4 * i + 2] = __uint_as_float(u.z); x[4 * i + 3] = __uint_as_float(u.w);
                         }
-                        if (p.epi == UEPI_F32) {
+                        if (EPI == UEPI_F32) {
                             if (n >= p.n_valid) continue;
                             const bool keep = p.lens == nullptr || (long long)t < p.lens[b];
                             // the activation switch sits OUTSIDE the element loops: with it inside, the 16 outputs of a
@@ -387,12 +406,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f) + fminf(v[j], 0.f) * p.out_slope;
                             }
-                            if (p.addvec) {
-                                float a[16];
-                                load16f(p.addvec + (long long)ub * p.addvec_bstride + n, a);
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) v[j] += a[j];
-                            }
+                            for (int j = 0; j < 16; ++j) v[j] += av[j];     // zeros without addvec
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = keep ? fmaf(x[j], p.res_scale, v[j]) * p.out_scale : 0.f;
                             if (p.out_f32) {
@@ -404,27 +419,21 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                                 if (p.out_lo) store16_hilo(p.out_h + o, p.out_lo + o, v);
                                 else store16h(p.out_h + o, v);          // plain fp16 (vocoder activated storage)
                             }
-                        } else if (p.epi == UEPI_DN_COND) {
-                            float a[16];
-                            load16f(p.addvec + (long long)ub * p.addvec_bstride + n, a);
+                        } else if (EPI == UEPI_DN_COND) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] += a[j] + x[j];
+                            for (int j = 0; j < 16; ++j) v[j] += av[j] + x[j];
                             const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
                             store16_hilo(p.out_h + o, p.out_lo + o, v);
-                        } else if (p.epi == UEPI_DN_OUTY) {
-                            float a[16];
-                            load16f(p.addvec + (long long)ub * p.addvec_bstride + n, a);
+                        } else if (EPI == UEPI_DN_OUTY) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] += a[j];
+                            for (int j = 0; j < 16; ++j) v[j] += av[j];
                             const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
                             store16_hilo(p.out_h + o, p.out_lo + o, v);
                         } else {  // UEPI_DN_OUT
                             const int half_n = p.N >> 1;
                             if (n < half_n) {
-                                float a[16];
-                                load16f(p.addvec + (long long)ub * p.addvec_bstride + n, a);
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) v[j] = (v[j] + a[j] + x[j]) * p.out_scale;
+                                for (int j = 0; j < 16; ++j) v[j] = (v[j] + av[j] + x[j]) * p.out_scale;
                                 store16f(p.x_f32 + (long long)b * p.x_bstride + (long long)t * p.x_ld + n, v);
                             } else {
 #pragma unroll
@@ -454,7 +463,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 // host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------
 
-template <int BN, int BK, int SPLIT>
+template <int BN, int BK, int SPLIT, int EPI = UEPI_VOC>
 int launch_cfg(const UmmaConvParams& p, cudaStream_t s) {
     constexpr int NOP = SPLIT ? 2 : 1;
     constexpr int STAGE_BYTES = NOP * (128 * BK * 2 + BN * BK * 2);
@@ -462,7 +471,7 @@ int launch_cfg(const UmmaConvParams& p, cudaStream_t s) {
     constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
     static_assert(STAGES >= 2, "pipeline needs at least two stages");
     constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
-    auto kern = umma_conv_kernel<BN, BK, SPLIT, STAGES>;
+    auto kern = umma_conv_kernel<BN, BK, SPLIT, STAGES, EPI>;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM) != cudaSuccess) {
@@ -535,7 +544,17 @@ int launch_umma_conv(const UmmaConvParams& p_in, cudaStream_t s) {
             const int rc = launch_umma_gate(p, s);
             if (rc != CMTTS_ERR_UNSUPPORTED) return rc;
         }
-        return launch_cfg<128, 64, 1>(p, s);
+        CMTTS_REQUIRE(p.bias == nullptr || ((uintptr_t)p.bias % 16) == 0, "umma_conv: bias must be 16-byte aligned");
+        CMTTS_REQUIRE(p.addvec == nullptr || (((uintptr_t)p.addvec % 16) == 0 && p.addvec_bstride % 4 == 0),
+                      "umma_conv: addvec must be 16-byte aligned");
+        switch (p.epi) {
+            case UEPI_DN_COND: return launch_cfg<128, 64, 1, UEPI_DN_COND>(p, s);
+            case UEPI_DN_GATE: return launch_cfg<128, 64, 1, UEPI_DN_GATE>(p, s);
+            case UEPI_DN_OUT: return launch_cfg<128, 64, 1, UEPI_DN_OUT>(p, s);
+            case UEPI_DN_OUTY: return launch_cfg<128, 64, 1, UEPI_DN_OUTY>(p, s);
+            case UEPI_F32: return launch_cfg<128, 64, 1, UEPI_F32>(p, s);
+            default: CMTTS_REQUIRE(false, "umma_conv: unknown split-mode epilogue");
+        }
     }
     CMTTS_REQUIRE(p.epi == UEPI_VOC, "umma_conv: denoiser epilogues need split mode");
     if (!(p.dbg & 2)) {
