@@ -92,10 +92,9 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}" : "=r"(p));
     return p != 0;
 }
-// Warp-convergent variants: the WHOLE warp executes these with identical operands and `issue` true in
-// exactly one lane; the instruction itself is predicated in PTX.  Keeping the surrounding control flow
-// convergent lets ptxas hold descriptors / addresses in uniform registers instead of emitting an
-// ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop in front of every UTCHMMA / UTMALDG.
+// Warp-convergent predicated variants (the whole warp executes them with identical operands; the instruction itself is
+// predicated on elect.sync in PTX).  Still used for barrier commits outside elect blocks and by the TMA producers; the
+// MMA issue loops use `if (elect_one())` + umma_f16 / umma_commit instead (see above).
 __device__ __forceinline__ void umma_f16_pred(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                               uint32_t accum, uint32_t /*issue*/) {
     asm volatile(

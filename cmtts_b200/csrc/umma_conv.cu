@@ -14,11 +14,13 @@
 // * 128B- (BK=64) or 64B- (BK=32, for the 32-channel level) swizzled K-major operand tiles, shared
 //   by the TMA tensor maps and the UMMA shared-memory descriptors;
 // * `split` mode (denoiser): operands are fp16 hi/lo pairs (v = hi + lo, 22 significant bits) and
-//   every K step issues A_hi W_hi + A_hi W_lo + A_lo W_hi into the same fp32 accumulator — fp32-class
+//   every K step issues A_hi W_hi (accumulator 0) + A_hi W_lo + A_lo W_hi (accumulator 1) — fp32-class
 //   products on the fp16 tensor pipe (the dropped lo*lo term is ~2^-22 relative), needed for the
 //   1e-3 mel tolerance through 20 residual layers;
 // * fused epilogues (bias, conditioner/step/speaker adds, gated activation, residual, skip / MRF
-//   accumulation, leaky-ReLU for the next conv's operand) — see UmmaEpi in umma_conv.cuh.
+//   accumulation, leaky-ReLU for the next conv's operand) — see UmmaEpi in umma_conv.cuh; the epilogue type is a
+//   template parameter (one epilogue per instantiation) and its element loops are straight-line code;
+// * the denoiser's k=3 gate conv has its own kernel (umma_gate.cu); this one keeps a DN_GATE path as its fallback.
 #include "umma_common.cuh"
 #include <stdlib.h>
 
@@ -180,9 +182,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     } else if (warp == 1 || (SPLIT && warp == 3)) {
         // ================================ MMA issuer(s) ================================
         // SPLIT: warp 1 issues the main products A_hi W_hi (accumulator 0), warp 3 the cross terms A_hi W_lo +
-        // A_lo W_hi (accumulator 1).  One tcgen05.mma costs ~10 uniform-datapath instructions of descriptor set-up
-        // (~60-70 cycles) against 64 tensor-pipe cycles for 128x128x16, so a single issuer kept the pipe ~65 % busy;
-        // the accumulators are disjoint, so the two instruction streams need no ordering between them.
+        // A_lo W_hi (accumulator 1); the accumulators are disjoint, so the two instruction streams need no ordering
+        // between them.
         {
             // Issue form: `if (elect_one())` blocks whose operands all derive from warp-uniform values (make_uniform()'d
             // bases, scalar ring counters) -> bare UTCHMMA runs with descriptors in uniform registers (umma_common.cuh).
@@ -191,7 +192,6 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const uint32_t idesc = make_idesc(BM, BN);
             constexpr uint64_t HI = (uint64_t)((uint32_t)((8 * BK * 2) >> 4) | (1u << 14) | ((BK == 64 ? 2u : 4u) << 29)) << 32;
             const uint32_t s_base = make_uniform(((smem_u32(smem) >> 4) & 0x3FFF) | (1u << 16));
-            const uint32_t bar_base = make_uniform(smem_u32(full));
             int stage = 0; uint32_t phase = 0;
             int abuf = 0; uint32_t aphase = 0;
             TileSched ts(p, BN, BK);
@@ -233,7 +233,6 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 umma_commit_pred(&tfull[abuf], 0u);        // accumulator complete -> epilogue
                 abuf ^= 1; if (abuf == 0) aphase ^= 1;
             }
-            (void)bar_base;
         }
     } else if (warp >= 4) {
         // ================================ epilogue ================================

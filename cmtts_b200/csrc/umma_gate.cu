@@ -77,7 +77,6 @@ __device__ __forceinline__ void issue_tiles(const UmmaConvParams& p, uint8_t* sm
         const uint32_t d_tmem = make_uniform(tmem_u + abuf * (uint32_t)ACC_COLS + (CROSS ? (uint32_t)BN : 0u));
 #pragma unroll
         for (int cb = 0; cb < CB; ++cb) {
-            constexpr int dummy = 0; (void)dummy;
             const int as = cb % G_A_STAGES;
             const uint32_t aphase = (uint32_t)((it * A_USES + cb / G_A_STAGES) & 1u);
             mbar_wait(&a_full[as], aphase);

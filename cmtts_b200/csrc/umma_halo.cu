@@ -154,16 +154,15 @@ umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == 1 || (warp == 2 && wres)) {
         // ======================= MMA issuer(s) =======================
         // With resident weights TWO warps issue, on alternating tiles (warp 1: even, warp 2: odd; the accumulator
-        // buffer is the tile parity): each tcgen05.mma costs ~10 uniform-datapath instructions of descriptor set-up
-        // (~60-70 cycles), which is more than a 128 x 64 x 16 MMA occupies the tensor pipe and left a single issuer
-        // as the limiter of the C <= 64 shapes.  With streamed weights the ring is consumed in tile order, so one
-        // warp issues (those shapes are bound by the L2 -> SM weight traffic anyway).
+        // buffer is the tile parity), a split that dates from the predicated issue form (13-17 SASS instructions per
+        // tcgen05.mma, more than a 128 x 64 x 16 MMA occupies the tensor pipe); it is kept with the elect-branch form
+        // because the two warps also overlap their barrier waits.  With streamed weights the ring is consumed in tile
+        // order, so one warp issues (those shapes are bound by the L2 -> SM weight traffic anyway).
         {
             const int first = wres ? warp - 1 : 0, step = wres ? 2 : 1;
             const uint32_t tmem_u = make_uniform(tmem_base);
-            // The issuing thread is a single lane: every integer instruction on its path delays the next
-            // tcgen05.mma.  With the tap count a template parameter the loops unroll completely, all
-            // descriptor offsets fold into immediates / one IADD each, and the tensor pipe stays fed.
+            // With the tap count a template parameter the loops unroll completely and all descriptor offsets fold
+            // into immediates / one UIADD3 each.
             const uint32_t idesc = make_idesc(BM, BN);
             constexpr uint32_t DESC_HI = (uint32_t)((8 * ROW_BYTES) >> 4) | (1u << 14) | ((BK == 64 ? 2u : 4u) << 29);
             const uint32_t tap_step = (uint32_t)(((p.taps > 1 ? p.shift[1] - p.shift[0] : 0) * ROW_BYTES) >> 4);

@@ -18,7 +18,8 @@ def gate_fast_f32(g, f):
 
 def ref(g, f):
     g = g.astype(np.float64); f = f.astype(np.float64)
-    return (1.0 / (1.0 + np.exp(-g))) * np.tanh(f)
+    with np.errstate(over="ignore"):                 # exp(1e4) = inf -> sigmoid = 0 exactly, which is the right limit
+        return (1.0 / (1.0 + np.exp(-g))) * np.tanh(f)
 
 
 def test_gate_math_matches_sigmoid_tanh():
