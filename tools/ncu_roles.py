@@ -6,7 +6,9 @@ the roles — recognised by their landmark instructions (UTMALDG / UTCHMMA / LDT
 (= end of a role's tile loop) between two landmarks of different kinds — and prints, per role: samples, samples spent
 spinning on an mbarrier (try_wait loop), top stall reasons and top opcodes.  A role that never spins is the bottleneck.
 
-    python tools/ncu_roles.py report.ncu-rep [launch index, default 0]
+    python tools/ncu_roles.py report.ncu-rep [launch index | kernel-name regex, default 0]
+
+(the source page may list a launch more than once, so its indices are not those of the raw page: select by name)
 """
 import collections
 import csv
@@ -22,6 +24,11 @@ def load(rep, idx):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+    if not isinstance(idx, int):
+        hits = [k for k, i in enumerate(starts[:-1]) if re.search(idx, rows[i][1].replace("(int)", "").replace(" ", ""))]
+        if not hits:
+            raise SystemExit(f"no launch matches {idx!r}")
+        idx = hits[0]
     rows = rows[starts[idx]:starts[idx + 1]]
     name, hdr = rows[0][1], rows[1]
     body = [r for r in rows[2:] if len(r) == len(hdr) and r[0].startswith("0x")]
@@ -30,7 +37,8 @@ def load(rep, idx):
 
 def main():
     rep = sys.argv[1]
-    idx = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    idx = sys.argv[2] if len(sys.argv) > 2 else "0"
+    idx = int(idx) if idx.isdigit() else idx
     name, hdr, body = load(rep, idx)
     ci = {h: i for i, h in enumerate(hdr)}
     addr = [int(r[ci["Address"]], 16) for r in body]
