@@ -184,3 +184,113 @@ def rtf_like_reference(pipe: Pipeline, texts, src_lens, spker_embeds, T: int, ou
     dur0 = mel_lens[0] * pipe.spec.hop_length / pipe.spec.sampling_rate
     total = sum(mel_lens) * pipe.spec.hop_length / pipe.spec.sampling_rate
     return elapsed / dur0, elapsed / total, elapsed
+
+
+# ------------------------------------------------------------------------------------------------
+# command line: the reference's `python synthesize.py ...` (synthesize.py:227-397), same flags
+# ------------------------------------------------------------------------------------------------
+def get_configs_of(dataset: str, config_dir: str = "./config"):
+    """utils/tools.py:25-34: `<config_dir>/<dataset>/{preprocess,model,train}.yaml` (cwd-relative in the reference)."""
+    import yaml
+
+    out = []
+    for name in ("preprocess", "model", "train"):
+        with open(os.path.join(config_dir, dataset, name + ".yaml")) as f:
+            out.append(yaml.load(f, Loader=yaml.FullLoader))
+    return tuple(out)
+
+
+def build_arg_parser() -> argparse.ArgumentParser:
+    """The reference's flags (synthesize.py:229-310) with their names and defaults.  Its copy-pasted help strings and
+    the float defaults of `--model_path` / `--T` are not reproduced; `--model_path` is required here (the reference
+    crashes in os.path.join without it).  Added: --config_dir, --hifigan_dir, --device, --checkpoint,
+    --forward_controls, --batch_size (the reference hard-codes 8, :368)."""
+    p = argparse.ArgumentParser(prog="python -m cmtts_b200.synthesize")
+    p.add_argument("--restore_step", type=int, required=True)
+    p.add_argument("--path_tag", type=str, default="")
+    p.add_argument("--model", type=str, choices=["naive", "aux", "shallow"], default="naive", help="training model type")
+    p.add_argument("--teacher_forced", action="store_true")
+    p.add_argument("--mode", type=str, choices=["batch", "single"], required=True,
+                   help="synthesize a source file (batch) or one sentence (single)")
+    p.add_argument("--source", type=str, default=None, help="file in the format of train.txt / val.txt (batch mode)")
+    p.add_argument("--text", type=str, default=None, help="raw text (single mode)")
+    p.add_argument("--speaker_id", type=str, default="p225", help="speaker for multi-speaker models (single mode)")
+    p.add_argument("--dataset", type=str, required=True, help="config/<dataset>/*.yaml")
+    p.add_argument("--pitch_control", type=float, default=1.0)
+    p.add_argument("--energy_control", type=float, default=1.0)
+    p.add_argument("--duration_control", type=float, default=1.0)
+    p.add_argument("--result_path", type=str, default=None, help="output directory (default: train.yaml path.result_path)")
+    p.add_argument("--model_path", type=str, required=True, help="directory that holds CMDenoiserTTS/model<step>.pt")
+    p.add_argument("--T", type=int, default=1, choices=[1, 2, 4], help="consistency sampling steps")
+    p.add_argument("--config_dir", type=str, default="./config")
+    p.add_argument("--hifigan_dir", type=str, default="hifigan", help="directory of config.json + generator_*.pth.tar")
+    p.add_argument("--device", type=str, default="cuda:0")
+    p.add_argument("--checkpoint", type=str, default="model",
+                   help="model | target_model | teacher_model | ema_<rate> (train_util.py:890-917)")
+    p.add_argument("--forward_controls", action="store_true",
+                   help="hand the p/e/d controls to the variance adaptor (the reference parses but never forwards them)")
+    p.add_argument("--batch_size", type=int, default=8)
+    return p
+
+
+def check_args(args) -> None:
+    """synthesize.py:312-320 (asserts in the reference)."""
+    if args.mode == "batch":
+        if args.text is not None:
+            raise ValueError("--text is for --mode single")
+        if args.teacher_forced:
+            raise NotImplementedError("--teacher_forced needs ground-truth features (training data path, out of scope)")
+        if args.source is None:
+            raise ValueError("--mode batch needs --source")
+    if args.mode == "single":
+        if args.source is not None or args.text is None or args.teacher_forced:
+            raise ValueError("--mode single needs --text and neither --source nor --teacher_forced")
+
+
+def prepare_batches(args, preprocess_config, model_config, g2p=None):
+    """synthesize.py:358-394: the list of 7-tuple batches for either mode."""
+    from .frontend import TextDataset, single_batch
+
+    if args.mode == "batch":
+        return list(TextDataset(args.source, preprocess_config, model_config).batches(args.batch_size))
+    return [single_batch(args.text, args.speaker_id, preprocess_config, model_config, g2p)]
+
+
+def main(argv=None) -> List[str]:
+    """Text in, WAV files out, through the CUDA hot path; returns the paths written.  Unlike the reference the
+    checkpoint and vocoder are loaded once, not per batch (synthesize.py:203)."""
+    from .output import AsyncWavWriter, synth_samples
+    from .vocoder import get_vocoder
+
+    args = build_arg_parser().parse_args(argv)
+    check_args(args)
+    preprocess_config, model_config, train_config = get_configs_of(args.dataset, args.config_dir)
+    path_tag = "_{}".format(args.path_tag) if args.path_tag != "" else ""
+    result_path = args.result_path or (train_config["path"]["result_path"] + "_{}{}".format(args.model, path_tag))
+    # only len() of cwt_scales is read on this path (pitch_tools.py:246); the reference computes it with pycwt (:333-336)
+    preprocess_config["preprocessing"]["pitch"].setdefault("cwt_scales", [0.0] * 10)
+    batchs = prepare_batches(args, preprocess_config, model_config)
+    if not torch.cuda.is_available():
+        raise _lib.CmttsError("cmtts_b200.synthesize needs a CUDA device (there is no CPU fallback for the hot path)")
+    device = torch.device(args.device)
+    speaker = model_config["vocoder"]["speaker"]
+    vocoder = get_vocoder(model_config, device,
+                          checkpoint_path=os.path.join(args.hifigan_dir, f"generator_{speaker}.pth.tar"),
+                          hifigan_config=os.path.join(args.hifigan_dir, "config.json"))
+    tool = CMTotalTTSSynthesize(args.model_path, args.restore_step, args, preprocess_config, model_config, train_config,
+                                p_control=args.pitch_control, e_control=args.energy_control,
+                                d_control=args.duration_control, device=device, checkpoint=args.checkpoint,
+                                forward_controls=args.forward_controls)
+    written: List[str] = []
+    with torch.no_grad(), AsyncWavWriter() as writer:
+        for batch in batchs:
+            batch = to_device(batch, device)
+            out_put = tool.synthesize(batch)
+            written += synth_samples(args, batch, out_put, vocoder, model_config, preprocess_config, result_path,
+                                     tool.diffusion, writer=writer)
+    return written
+
+
+if __name__ == "__main__":
+    for path in main():
+        print(path)
