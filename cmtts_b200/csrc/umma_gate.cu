@@ -1,9 +1,10 @@
 // tcgen05 k-tap conv + gated activation for the denoiser's residual layers (blocks.py:677-681), fp16 hi/lo operands
-// (3 MMAs per K step, see umma_conv.cu) — the general kernel's SPLIT path restructured around what bounded it on
-// this shape: the L2 -> SM operand stream.  umma_conv_kernel<128,64,1> fetches one 128-row A tile PER TAP, i.e.
-// 3 x (hi + lo) x 16 KB per 64-channel block next to 3 x 32 KB of weights: 786 KB per 128 x 128 output tile, which
-// at the ~11 TB/s the L2 delivers to 148 SMs is 10.6 us per tile against 8.0 us of tensor-pipe time (measured:
-// 62 us per launch = 6 tiles x 10.3 us).  Here:
+// (3 MMAs per K step, see umma_conv.cu): the general kernel's SPLIT path specialised for this one shape (K = 3 x 256,
+// N = 512, 80 launches per step).  What the profiles said, in the order it was learnt (profiles/ncu_r1_gate_roles.txt):
+// the general kernel streams 786 KB of operands per 128 x 128 tile (one A tile PER TAP); fetching the A tile once cut
+// that by a third and changed nothing (62 us) — the kernel was bound by the warp issuing the cross-term MMAs (~100 % busy
+// at 15 SASS instructions per tcgen05.mma) AND by its epilogue warps (libm expf / tanhf evaluated one output at a
+// time); with both fixed it runs in 48 us at 79 % tensor-pipe activity.
 //
 // * HALO A TILE: the (128 + span)-row activation tile of a channel block is fetched ONCE (hi and lo) and every tap's
 //   A operand is that tile at a row offset in the UMMA descriptor (same trick as umma_halo.cu: the 128B swizzle is a
