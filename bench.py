@@ -1,17 +1,24 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the CM-TTS inference hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--T 4] [--batch 32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config C1|C2|C3|C4|C5] [--T t] [--batch b] [--scaling weak|strong] [--shard balanced|contiguous]
 
-One "step" = one pass of the hot path over one synthetic LJSpeech-shape batch
-(BASELINE.json configs[1]: B=32 utterances, 80..115 phonemes -> L ~ 800 mel frames, T=4 solver
-steps, HiFi-GAN V1): encoder + variance adaptor -> T consistency evaluations -> vocoder -> int16.
+One "step" = one pass of the hot path over one synthetic batch: encoder + variance adaptor -> T consistency
+evaluations -> HiFi-GAN -> int16.  Workloads are BASELINE.json's configs:
+  C1  LJSpeech, single text (1 utterance of 20..40 phonemes), T=1          — latency of single_synthesize_lj.sh
+  C2  LJSpeech, 32 utterances per GPU of 80..115 phonemes (L ~ 800), T=4   — THE DEFAULT, the line the driver records
+  C3  VCTK multi-speaker, global batch 64 (8 per GPU on 8 GPUs) of 20..60 phonemes, T=1
+  C4  LibriTTS zero-shot shapes, global batch 128 (16 per GPU on 8 GPUs) of 60..150 phonemes, T=4
+  C5  HiFi-GAN generator only: (batch, 80, 1024) mels -> int16, --batch 1..256
+--scaling weak keeps the per-GPU batch fixed as N grows, strong keeps the global batch fixed.
 Metric: valid mel-frames per second (sum of mel_lens / time), whole job over all N GPUs.
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each key means.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -27,6 +34,21 @@ import torch  # noqa: E402
 METRIC = "mel_frames_per_sec"
 UNIT = "mel-frames/s"
 
+# per_gpu: utterances per GPU under weak scaling; global_batch: the fixed batch under strong scaling
+CONFIGS = {
+    "C1": dict(dataset="LJSpeech", per_gpu=1, global_batch=1, T=1, lo=20, hi=40,
+               what="LJSpeech single text (single_synthesize_lj.sh:2-7)"),
+    "C2": dict(dataset="LJSpeech", per_gpu=32, global_batch=32, T=4, lo=80, hi=115,
+               what="LJSpeech batch=32, ~800 frames (BASELINE.json configs[1])"),
+    "C3": dict(dataset="VCTK", per_gpu=8, global_batch=64, T=1, lo=20, hi=60,
+               what="VCTK multi-speaker batch=64 over 8 GPUs (configs[2])"),
+    "C4": dict(dataset="LibriTTS", per_gpu=16, global_batch=128, T=4, lo=60, hi=150,
+               what="LibriTTS zero-shot batch=128 over 8 GPUs (configs[3])"),
+    "C5": dict(dataset="LJSpeech", per_gpu=32, global_batch=32, T=0, lo=0, hi=0,
+               what="HiFi-GAN generator only, 80 x 1024 mels (configs[4])"),
+}
+C5_FRAMES = 1024
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -34,19 +56,41 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--T", type=int, default=4)
-    ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
-    ap.add_argument("--dataset", default="LJSpeech")
-    ap.add_argument("--src-lo", type=int, default=80)
-    ap.add_argument("--src-hi", type=int, default=115)
-    ap.add_argument("--cpu-sample", type=int, default=6, help="utterances in the CPU-baseline sample")
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    ap.add_argument("--T", type=int, default=None, help="solver steps (default: the config's)")
+    ap.add_argument("--batch", type=int, default=None, help="utterances per GPU (weak) / global batch (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--shard", default="balanced", choices=["balanced", "contiguous"],
+                    help="N>1: balanced = length-bucketed shards, per-shard padding (no collective in the model); "
+                         "contiguous = equal row slices padded to the global L_max (bit-identical to the single-GPU batch)")
+    ap.add_argument("--dataset", default=None)
+    ap.add_argument("--src-lo", type=int, default=None)
+    ap.add_argument("--src-hi", type=int, default=None)
+    ap.add_argument("--cpu-sample", type=int, default=None, help="utterances in the CPU sample (default: 4 beside the GPU "
+                    "arm, 8 = the reference's own DataLoader batch size in the reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel launch profile / roofline pass")
+    ap.add_argument("--synthetic-vocoder", action="store_true",
+                    help="synthetic HiFi-GAN weights even when the reference's generator_universal.pth.tar is staged")
     ap.add_argument("--ffma-frontend", action="store_true",
                     help="run the encoder / variance-adaptor GEMMs on the fp32 FFMA kernels instead of the hi/lo "
                          "tensor-core kernel")
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
                     help="tc: tcgen05 tensor cores (fp16 operands, fp32 accumulate; hi/lo pairs in the denoiser); fp32: FFMA yardstick")
-    return ap.parse_args()
+    a = ap.parse_args()
+    c = CONFIGS[a.config]
+    a.dataset = a.dataset or c["dataset"]
+    a.T = c["T"] if a.T is None else a.T
+    a.src_lo = c["lo"] if a.src_lo is None else a.src_lo
+    a.src_hi = c["hi"] if a.src_hi is None else a.src_hi
+    return a
+
+
+def global_batch_size(args, world: int) -> int:
+    c = CONFIGS[args.config]
+    if args.scaling == "weak":
+        return (args.batch if args.batch is not None else c["per_gpu"]) * world
+    return args.batch if args.batch is not None else c["global_batch"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -128,73 +172,34 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# live single-kernel probes for the roofline block: the dominant conv shapes at bench size, launched
-# through the C ABI (cmtts_umma_conv1d) and timed with CUDA events on the launching stream
+# per-kernel launch profile of ONE step (cmtts_prof_begin / cmtts_prof_end of the C ABI: a CUDA event after every
+# launch of the library on the launching stream) -> each kernel's share of the step, algorithmic rate, roofline
 # ------------------------------------------------------------------------------------------------
-def _probe(lib, desc, ptrs, reps=10):
-    import ctypes as C
+def kernel_profile(lib, step_fn, dev):
     from cmtts_b200 import _lib
-    p = _lib.ptr
-    args = [p(t) for t in ptrs]
-
-    def launch():
-        _lib.check(lib.cmtts_umma_conv1d(C.byref(desc), *args, _lib.stream_ptr()), "umma_conv1d")
-    for _ in range(3):
-        launch()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(reps):
-        launch()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps * 1e-3          # seconds per launch
-
-
-def kernel_probes(lib, dev, B, L):
-    """(a) HiFi-GAN level-1 ResBlock conv, C=128 k=11 dilation 5 with residual (largest FLOP consumer of the vocoder):
-    plain fp16 operands, algorithmic FLOPs == executed FLOPs.  (b) the denoiser's k=3 gate conv (K=768, N=512) on
-    fp16 hi/lo pairs: 3 MMAs per algorithmic MAC.  Inputs are far larger than L2 (0.4 GB / 26 MB x 2 operands re-read
-    from L2 by design), launches back to back."""
-    from cmtts_b200 import _lib
-    g = torch.Generator(device="cpu").manual_seed(3)
-    out = {}
-    # (a)
-    Cc, k, dil, rows = 128, 11, 5, L * 64
-    a = torch.randn(B, rows, Cc, generator=g).half().to(dev)
-    w = (torch.randn(k * Cc, Cc, generator=g) / (Cc * k) ** 0.5).half().to(dev)
-    bias = torch.randn(Cc, generator=g).to(dev)
-    res = a.clone()
-    o = torch.empty_like(a)
-    d = _lib.UmmaDesc(B=B, M=rows, Lin=rows, N=Cc, Cin=Cc, taps=k, split=0, epi=0, a_ld=Cc, res_ld=Cc, out_ld=Cc, x_ld=0,
-                      a_bstride=rows * Cc, res_bstride=rows * Cc, out_bstride=rows * Cc, x_bstride=0, addvec_bstride=0,
-                      alpha=1.0, res_inv_slope=10.0, out_slope=0.1, out_scale=1.0, skip_accumulate=0)
-    for i in range(k):
-        d.shift[i] = (i - (k - 1) // 2) * dil
-    t = _probe(lib, d, [a, None, w, None, bias, res, None, o, None, None, None, None])
-    out["vocoder_c128_k11"] = {"seconds": t, "flops": 2.0 * B * rows * Cc * Cc * k,
-                               "algorithmic_bytes": float(B * rows * Cc * 2 * 3)}
-    del a, res, o
-    # (b)
-    Cd, R = 256, B * (L + 1)
-    y = torch.randn(1, R, Cd, generator=g)
-    yh = y.half(); yl = (y - yh.float()).half()
-    wk = torch.randn(3 * 2 * Cd, Cd, generator=g) / (3 * Cd) ** 0.5 * 1024.0
-    wh = wk.half(); wl = (wk - wh.float()).half()
-    bias2 = (torch.randn(2 * Cd, generator=g) * 0.1).to(dev)
-    gh = torch.empty(1, R, Cd, dtype=torch.float16, device=dev); gl = torch.empty_like(gh)
-    d2 = _lib.UmmaDesc(B=1, M=R, Lin=R, N=2 * Cd, Cin=Cd, taps=3, split=1, epi=2, a_ld=Cd, res_ld=Cd, out_ld=Cd, x_ld=0,
-                       a_bstride=R * Cd, res_bstride=0, out_bstride=R * Cd, x_bstride=0, addvec_bstride=0,
-                       alpha=1.0 / 1024.0, res_inv_slope=1.0, out_slope=1.0, out_scale=1.0, skip_accumulate=0)
-    d2.shift[0], d2.shift[1], d2.shift[2] = -1, 0, 1
-    t2 = _probe(lib, d2, [yh.to(dev), yl.to(dev), wh.to(dev), wl.to(dev), bias2, None, None, gh, gl, None, None, None])
-    out["denoiser_gate_k3"] = {"seconds": t2, "flops": 2.0 * R * 3 * Cd * 2 * Cd, "mma_flops": 3 * 2.0 * R * 3 * Cd * 2 * Cd}
-    return out
+    torch.cuda.synchronize(dev)
+    _lib.check(lib.cmtts_prof_begin(_lib.stream_ptr(dev)), "prof_begin")
+    step_fn()
+    cap = 1 << 18
+    buf = ctypes.create_string_buffer(cap)
+    n = lib.cmtts_prof_end(buf, cap)
+    if n < 0:
+        _lib.check(int(n), "prof_end")
+    rows = []
+    for line in buf.value.decode().splitlines():
+        label, cnt, us, fl, by = line.split("\t")
+        rows.append({"kernel": label, "launches": int(cnt), "us": float(us), "flops": float(fl), "bytes": float(by)})
+    tot = sum(r["us"] for r in rows) or 1.0
+    for r in rows:
+        r["share"] = r["us"] / tot
+    rows.sort(key=lambda r: -r["us"])
+    return rows, tot
 
 
-def profile_traffic():
-    """DRAM bytes per launch of the probed kernels from the committed `ncu --set full` capture (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "roofline_traffic_r1.json")
+def traffic_table():
+    """DRAM bytes per launch from the committed `ncu --set full` capture of THIS round's build (profiles/), keyed by the
+    profiler label; {} if none has been committed for the current sources."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic_r2.json")
     if os.path.isfile(p):
         with open(p) as f:
             return json.load(f)
@@ -206,44 +211,106 @@ def measured_peaks():
     if os.path.isfile(p):
         with open(p) as f:
             d = json.load(f)
-        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
-    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "tflops_burst": d["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tflops_sustained": 1400.0, "tflops_burst": 1650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def roofline_blocks(rows, total_us, peaks, step_ms, total_flops, stage_ms, stage_flops):
+    """`roofline` = the kernel with the LARGEST share of the profiled step, rated against the SUSTAINED measured peak
+    (it is timed inside a long step); achieved = its algorithmic FLOPs (or bytes) / its in-step time."""
+    ridge = peaks["tflops_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)     # FLOP per byte
+    tr = traffic_table()
+
+    def block(r):
+        sec = r["us"] * 1e-6
+        tensor = r["flops"] > 0 and (r["bytes"] <= 0 or r["flops"] / r["bytes"] >= ridge or "hi/lo" in r["kernel"]
+                                     or ",1,e" in r["kernel"])
+        if tensor:
+            ach = r["flops"] / sec / 1e12
+            b = {"kernel": r["kernel"], "bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"],
+                 "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"]}
+            if "hi/lo" in r["kernel"] or ",1,e" in r["kernel"]:
+                b["mma_frac"] = 3.0 * b["frac"]
+                b["note"] = "fp16 hi/lo operand pairs: 3 tcgen05.mma per algorithmic MAC (mma_frac = executed MMA rate / peak)"
+        else:
+            ach = r["bytes"] / sec / 1e9 if r["bytes"] > 0 else 0.0
+            b = {"kernel": r["kernel"], "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                 "frac": ach / peaks["hbm_gbs"]}
+        t = tr.get(r["kernel"], {})
+        b.update({"traffic": t.get("dram_bytes_per_launch"), "launches_per_step": r["launches"],
+                  "us_per_launch": r["us"] / r["launches"], "share_of_step": r["share"],
+                  "algorithmic_flops_per_launch": r["flops"] / r["launches"],
+                  "algorithmic_bytes_per_launch": r["bytes"] / r["launches"]})
+        return b
+
+    top = block(rows[0])
+    top["peak_source"] = peaks["source"] + ", sustained (kernel timed inside the step)"
+    top["step_frac"] = total_flops / (step_ms * 1e-3) / 1e12 / peaks["tflops_sustained"]
+    top["stage_fracs"] = {k: (stage_flops[k] / (v * 1e-3) / 1e12 / peaks["tflops_sustained"]) for k, v in stage_ms.items()
+                          if v > 0 and k in stage_flops}
+    top["how"] = ("per-kernel time = distance between CUDA events recorded after every launch of one profiled step "
+                  f"(sum {total_us / 1e3:.2f} ms vs {step_ms:.2f} ms unprofiled); traffic = dram bytes of the committed ncu "
+                  "--set full capture (profiles/roofline_traffic_r2.json) or null")
+    others = [block(r) for r in rows[1:8]]
+    return top, others
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle port of the reference's CPU path, literal schedule
+# CPU baseline / reference arm: the reference's own CPU path (oracle/ref_bench.py)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(args, spec, sd, hifigan_sd, n_utt: int, steps: int, warmup: int):
-    """Times the reference's own schedule on the host cores: (T+1) encoder/variance-adaptor
-    passes with the Python-loop length regulator, T denoiser passes, HiFi-GAN, int16 (p_rtf_cm.py:
-    174-226), through oracle/cmtts_oracle.py (`kind: port`; the Python reference cannot travel to
-    the GPU box).  Bounded sample: the first `n_utt` utterances of the bench batch."""
+def real_hifigan_path():
+    for p in (os.path.join(ROOT, "oracle", "_ref", "hifigan", "generator_universal.pth.tar"),
+              "/root/reference/hifigan/generator_universal.pth.tar"):
+        if os.path.isfile(p):
+            return p
+    return None
+
+
+def load_hifigan(spec, synthetic_only: bool):
+    """BASELINE.json names the universal HiFi-GAN checkpoint the reference ships; it is staged (git-ignored) by
+    __graft_entry__.build().  Falls back to synthetic weights in the same checkpoint layout."""
     from cmtts_b200 import synthetic
-    from oracle import cmtts_oracle as O
+    p = None if synthetic_only else real_hifigan_path()
+    if p is not None:
+        return torch.load(p, map_location="cpu", weights_only=True)["generator"], "generator_universal.pth.tar (reference's shipped weights)"
+    return synthetic.make_hifigan_checkpoint(spec.hifigan, seed=7)["generator"], "synthetic (reference checkpoint layout)"
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    batch = synthetic.make_batch(spec, args.batch, args.src_lo, args.src_hi, seed=1234)
-    sub = {"speakers": batch["speakers"][:n_utt], "texts": batch["texts"][:n_utt].contiguous(),
-           "src_lens": batch["src_lens"][:n_utt],
-           "spker_embeds": None if batch["spker_embeds"] is None else batch["spker_embeds"][:n_utt]}
-    W = O.Weights(sd)
-    Wf = O.Weights(synthetic.fold_weight_norm(hifigan_sd))
-    g = torch.Generator().manual_seed(1)
-    times, frames = [], 0
-    with torch.no_grad():
-        for i in range(warmup + steps):
-            t0 = time.perf_counter()
-            mel, wav, i16, pre = O.synthesize(W, Wf, spec, sub, args.T, lambda s: torch.randn(*s, generator=g), literal=True)
-            dt = time.perf_counter() - t0
-            frames = int(pre["mel_lens"].sum())
-            if i >= warmup:
-                times.append(dt)
-    t = sum(times) / len(times)
-    return {"value": frames / t, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"first {n_utt} of {args.batch} utterances ({frames} valid frames), T={args.T}, reference schedule "
-                      f"((T+1) encoder passes, Python-loop length regulator), {len(times)} timed run(s), {t:.2f} s each",
-            "seconds_per_run": t}
+
+def cpu_reference_run(args, spec, sd, hifigan_sd, batch, n_utt: int, steps: int, warmup: int):
+    """Times the reference's own CPU path on the host cores (oracle/ref_bench.py: the unmodified reference when its
+    tree is available — /root/reference or the staged oracle/_ref — else the oracle port) on a bounded sample: the
+    first `n_utt` utterances of the bench batch, same T."""
+    import contextlib
+    from oracle.ref_bench import ReferenceRunner
+    with contextlib.redirect_stdout(sys.stderr):          # the reference prints ("Removing weight norm..."); stdout is the JSON line's
+        runner = ReferenceRunner(args.dataset, spec, sd, hifigan_sd)
+        if args.config == "C5":
+            from cmtts_b200 import synthetic
+            mel = synthetic.make_mels(n_utt, spec.n_mels, C5_FRAMES, seed=99)
+            runs = [runner.vocoder_step(mel) for _ in range(warmup + steps)][warmup:]
+            sample = f"{n_utt} of the batch's (80 x {C5_FRAMES}) mels"
+        else:
+            sub = {k: (None if v is None else v[:n_utt].contiguous()) for k, v in batch.items()}
+            runs = [runner.step(sub, args.T) for _ in range(warmup + steps)][warmup:]
+            sample = (f"first {n_utt} utterances of the batch, T={args.T}, the reference's schedule ((T+1) encoder passes, "
+                      f"Python-loop length regulator)")
+    t = sum(r["seconds"] for r in runs) / len(runs)
+    frames = runs[0]["valid_frames"]
+    out = {"value": frames / t, "unit": UNIT, "cores": runner.cores, "kind": runner.kind,
+           "sample": f"{sample}; {frames} valid frames, {len(runs)} timed run(s), {t:.2f} s each", "seconds_per_run": t}
+    if "first_utt_seconds_audio" in runs[0]:
+        t_rtf = sum(r["seconds_after_prepass"] for r in runs) / len(runs)
+        out["rtf_ref_p_rtf_cm"] = t_rtf / runs[0]["first_utt_seconds_audio"]
+    return out
+
+
+def workload_text(args, hifigan_src, B_per_gpu_text):
+    c = CONFIGS[args.config]
+    if args.config == "C5":
+        return f"C5: {c['what']}; batch {B_per_gpu_text}; HiFi-GAN V1 weights: {hifigan_src}"
+    return (f"{args.config}: {c['what']}; {args.dataset} {B_per_gpu_text} T={args.T} phonemes {args.src_lo}..{args.src_hi}, "
+            f"80 mels, HiFi-GAN V1 weights: {hifigan_src}; acoustic weights synthetic in the reference checkpoint layout")
 
 
 def main():
@@ -257,22 +324,27 @@ def main():
 
     spec = ModelSpec.preset(args.dataset)
     sd = synthetic.make_acoustic_state_dict(spec, seed=0)
-    hifigan_sd = synthetic.make_hifigan_checkpoint(spec.hifigan, seed=7)["generator"]
-    workload = (f"{args.dataset} B={args.batch}/GPU T={args.T} phonemes {args.src_lo}..{args.src_hi} (L~800), "
-                f"80 mels, HiFi-GAN V1; synthetic weights in the reference checkpoint layout")
+    hifigan_sd, hifigan_src = load_hifigan(spec, args.synthetic_vocoder)
+    GB = global_batch_size(args, world if args.impl == "ours" else max(args.gpus, 1))
+    gb = None if args.config == "C5" else synthetic.make_batch(spec, GB, args.src_lo, args.src_hi, seed=1234)
+    btxt = (f"{GB // max(world, 1)} utterances/GPU (weak)" if args.scaling == "weak" else f"global batch {GB} (strong)")
 
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 3))
-        cb = cpu_reference_run(args, spec, sd, hifigan_sd, args.cpu_sample, steps, min(args.warmup, 1))
+        steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
+        n_utt = min(args.cpu_sample or 8, GB)
+        cb = cpu_reference_run(args, spec, sd, None if real_hifigan_path() and not args.synthetic_vocoder else hifigan_sd,
+                               gb, n_utt, steps, warmup)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-                "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["seconds_per_run"] * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload + f" [CPU sample: {cb['sample']}]"},
+                "steps": steps, "warmup": warmup, "ms_per_step": cb["seconds_per_run"] * 1e3,
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_text(args, hifigan_src, btxt) + f" [CPU sample: {cb['sample']}]"},
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
+        if "rtf_ref_p_rtf_cm" in cb:
+            line["rtf"] = {"rtf_ref_p_rtf_cm": cb["rtf_ref_p_rtf_cm"], "definition": "p_rtf_cm.py:190-230 on the CPU sample"}
         print(json.dumps(line))
         return
 
@@ -286,28 +358,16 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from cmtts_b200 import _lib
-    from cmtts_b200.dist import ShardedSynthesizer
+    from cmtts_b200.dist import ShardedSynthesizer, balanced_partition, shard_counts, shard_rows
     from cmtts_b200.synthesize import Pipeline
 
     lib = _lib.load()
     pipe = Pipeline(spec, sd, hifigan_sd, dev, precision=args.precision, tc_frontend=not args.ffma_frontend)
-    synth = ShardedSynthesizer(pipe, dist if world > 1 else None)
-    # per-rank shard of the global synthetic batch (weak scaling: args.batch utterances per GPU)
-    gb = synthetic.make_batch(spec, args.batch * world, args.src_lo, args.src_hi, seed=1234)
-    sl = slice(rank * args.batch, (rank + 1) * args.batch)
-    h_texts = gb["texts"][sl].contiguous().pin_memory()
-    h_lens = gb["src_lens"][sl].contiguous().pin_memory()
-    h_spk = None if gb["spker_embeds"] is None else gb["spker_embeds"][sl].contiguous().pin_memory()
-    d_texts, d_lens = h_texts.to(dev), h_lens.to(dev)
-    d_spk = None if h_spk is None else h_spk.to(dev)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(dev)
-
-    def step_resident():
-        return synth.run(d_texts, d_lens, d_spk, args.T, gather=(world > 1))
 
     pinned = {}
 
@@ -315,31 +375,78 @@ def main():
         """device -> pinned host staging buffer (grow-only), as cmtts_b200.output does for the WAV writer"""
         buf = pinned.get(name)
         if buf is None or buf.numel() < t.numel() or buf.dtype != t.dtype:
-            buf = pinned[name] = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
+            buf = pinned[name] = torch.empty(max(t.numel(), 1), dtype=t.dtype, pin_memory=True)
         view = buf[: t.numel()].view(t.shape)
         view.copy_(t, non_blocking=True)
         return view
 
-    def step_e2e():
-        t = h_texts.to(dev, non_blocking=True)
-        l = h_lens.to(dev, non_blocking=True)
-        s = None if h_spk is None else h_spk.to(dev, non_blocking=True)
-        out = synth.run(t, l, s, args.T, gather=(world > 1))
-        w = to_pinned("wav", out["wav_i16"])
-        ml = to_pinned("mel_lens", out["mel_lens"])
-        torch.cuda.current_stream(dev).synchronize()          # the step's result is on the host
-        return out, w, ml
+    # ---- the per-rank shard --------------------------------------------------------------------
+    if args.config == "C5":
+        rows = list(range(GB))[shard_rows(GB, world, rank)]
+        mels = synthetic.make_mels(GB, spec.n_mels, C5_FRAMES, seed=99)[rows].transpose(1, 2).contiguous()   # (b, L, 80)
+        h_mel = mels.pin_memory()
+        d_mel = h_mel.to(dev)
+        synth = ShardedSynthesizer(pipe, dist if world > 1 else None)
+        padding = "n/a"
+
+        def step_resident():
+            _, w16 = pipe.vocoder.run(d_mel, want_float=False, want_int16=True, max_wav_value=spec.max_wav_value)
+            return {"wav_i16": w16, "mel_lens": None}
+
+        def step_e2e():
+            m = h_mel.to(dev, non_blocking=True)
+            _, w16 = pipe.vocoder.run(m, want_float=False, want_int16=True, max_wav_value=spec.max_wav_value)
+            w = to_pinned("wav", w16)
+            torch.cuda.current_stream(dev).synchronize()
+            return w, None
+
+        h2d = h_mel.numel() * 4
+    else:
+        if world > 1 and args.shard == "balanced":
+            parts = balanced_partition(gb["src_lens"].tolist(), world)
+            rows, counts, padding = parts[rank], [len(p) for p in parts], "local"
+        else:
+            rows, counts, padding = list(range(GB))[shard_rows(GB, world, rank)], shard_counts(GB, world), "global"
+        idx = torch.as_tensor(rows, dtype=torch.int64)
+        # every shard keeps the GLOBAL token padding in "global" mode; per-shard token padding in "local" mode
+        h_lens = gb["src_lens"][idx].contiguous()
+        tmax = int(gb["src_lens"].max()) if padding == "global" or not len(rows) else int(h_lens.max())
+        h_texts = gb["texts"][idx][:, :tmax].contiguous().pin_memory()
+        h_lens = h_lens.pin_memory()
+        h_spk = None if gb["spker_embeds"] is None else gb["spker_embeds"][idx].contiguous().pin_memory()
+        d_texts, d_lens = h_texts.to(dev), h_lens.to(dev)
+        d_spk = None if h_spk is None else h_spk.to(dev)
+        synth = ShardedSynthesizer(pipe, dist if world > 1 else None, padding=padding, counts=counts, dst=0)
+
+        def step_resident():
+            return synth.run(d_texts, d_lens, d_spk, args.T, gather=(world > 1))
+
+        def step_e2e():
+            t = h_texts.to(dev, non_blocking=True)
+            l = h_lens.to(dev, non_blocking=True)
+            s = None if h_spk is None else h_spk.to(dev, non_blocking=True)
+            out = synth.run(t, l, s, args.T, gather=(world > 1))
+            w = to_pinned("wav", out["wav_i16"])
+            ml = to_pinned("mel_lens", out["mel_lens"])
+            torch.cuda.current_stream(dev).synchronize()          # the step's result is on the host
+            return w, ml
+
+        h2d = h_texts.numel() * 8 + h_lens.numel() * 8 + (0 if h_spk is None else h_spk.numel() * 4)
 
     # ---- warm-up (the clock sampler is already running: nvidia-smi needs a moment before its first report) ----
     clocks = ClockSampler(local_rank)
     t_load0 = time.time()
     for _ in range(max(args.warmup, 3)):
         out = step_resident()
+    synth.flush()
     barrier()
-    mel_lens = out["mel_lens"].cpu()
-    B, L = out["mel"].shape[0], out["mel"].shape[1]
-    valid_local = int(mel_lens.sum())
-    Tsrc = h_texts.shape[1]
+    if args.config == "C5":
+        B, L, Tsrc = d_mel.shape[0], C5_FRAMES, 0
+        valid_local = B * L
+    else:
+        B, L = out["mel"].shape[0], out["mel"].shape[1]
+        valid_local = int(out["mel_lens"].sum().item()) if B else 0
+        Tsrc = h_texts.shape[1]
 
     # ---- timed: device-resident inputs ----
     launches0 = lib.cmtts_launch_count()
@@ -349,6 +456,7 @@ def main():
     ev0.record()
     for _ in range(args.steps):
         out = step_resident()
+    synth.flush()                                   # the last step's collation is part of the job
     ev1.record()
     barrier()
     wall1 = time.time()
@@ -359,33 +467,50 @@ def main():
     # ---- timed: end to end with host buffers ----
     for _ in range(2):
         step_e2e()
+    synth.flush()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        _, w_host, ml_host = step_e2e()
+        w_host, ml_host = step_e2e()
+    synth.flush()
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    d2h = w_host.numel() * 2 + (0 if ml_host is None else ml_host.numel() * 8)
 
-    # ---- instrumented pass: per-stage CUDA events (same workload, same stream) ----
-    stage_ms = synth.stage_times(d_texts, d_lens, d_spk, args.T, reps=max(2, min(args.steps, 5)))
-
-    # ---- RTF as p_rtf_cm.py defines it (rank 0 only, informational) ----
-    from cmtts_b200.synthesize import rtf_like_reference
-    rtf_ref, rtf_total, rtf_elapsed = rtf_like_reference(pipe, d_texts, d_lens, d_spk, args.T)
+    # ---- instrumented passes: per-stage CUDA events, per-kernel launch profile (same workload, same stream) ----
+    hf = hifigan_flops_per_frame(spec.hifigan)
+    if args.config == "C5":
+        stage_ms = {"vocoder": ms / args.steps}
+        stage_flops = {"vocoder": hf * B * L}
+        total_flops = stage_flops["vocoder"]
+        rtf = None
+        prof_step = step_resident
+    else:
+        stage_ms = synth.stage_times(d_texts, d_lens, d_spk, args.T, reps=max(2, min(args.steps, 5))) if B else {}
+        af = acoustic_flops(spec, B, Tsrc, L, args.T)
+        stage_flops = {"dpen": af["encoder"] + af["variance"], "sampler": af["denoiser"], "vocoder": hf * B * L}
+        total_flops = sum(stage_flops.values())
+        # RTF as p_rtf_cm.py defines it (informational; every rank computes its own, rank 0 reports)
+        from cmtts_b200.synthesize import rtf_like_reference
+        rtf = rtf_like_reference(pipe, d_texts, d_lens, d_spk, args.T) if B else None
+        prof_step = lambda: pipe(d_texts, d_lens, d_spk, T=args.T)       # noqa: E731
+    prof = None
+    if not args.no_profile and B:
+        prof = kernel_profile(lib, prof_step, dev)
 
     # max over ranks / totals
-    stats = torch.tensor([ms, ms_e2e, float(valid_local), float(B * L)], dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms, ms_e2e, float(valid_local), float(B * L), float(launches)], dtype=torch.float64, device=dev)
     if dist is not None:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms, ms_e2e = float(mx[0]), float(mx[1])
-        valid_total, padded_total = float(sm[2]), float(sm[3])
+        valid_total, padded_total, launches_total = float(sm[2]), float(sm[3]), float(sm[4])
     else:
-        valid_total, padded_total = float(valid_local), float(B * L)
+        valid_total, padded_total, launches_total = float(valid_local), float(B * L), float(launches)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -394,70 +519,51 @@ def main():
     sec = ms / 1e3 / args.steps
     sec_e2e = ms_e2e / 1e3 / args.steps
     value = valid_total / sec
-    hf = hifigan_flops_per_frame(spec.hifigan)
-    af = acoustic_flops(spec, B, Tsrc, L, args.T)
-    voc_flops = hf * B * L
     peaks = measured_peaks()
-    voc_s = stage_ms["vocoder"] / 1e3
-    achieved = voc_flops / voc_s / 1e12
-    total_flops = (voc_flops + af["encoder"] + af["variance"] + af["denoiser"])
-    h2d = h_texts.numel() * 8 + h_lens.numel() * 8 + (0 if h_spk is None else h_spk.numel() * 4)
-    d2h = w_host.numel() * 2 + ml_host.numel() * 8
-
-    # ---- roofline: the dominant conv shape timed live, kernel by kernel ----
-    if args.precision == "tc":
-        pr = kernel_probes(lib, dev, B, L)
-        tr = profile_traffic()
-        a = pr["vocoder_c128_k11"]; dn = pr["denoiser_gate_k3"]
-        ach = a["flops"] / a["seconds"] / 1e12
-        roofline = {"kernel": "umma_halo_kernel<128,64,2,11> (HiFi-GAN level-1 ResBlock conv, C=128 k=11 d=5 + residual; "
-                              "6 launches per step, the largest FLOP consumer)",
-                    "bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
-                    "traffic": tr.get("umma_halo_kernel<128,64,2,11>", {}).get("dram_bytes_per_launch"),
-                    "peak_source": peaks["source"], "algorithmic_flops_per_launch": a["flops"],
-                    "algorithmic_bytes_per_launch": a["algorithmic_bytes"], "us_per_launch": a["seconds"] * 1e6,
-                    "note": "timed live with CUDA events (10 back-to-back launches through the C ABI at bench size); "
-                            "traffic = dram__bytes_read+write of the committed ncu --set full capture (profiles/)"}
-        roofline_other = [
-            {"kernel": "umma_gate_kernel<3,4> (denoiser k=3 gate conv, K=768 N=512, fp16 hi/lo: 3 MMAs per MAC; "
-                       "80 launches per step)", "bound": "tensor", "unit": "TFLOP/s", "peak": peaks["tflops"],
-             "achieved": dn["flops"] / dn["seconds"] / 1e12, "frac": dn["flops"] / dn["seconds"] / 1e12 / peaks["tflops"],
-             "achieved_mma": dn["mma_flops"] / dn["seconds"] / 1e12, "frac_mma": dn["mma_flops"] / dn["seconds"] / 1e12 / peaks["tflops"],
-             "us_per_launch": dn["seconds"] * 1e6,
-             "traffic": tr.get("umma_gate_kernel<3,4>", {}).get("dram_bytes_per_launch")},
-            {"kernel": "HiFi-GAN stage (all vocoder launches of one step)", "bound": "tensor", "unit": "TFLOP/s",
-             "peak": peaks["tflops"], "achieved": achieved, "frac": achieved / peaks["tflops"], "stage_ms": stage_ms["vocoder"],
-             "algorithmic_flops": voc_flops,
-             "note": "614.1 MFLOP/mel-frame x padded frames / CUDA-event time of the vocoder stage (86% of step FLOPs)"}]
-    else:
-        roofline = {"kernel": synth.dominant_kernel(), "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"],
-                    "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
-                    "note": "fp32 FFMA yardstick path: vocoder stage aggregate"}
-        roofline_other = []
-
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": synth.dtype_label(), "data": "synthetic",
-        "config": {"workload": workload, "global_batch": B * world, "padded_frames_per_gpu": B * L, "L_max": L,
-                   "Tsrc_max": Tsrc, "valid_frames_total": valid_total, "parallelism": f"utterance-sharded x{world}",
-                   "l2_policy": "working set (>3 GB of activations per step) is far larger than the 126 MB L2; no flush needed",
-                   "padding_mode": "global L_max (all-reduce MAX)" if world > 1 else "single batch"},
+        "config": {"workload": workload_text(args, hifigan_src, btxt), "name": args.config, "T": args.T,
+                   "global_batch": GB, "rank0_utterances": B, "rank0_padded_frames": B * L, "rank0_L_max": L,
+                   "rank0_Tsrc_max": Tsrc, "valid_frames_total": valid_total, "padded_frames_total": padded_total,
+                   "padded_over_valid": padded_total / max(valid_total, 1.0),
+                   "parallelism": f"utterance-sharded x{world}" + (f", {args.shard} shards" if world > 1 else ""),
+                   "padding_mode": {"global": "global L_max (one 8-byte MAX all-reduce; bit-identical to the single-GPU batch)",
+                                    "local": "per-shard L_max (length-bucketed shards; each shard = the reference run on its rows)",
+                                    "n/a": "fixed-length mels"}[padding] if world > 1 else "single batch",
+                   "collation": "async gather of int16 wavs + mel_lens to rank 0, inside the timed region" if world > 1 else "none",
+                   "l2_policy": "working set (GBs of activations per step) is far larger than the 126 MB L2; no flush needed"
+                   if B * L >= 8000 else "small batch: activations of consecutive launches stay L2-resident by design "
+                                         "(one step's working set is the workload; inputs are re-uploaded / re-generated every step)"},
         "clocks": clk,
         "e2e": {"value": valid_total / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": sec_e2e * 1e3},
-        "gpu_launches": int(launches),
-        "roofline": roofline,
-        "roofline_other": roofline_other,
+        "gpu_launches": int(launches_total),
         "stages_ms": stage_ms,
         "algorithmic_tflop_per_step": total_flops / 1e12,
-        "whole_step_tflops": total_flops / sec / 1e12,
+        "whole_step_tflops": total_flops * (1 if world == 1 else padded_total / max(B * L, 1)) / sec / 1e12,
         "padded_frames_per_sec": padded_total / sec,
-        "rtf": {"rtf_ref_p_rtf_cm": rtf_ref, "rtf_total": rtf_total, "elapsed_s": rtf_elapsed,
-                "definition": "p_rtf_cm.py:190-230 (timer after the pre-pass; / duration of utterance 0)"},
     }
+    if rtf is not None:
+        line["rtf"] = {"rtf_ref_p_rtf_cm": rtf[0], "rtf_total": rtf[1], "elapsed_s": rtf[2],
+                       "definition": "p_rtf_cm.py:190-230 (timer after the pre-pass; / duration of utterance 0)"}
+    if prof is not None:
+        rows_, tot_us = prof
+        top, others = roofline_blocks(rows_, tot_us, peaks, sec * 1e3, total_flops, stage_ms, stage_flops)
+        line["roofline"] = top
+        line["roofline_other"] = others
+        line["kernels"] = [{"kernel": r["kernel"], "launches": r["launches"], "ms": r["us"] / 1e3, "share": r["share"]}
+                           for r in rows_[:12]]
+    else:
+        line["roofline"] = {"kernel": synth.dominant_kernel(), "bound": "tensor", "achieved": total_flops / sec / 1e12,
+                            "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                            "frac": total_flops / sec / 1e12 / peaks["tflops_sustained"], "traffic": None,
+                            "note": "whole-step aggregate (per-kernel profile skipped)"}
     if world == 1 and not args.no_cpu_baseline:
-        cb = cpu_reference_run(args, spec, sd, hifigan_sd, args.cpu_sample, 1, 0)
+        n_utt = min(args.cpu_sample or 4, GB)
+        cb = cpu_reference_run(args, spec, sd, None if real_hifigan_path() and not args.synthetic_vocoder else hifigan_sd,
+                               gb, n_utt, 1, 0)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
     if dist is not None:

@@ -67,6 +67,8 @@ PROTOTYPES = {
     "cmtts_last_error": (C.c_char_p, []),
     "cmtts_launch_count": (C.c_uint64, []),
     "cmtts_debug_set": (None, [C.c_int32, C.c_int32]),
+    "cmtts_prof_begin": (C.c_int, [vp]),
+    "cmtts_prof_end": (C.c_int64, [C.c_char_p, szt]),
     "cmtts_encoder_workspace_bytes": (szt, [PD, i64, i64]),
     "cmtts_encoder_forward": (C.c_int, [PD, PV, vp, vp, i64, i64, vp, vp, szt, vp]),
     "cmtts_variance_token_workspace_bytes": (szt, [PD, i64, i64]),

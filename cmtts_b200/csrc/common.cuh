@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #define CMTTS_OK 0
 #define CMTTS_ERR_ARG (-1)
@@ -14,9 +15,17 @@ extern unsigned long long g_cmtts_launches;   // kernels launched by this librar
 extern int g_cmtts_umma_dbg;                  // CMTTS_UMMA_DBG experiment bits (-1: not read yet)
 extern int g_cmtts_pdl;                       // CMTTS_PDL: programmatic dependent launch on (1, default) / off (0)
 
+// launch profiler (cmtts_prof_begin / cmtts_prof_end of the C ABI): when on, every launch site records a CUDA event
+// on the profiled stream; a launch's duration is the distance to the previous event.  cmtts_prof_note() labels the NEXT
+// launch and attaches its algorithmic FLOPs / bytes (sites without a note are labelled function:line).
+extern int g_cmtts_prof_on;
+void cmtts_prof_note(const char* label, double flops, double bytes);
+void cmtts_prof_mark(const char* func, int line);
+
 #define CMTTS_CHECK_LAUNCH()                                  \
     do {                                                      \
         ++g_cmtts_launches;                                   \
+        if (g_cmtts_prof_on) cmtts_prof_mark(__func__, __LINE__); \
         cudaError_t e__ = cudaPeekAtLastError();              \
         if (e__ != cudaSuccess) { cmtts_set_error(cudaGetErrorString(e__), __FILE__, __LINE__); return CMTTS_ERR_CUDA; } \
     } while (0)

@@ -32,6 +32,83 @@ int g_cmtts_umma_dbg = -1;
 int g_cmtts_pdl = -1;
 extern "C" void cmtts_debug_set(int32_t umma_dbg, int32_t pdl) { g_cmtts_umma_dbg = umma_dbg; g_cmtts_pdl = pdl; }
 
+// --------------------------------------------------------------------------------------------
+// launch profiler: per-label launch counts, device time (CUDA events on the launching stream), algorithmic work
+// --------------------------------------------------------------------------------------------
+int g_cmtts_prof_on = 0;
+namespace {
+struct ProfMark { cudaEvent_t ev; char label[96]; double flops, bytes; };
+constexpr int PROF_MAX = 8192;
+ProfMark* g_prof = nullptr;
+int g_prof_n = 0;
+cudaStream_t g_prof_stream = nullptr;
+cudaEvent_t g_prof_ev0 = nullptr;
+char g_prof_pending[96] = "";
+double g_prof_pending_flops = 0, g_prof_pending_bytes = 0;
+}  // namespace
+
+void cmtts_prof_note(const char* label, double flops, double bytes) {
+    if (!g_cmtts_prof_on) return;
+    snprintf(g_prof_pending, sizeof(g_prof_pending), "%s", label);
+    g_prof_pending_flops = flops; g_prof_pending_bytes = bytes;
+}
+
+void cmtts_prof_mark(const char* func, int line) {
+    if (!g_cmtts_prof_on || g_prof_n >= PROF_MAX) return;
+    ProfMark& m = g_prof[g_prof_n];
+    if (!m.ev) cudaEventCreate(&m.ev);
+    cudaEventRecord(m.ev, g_prof_stream);
+    if (g_prof_pending[0]) snprintf(m.label, sizeof(m.label), "%s", g_prof_pending);
+    else snprintf(m.label, sizeof(m.label), "%s:%d", func, line);
+    m.flops = g_prof_pending_flops; m.bytes = g_prof_pending_bytes;
+    g_prof_pending[0] = 0; g_prof_pending_flops = g_prof_pending_bytes = 0;
+    ++g_prof_n;
+}
+
+extern "C" int cmtts_prof_begin(void* stream) {
+    if (!g_prof) g_prof = (ProfMark*)calloc(PROF_MAX, sizeof(ProfMark));
+    if (!g_prof) { cmtts_set_error("prof: out of memory", __FILE__, __LINE__); return CMTTS_ERR_ARG; }
+    g_prof_stream = (cudaStream_t)stream;
+    if (!g_prof_ev0) cudaEventCreate(&g_prof_ev0);
+    g_prof_n = 0; g_prof_pending[0] = 0;
+    cudaEventRecord(g_prof_ev0, g_prof_stream);
+    g_cmtts_prof_on = 1;
+    return CMTTS_OK;
+}
+
+// Stops profiling, synchronises the stream and writes one line per label to `buf`:
+//   label<TAB>launches<TAB>total_us<TAB>flops<TAB>bytes\n   (totals over all launches with that label)
+// Returns the number of bytes needed (excluding the NUL), or a negative error code.
+extern "C" int64_t cmtts_prof_end(char* buf, size_t cap) {
+    g_cmtts_prof_on = 0;
+    if (!g_prof) return 0;
+    if (cudaStreamSynchronize(g_prof_stream) != cudaSuccess) { cmtts_set_error("prof: sync failed", __FILE__, __LINE__); return CMTTS_ERR_CUDA; }
+    struct Agg { char label[96]; long long n; double us, flops, bytes; };
+    Agg* agg = (Agg*)calloc(g_prof_n > 0 ? g_prof_n : 1, sizeof(Agg));
+    int na = 0;
+    cudaEvent_t prev = g_prof_ev0;
+    for (int i = 0; i < g_prof_n; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, prev, g_prof[i].ev);
+        prev = g_prof[i].ev;
+        int j = 0;
+        for (; j < na; ++j) if (strcmp(agg[j].label, g_prof[i].label) == 0) break;
+        if (j == na) { snprintf(agg[na].label, sizeof(agg[na].label), "%s", g_prof[i].label); ++na; }
+        agg[j].n += 1; agg[j].us += ms * 1e3; agg[j].flops += g_prof[i].flops; agg[j].bytes += g_prof[i].bytes;
+    }
+    size_t need = 0;
+    for (int j = 0; j < na; ++j) {
+        char line[256];
+        const int len = snprintf(line, sizeof(line), "%s\t%lld\t%.3f\t%.6e\t%.6e\n", agg[j].label, agg[j].n, agg[j].us,
+                                 agg[j].flops, agg[j].bytes);
+        if (buf && need + len < cap) memcpy(buf + need, line, len);
+        need += len;
+    }
+    if (buf && cap) buf[need < cap ? need : cap - 1] = 0;
+    free(agg);
+    return (int64_t)need;
+}
+
 namespace {
 
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
@@ -632,12 +709,14 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
     cudaMemset2DAsync(yc_lo + (size_t)L * YC, (size_t)Lp * YC * 2, 0, (size_t)C * 2, B, s);
     CMTTS_TRY(launch_pack_rows_f16((const __half*)cond_hi, yc_hi, B, L, Lp, H, YC, C, s));
     CMTTS_TRY(launch_pack_rows_f16((const __half*)cond_lo, yc_lo, B, L, Lp, H, YC, C, s));
-    // input projection: relu(W (c_in x_t) + b), x_t zero-padded to 128 channels as an fp16 hi/lo pair
-    CMTTS_TRY(launch_f32_to_f16_rows(x_t, xt_hi, xt_lo, B, L, Lp, M, 128, 128, s));
+    // input projection: relu(W (c_in x_t) + b).  c_in * x_t is formed in fp32 first, like the reference
+    // (karras_diffusion.py:405), and THEN split into an fp16 hi/lo pair zero-padded to 128 channels: the operand is
+    // O(1) whatever sigma_max the config holds (raw x_t ~ 6 sigma_max would overflow fp16 for sigma_max > 1e4)
+    CMTTS_TRY(launch_f32_to_f16_rows(x_t, xt_hi, xt_lo, B, L, Lp, M, 128, 128, c_in, s));
     {
         UmmaConvParams u = tc_same(HL{xt_hi, xt_lo}, 1, R, 128, wx[0], wx[1], F(w, CMTTS_DN_IN_B), C, 1, 1);
         flat(u);
-        u.alpha = c_in * TC_W_SCALE_INV; u.act = ACT_RELU;
+        u.alpha = TC_W_SCALE_INV; u.act = ACT_RELU;
         tc_out32(u, x, R, C);
         CMTTS_TRY(launch_umma_conv(u, s));
     }

@@ -564,6 +564,8 @@ int launch_length_regulate(const float* x, const long long* cumsum, const long l
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(length_regulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((L + 63) / 64, B);
+    if (g_cmtts_prof_on)   // read (N_tok C + N_tok) 4 + write N_frm (C 4 + 8)
+        cmtts_prof_note("length_regulate (scan + gather)", 0.0, ((double)B * T * C + (double)B * T) * 4.0 + (double)B * L * (C * 4.0 + 8.0));
     length_regulate_kernel<<<grid, 256, smem, s>>>(x, cumsum, mel_lens, out, mel2ph, T, L, C);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
@@ -607,6 +609,7 @@ int launch_renoise(const float* x0, const float* noise, float s1, float s2, floa
     if (n == 0) return CMTTS_OK;
     CMTTS_REQUIRE(n % 4 == 0, "renoise: n % 4");
     const long long n4 = n / 4;
+    if (g_cmtts_prof_on) cmtts_prof_note("renoise (x0 + noise s)", 2.0 * n, 12.0 * n);
     renoise_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>((const float4*)x0, (const float4*)noise, s1, s2, (float4*)out, n4);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;

@@ -502,6 +502,19 @@ int launch_cfg(const UmmaConvParams& p, cudaStream_t s) {
     }
     const int tiles = p.B * ((p.M + 127) / 128) * (p.N / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
+    if (g_cmtts_prof_on) {
+        const double rows = (double)p.B * p.M, nop = NOP;
+        const int taps_eff = p.tap_split_n ? p.taps - 1 : p.taps;              // zero tap of a packed transposed conv
+        const double K = (double)taps_eff * p.Cin + (p.a2_hi ? p.n_k2 : 0);
+        const double out_b = (p.out_h ? 2.0 * (p.out_lo ? 2 : 1) : 0.0) + (p.out_f32 ? 4.0 : 0.0);
+        const int n_out = (EPI == UEPI_DN_GATE) ? p.N / 2 : (p.n_valid ? p.n_valid : p.N);
+        char lbl[96];
+        snprintf(lbl, sizeof(lbl), "umma_conv<%d,%d,%d,e%d> t%d %d->%d", BN, BK, SPLIT, EPI, p.taps, p.Cin + (p.a2_hi ? p.n_k2 : 0), p.N);
+        cmtts_prof_note(lbl, 2.0 * rows * p.N * K,
+                        rows * (p.Cin * (p.a_tap_dim ? p.taps : 1) + (p.a2_hi ? p.n_k2 + p.a2_diag : 0)) * 2.0 * nop + rows * n_out * out_b +
+                            (p.res_h ? rows * p.N * 2.0 : 0.0) + (p.sum_h ? rows * p.N * 2.0 : 0.0) + (p.x_f32 ? rows * n_out * 4.0 : 0.0) +
+                            (double)p.taps * p.N * (p.Cin + (p.a2_hi ? p.Cin2 : 0)) * 2.0 * nop);
+    }
     launch_pdl(kern, grid, 384, SMEM, s, a0, a1, b0, b1, a2, a3, p);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
@@ -607,7 +620,7 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ x, __half* __restric
 // Flattened-utterance layout helpers (denoiser): row b*L + t of a (B, L, *) tensor goes to row b*Lp + t (Lp = L + 1:
 // one guard row per utterance) of a matrix with row pitch `out_ld` elements, at column `col_off`.
 __global__ void f32_to_f16_rows_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
-                                       long long rows, int L, int Lp, int C, int Cpad, int out_ld) {
+                                       long long rows, int L, int Lp, int C, int Cpad, int out_ld, float scale) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 8 output channels
     const int per_row = Cpad >> 3;
     if (i >= rows * per_row) return;
@@ -616,7 +629,7 @@ __global__ void f32_to_f16_rows_kernel(const float* __restrict__ x, __half* __re
     const long long ro = (r / L) * Lp + (r % L);
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (c + j < C) ? x[r * C + c + j] : 0.f;
+    for (int j = 0; j < 8; ++j) v[j] = (c + j < C) ? __fmul_rn(x[r * C + c + j], scale) : 0.f;   // c_in * x_t in fp32, as the reference
     uint4 uh, ul;
     __half2* ph = reinterpret_cast<__half2*>(&uh);
     __half2* pl = reinterpret_cast<__half2*>(&ul);
@@ -699,18 +712,19 @@ int launch_f32_to_f16(const float* x, __half* hi, __half* lo, long long rows, in
     if (rows == 0) return CMTTS_OK;
     CMTTS_REQUIRE(Cpad % 8 == 0 && Cpad >= C, "f32_to_f16: Cpad must be a multiple of 8 and >= C");
     const long long n = rows * (Cpad / 8);
+    if (g_cmtts_prof_on) cmtts_prof_note("f32_to_f16 (hi/lo split)", 0.0, (double)rows * (C * 4.0 + Cpad * 2.0 * (lo ? 2 : 1)));
     f32_to_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, hi, lo, rows, C, Cpad, slope);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }
 
 int launch_f32_to_f16_rows(const float* x, __half* hi, __half* lo, int B, int L, int Lp, int C, int Cpad, int out_ld,
-                           cudaStream_t s) {
+                           float scale, cudaStream_t s) {
     const long long rows = (long long)B * L;
     if (rows == 0) return CMTTS_OK;
     CMTTS_REQUIRE(Cpad % 8 == 0 && Cpad >= C && out_ld % 8 == 0 && Lp >= L, "f32_to_f16_rows: shape");
     const long long n = rows * (Cpad / 8);
-    f32_to_f16_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, hi, lo, rows, L, Lp, C, Cpad, out_ld);
+    f32_to_f16_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, hi, lo, rows, L, Lp, C, Cpad, out_ld, scale);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }
@@ -731,6 +745,9 @@ int launch_conv_post_f16(const __half* x, const float* w, const float* bias, flo
     const size_t smem = (size_t)((K * C * 4 + 15) & ~15) + (size_t)(POST_TILE + K - 1) * (C * 2 + 16);
     CMTTS_REQUIRE(C % 8 == 0 && smem <= 48 * 1024, "conv_post_f16: shape");
     dim3 grid((L + POST_TILE - 1) / POST_TILE, B);
+    if (g_cmtts_prof_on)
+        cmtts_prof_note("conv_post_f16 (k7 conv + tanh + int16)", 2.0 * B * L * C * K,
+                        (double)B * L * (C * 2.0 + (wav ? 4.0 : 0.0) + (wav_i16 ? 2.0 : 0.0)));
     conv_post_f16_kernel<<<grid, POST_TILE, smem, s>>>(x, w, bias, pre_div, wav, wav_i16, max_wav, L, C, K);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;

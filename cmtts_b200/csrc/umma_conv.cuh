@@ -91,7 +91,7 @@ int launch_f32_to_f16(const float* x, __half* hi, __half* lo, long long rows, in
 // flattened-utterance layout (one guard row per utterance): (B, L, C) fp32 -> rows b*Lp + t of an fp16 hi/lo matrix;
 // and the same row mapping for an existing fp16 (B, L, W) tensor, placed at a column offset
 int launch_f32_to_f16_rows(const float* x, __half* hi, __half* lo, int B, int L, int Lp, int C, int Cpad, int out_ld,
-                           cudaStream_t s);
+                           float scale, cudaStream_t s);
 int launch_pack_rows_f16(const __half* src, __half* dst, int B, int L, int Lp, int W, int out_ld, int col_off, cudaStream_t s);
 // HiFi-GAN output stage on fp16 activated input
 int launch_conv_post_f16(const __half* x, const float* w, const float* bias, float pre_div, float* wav, short* wav_i16,

@@ -304,6 +304,13 @@ int launch_gate_cfg(const UmmaConvParams& p, cudaStream_t s) {
     }
     const int tiles = p.B * ((p.M + 127) / 128) * (p.N / G_BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
+    if (g_cmtts_prof_on) {
+        const double rows = (double)p.B * p.M;
+        char lbl[96];
+        snprintf(lbl, sizeof(lbl), "umma_gate<%d> t%d %d->%d (hi/lo)", p.taps, p.taps, p.Cin, p.N);
+        cmtts_prof_note(lbl, 2.0 * rows * p.N * p.taps * p.Cin,
+                        rows * p.Cin * 4.0 + rows * (p.N / 2) * 4.0 + (double)p.taps * p.N * p.Cin * 4.0);
+    }
     launch_pdl(kern, grid, 384, smem, s, a0, a1, b0, b1, p, rows_alloc, box_rows);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;

@@ -406,6 +406,15 @@ int launch_halo_cfg(const UmmaConvParams& p, cudaStream_t s) {
     }
     const int tiles = p.B * ((p.M + 127) / 128);
     const int grid = tiles < num_sms() ? tiles : num_sms();
+    if (g_cmtts_prof_on) {
+        const double rows = (double)p.B * p.M;
+        char lbl[96];
+        snprintf(lbl, sizeof(lbl), "umma_halo<%d> k%d d%d%s%s", p.N, p.taps, p.taps > 1 ? p.shift[1] - p.shift[0] : 1,
+                 p.res_h ? " +res" : "", p.sum_h ? " +sum" : "");
+        cmtts_prof_note(lbl, 2.0 * rows * p.N * p.taps * p.Cin,
+                        rows * (p.Cin + p.N) * 2.0 + (p.res_h ? rows * p.N * 2.0 : 0.0) + (p.sum_h ? rows * p.N * 2.0 : 0.0) +
+                            (double)p.taps * p.N * p.Cin * 2.0);
+    }
     launch_pdl(kern, grid, 384, smem, s, a_map, w_map, o_map, p, cfg);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;

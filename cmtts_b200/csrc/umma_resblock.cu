@@ -470,6 +470,13 @@ int launch_rb_cfg(const UmmaResblockParams& p, cudaStream_t s) {
     }
     const int tiles = p.B * cfg.m_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
+    if (g_cmtts_prof_on) {
+        const double rows = (double)p.B * p.L;
+        char lbl[96];
+        snprintf(lbl, sizeof(lbl), "umma_resblock<%d> k%d d%d%s (conv1+conv2)", C, p.taps, p.dil, p.sum_h ? " +sum" : "");
+        cmtts_prof_note(lbl, 2.0 * 2.0 * rows * C * C * p.taps,
+                        rows * C * 2.0 * 2.0 + (p.sum_h ? rows * C * 2.0 : 0.0) + 2.0 * p.taps * C * C * 2.0);
+    }
     launch_pdl(kern, grid, RB_THREADS, smem, s, a_map, w1_map, w2_map, o_map, ot_map, p, cfg);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;

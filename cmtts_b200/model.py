@@ -85,7 +85,6 @@ class CMTotalTTS:
         self._sd: Optional[Dict[str, torch.Tensor]] = None
         self.packed: Optional[PackedAcoustic] = None
         self.training = False
-        self._cond_split_cache = None
         self.duration_pitch_energy_net = DurationPitchSpeakerNet(self)
         self._ws: Optional[_Workspace] = None
         self.lib = _lib.load()
@@ -147,6 +146,12 @@ class CMTotalTTS:
         lib, s, dev = self.lib, self.spec, self.device
         if s.multi_speaker and spker_embeds is None:
             raise AssertionError("Speaker embedding should not be None")  # cmtts.py:80
+        if not texts.is_cuda and texts.numel() and (int(texts.min()) < 0 or int(texts.max()) >= s.vocab):
+            # nn.Embedding raises IndexError here (modules.py:145); the gather kernel would read out of bounds
+            raise IndexError(f"token id outside [0, {s.vocab}) (wrong symbol table?)")
+        bad_tok = None
+        if texts.is_cuda and texts.numel():
+            bad_tok = ((texts < 0) | (texts >= s.vocab)).any()     # read back with mel_lens.max(), same host sync
         texts = texts.to(dev, torch.int64).contiguous()
         src_lens = src_lens.to(dev, torch.int64).contiguous()
         B, T = texts.shape
@@ -190,10 +195,25 @@ class CMTotalTTS:
                 ws = self._ws.get("vat", lib.cmtts_variance_token_workspace_bytes(d, B, T))
                 _lib.check(lib.cmtts_variance_token(d, self.packed.va.ptrs, *vt_args, _lib.ptr(ws), ws.numel(), st),
                            "variance_token")
-            # the one host round trip of the path: output length is data dependent
-            local_max = int(mel_lens.max().item()) if B > 0 else 0
+            # the one host round trip of the path: output length is data dependent.  The multi-GPU hook reduces the
+            # device scalar BEFORE it is read (cmtts_b200/dist.py), so there is still exactly one sync.
+            m = mel_lens.max() if B > 0 else torch.zeros((), dtype=torch.int64, device=dev)
+            extra = []
             if l_max_hook is not None:
-                local_max = int(l_max_hook(local_max))
+                m = l_max_hook(m)
+            if isinstance(m, torch.Tensor):
+                if bad_tok is not None:
+                    m = torch.cat([m.reshape(-1).to(torch.int64), bad_tok.reshape(1).to(torch.int64)])
+                vals = m.reshape(-1).tolist()
+                if bad_tok is not None and vals.pop():
+                    raise IndexError(f"token id outside [0, {s.vocab}) (wrong symbol table?)")
+                local_max, extra = int(vals[0]), [int(v) for v in vals[1:]]
+            else:
+                local_max = int(m)
+            if max_mel_len and int(max_mel_len) < local_max:
+                # the reference's pad(output, max_len) fails here too (utils/tools.py:724-742: negative F.pad of a
+                # longer row); truncating silently would leave mel_lens / mel_masks inconsistent with cond
+                raise ValueError(f"dpen: max_mel_len={int(max_mel_len)} is shorter than the predicted length {local_max}")
             L = int(max_mel_len) if max_mel_len else local_max
             self.packed_check_rows(L)
             cond = torch.empty(B, L, H, **f32)
@@ -230,7 +250,7 @@ class CMTotalTTS:
             "speaker_emb": spk,
             "src_lens": src_lens,
             # extras (not in the reference dict)
-            "enc": enc, "mel2ph": mel2ph, "e_idx": e_idx, "pitch_idx": pitch_idx,
+            "enc": enc, "mel2ph": mel2ph, "e_idx": e_idx, "pitch_idx": pitch_idx, "l_max_extra": extra,
         }
 
     def packed_check_rows(self, n: int):
@@ -259,12 +279,18 @@ class CMTotalTTS:
         return ds_all, dsp_all
 
     def denoise_step(self, x_t: torch.Tensor, cond: torch.Tensor, steps: Tuple[torch.Tensor, torch.Tensor],
-                     c_in: float = 1.0, c_out: float = 1.0, c_skip: float = 0.0, want_model_out: bool = False):
-        """out = c_out * F(c_in * x_t) + c_skip * x_t on (B,1,L,M) / (B,L,M) channels-last mels."""
+                     c_in: float = 1.0, c_out: float = 1.0, c_skip: float = 0.0, want_model_out: bool = False,
+                     cond16: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+        """out = c_out * F(c_in * x_t) + c_skip * x_t on (B,1,L,M) / (B,L,M) channels-last mels.
+        `cond16`: the conditioner's fp16 hi/lo pair from `split_cond(cond)` when the caller evaluates several solver
+        steps on one conditioner (the sampler does); made here per call otherwise."""
         self._ready()
         lib, s, dev = self.lib, self.spec, self.device
-        shape = x_t.shape
-        x = x_t.to(dev, torch.float32).contiguous().view(-1, shape[-2], shape[-1])
+        shape = tuple(x_t.shape)
+        lead = 1
+        for n in shape[:-2]:
+            lead *= int(n)
+        x = x_t.to(dev, torch.float32).contiguous().view(lead, shape[-2], shape[-1])   # explicit: B may be 0
         B, L, M = x.shape
         if M != s.n_mels or tuple(cond.shape) != (B, L, s.hidden):
             raise ValueError(f"denoise_step: x {tuple(shape)} / cond {tuple(cond.shape)} mismatch")
@@ -274,7 +300,7 @@ class CMTotalTTS:
         d = C.byref(self._dims)
         with torch.cuda.device(dev):
             if self.precision == "tc":
-                c_hi, c_lo = self._cond_split(cond)
+                c_hi, c_lo = cond16 if cond16 is not None else self.split_cond(cond)
                 ws = self._ws.get("dn", lib.cmtts_denoiser_tc_workspace_bytes(d, B, L))
                 _lib.check(lib.cmtts_denoiser_forward_tc(d, self.packed.dn.ptrs, self.packed.dn16.ptrs, _lib.ptr(x),
                                                          _lib.ptr(c_hi), _lib.ptr(c_lo), _lib.ptr(steps[0]),
@@ -290,18 +316,18 @@ class CMTotalTTS:
         out = out.view(shape)
         return (out, mo.view(shape)) if want_model_out else out
 
-    def _cond_split(self, cond: torch.Tensor):
-        """fp16 hi/lo operand pair of the conditioner, made once per conditioner tensor (it is the
-        same for every solver step)."""
-        key = (cond.data_ptr(), tuple(cond.shape), cond._version)
-        if self._cond_split_cache is not None and self._cond_split_cache[0] == key:
-            return self._cond_split_cache[1]
+    def split_cond(self, cond: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """fp16 hi/lo operand pair of the conditioner (B, L, hidden).  It is the same for every solver step
+        (SURVEY.md App. C.1), so the sampler makes it once per call and hands it to `denoise_step`; nothing is cached
+        behind the caller's back (a pointer-keyed cache goes stale when a buffer is refilled through raw pointers)."""
+        cond = cond.to(self.device, torch.float32).contiguous()
         hi = torch.empty(cond.shape, dtype=torch.float16, device=cond.device)
         lo = torch.empty_like(hi)
         rows = cond.shape[0] * cond.shape[1]
-        _lib.check(self.lib.cmtts_f32_to_f16(_lib.ptr(cond), _lib.ptr(hi), _lib.ptr(lo), rows, cond.shape[2],
-                                             cond.shape[2], 1.0, _lib.stream_ptr(cond.device)), "f32_to_f16")
-        self._cond_split_cache = (key, (hi, lo), cond)   # keep `cond` alive so the pointer key stays valid
+        if rows:
+            with torch.cuda.device(cond.device):
+                _lib.check(self.lib.cmtts_f32_to_f16(_lib.ptr(cond), _lib.ptr(hi), _lib.ptr(lo), rows, cond.shape[2],
+                                                     cond.shape[2], 1.0, _lib.stream_ptr(cond.device)), "f32_to_f16")
         return hi, lo
 
     def get_segmentation_model(self):

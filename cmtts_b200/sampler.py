@@ -71,6 +71,7 @@ class _FusedDistiller:
         self.cond = cond
         self._steps_key = None
         self._steps = None
+        self._cond16 = None          # (cond tensor, fp16 hi/lo pair): made once per sampler call
         self.model_outputs = None  # set to a list to capture F per evaluation (parity tests)
 
     def conditioner(self, L: int) -> dict:
@@ -90,11 +91,17 @@ class _FusedDistiller:
             rescaled_t = 1000 * 0.25 * torch.log(sig + 1e-44)
             self._steps = self.model.prepare_steps(rescaled_t, cond["speaker_emb"])
             self._steps_key = sigma_value
+        c16 = None
+        if self.model.precision == "tc":
+            if self._cond16 is None or self._cond16[0] is not cond["cond"]:
+                self._cond16 = (cond["cond"], self.model.split_cond(cond["cond"]))
+            c16 = self._cond16[1]
         if self.model_outputs is not None:
-            out, mo = self.model.denoise_step(x_t, cond["cond"], self._steps, c_in, c_out, c_skip, want_model_out=True)
+            out, mo = self.model.denoise_step(x_t, cond["cond"], self._steps, c_in, c_out, c_skip, want_model_out=True,
+                                              cond16=c16)
             self.model_outputs.append(mo)
             return out
-        return self.model.denoise_step(x_t, cond["cond"], self._steps, c_in, c_out, c_skip)
+        return self.model.denoise_step(x_t, cond["cond"], self._steps, c_in, c_out, c_skip, cond16=c16)
 
 
 def karras_sample_tts(diffusion, model, shape, steps=2, clip_denoised=False, progress=False, callback=None,

@@ -40,6 +40,15 @@ uint64_t cmtts_launch_count(void);
  * umma_dbg: bit field of CMTTS_UMMA_DBG (2 = no halo kernel, 128 = no gate kernel, ...); pdl: 1/0 = programmatic
  * dependent launch on/off; -1 = take the value from the environment */
 void cmtts_debug_set(int32_t umma_dbg, int32_t pdl);
+/* launch profiler (bench.py's per-kernel table and roofline block; the reference has no counterpart — its closest
+ * relative is the wall-clock Timer of p_rtf_cm.py:64-108).  Between begin and end every kernel launch of this library
+ * on `stream` is followed by a CUDA event; cmtts_prof_end synchronises the stream and writes one line per kernel label,
+ * "label\tlaunches\ttotal_us\talgorithmic_flops\talgorithmic_bytes\n", into host buffer `buf` (NUL-terminated, truncated
+ * to `cap`) and returns the number of bytes needed, or a negative error code.  Timing a launch as the distance between
+ * consecutive events serialises programmatic dependent launches, so a profiled step is a few % slower than a plain one:
+ * the profile gives each kernel's SHARE of the step, the step time itself is measured without it. */
+int cmtts_prof_begin(void* stream);
+int64_t cmtts_prof_end(char* host_buf, size_t cap);
 
 /* ---- model dimensions shared by the acoustic entry points ---- */
 typedef struct cmtts_dims {

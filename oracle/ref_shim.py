@@ -10,8 +10,8 @@ The reference is plain Python/PyTorch but does not import as shipped (SURVEY.md 
     parselmouth / pycwt at module import, none of which the hot path calls;
   * model/cm_tool/dist_util.py imports mpi4py + blobfile, model/loss.py imports piq.
 The shim registers stub modules for the absent third-party packages and the one alias; no
-reference source is edited or copied.  It only works inside the build container, where
-/root/reference is mounted; the GPU box never sees it (tests that need it are skipped there).
+reference source is edited or copied.  It reads /root/reference in the build container; on
+the GPU box it falls back to the copy that __graft_entry__.build() stages under oracle/_ref/ (git-ignored).
 """
 from __future__ import annotations
 
@@ -22,7 +22,44 @@ import sys
 import tempfile
 import types
 
-REFERENCE_ROOT = os.environ.get("CMTTS_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+#: staged copy made by __graft_entry__.build() (git-ignored; travels to the GPU box with the snapshot)
+STAGED_ROOT = os.path.join(_HERE, "_ref")
+#: sub-trees of the reference the hot path imports (+ its YAML configs): ~0.4 MB of Python + the HiFi-GAN weights
+STAGED_PARTS = ("model", "utils", "text", "config", "hifigan/__init__.py", "hifigan/models.py", "hifigan/config.json",
+                "hifigan/generator_universal.pth.tar")
+
+
+def _pick_root() -> str:
+    env = os.environ.get("CMTTS_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile(os.path.join("/root/reference", "model", "cmtts.py")):
+        return "/root/reference"
+    return STAGED_ROOT
+
+
+REFERENCE_ROOT = _pick_root()
+
+
+def stage_reference(src: str = "/root/reference", dst: str = STAGED_ROOT) -> bool:
+    """Copy the UNMODIFIED hot-path sub-trees of the mounted reference into oracle/_ref/ (build container only), so
+    that `bench.py --impl reference` and the boundary tests can run the reference's own code and read its own YAML
+    configs on the GPU box, where /root/reference does not exist.  oracle/_ref/ is git-ignored: nothing of the
+    reference enters the history."""
+    import shutil
+
+    if not os.path.isfile(os.path.join(src, "model", "cmtts.py")):
+        return False
+    for part in STAGED_PARTS:
+        s, d = os.path.join(src, part), os.path.join(dst, part)
+        if os.path.isdir(s):
+            shutil.copytree(s, d, dirs_exist_ok=True, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
+        elif os.path.isfile(s):
+            os.makedirs(os.path.dirname(d), exist_ok=True)
+            if not (os.path.isfile(d) and os.path.getsize(d) == os.path.getsize(s)):
+                shutil.copyfile(s, d)
+    return True
 
 
 def reference_available() -> bool:

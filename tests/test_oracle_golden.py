@@ -164,3 +164,36 @@ def test_edge_cases():
     assert O.round_durations(ld).tolist() == [[0.0, 2.0, 2.0, 0.0]]
     with pytest.raises(ValueError):
         O.sampler_plan(3)
+
+
+# ---- bench-size fixtures (oracle/make_fullsize_batches.py): BASELINE.json C2 / C3 / C4 at their per-GPU sizes ----
+FULLSIZE = sorted(glob.glob(os.path.join(GOLDEN, "fullsize_*.pt")))
+
+
+def test_fullsize_fixtures_present():
+    assert [os.path.basename(p) for p in FULLSIZE] == ["fullsize_C2.pt", "fullsize_C3.pt", "fullsize_C4.pt"]
+
+
+@pytest.mark.parametrize("path", FULLSIZE, ids=[os.path.basename(p) for p in FULLSIZE])
+def test_oracle_matches_reference_at_bench_size(path):
+    """The oracle against the reference's outputs at the sizes bench.py runs: integer stages bit-exact over the whole
+    batch (the inputs are cliff-free by construction), log_d / energy within a few ulps, and the mels the reference's
+    own sampler produced for the first and last utterance (T as the config names it, replayed noise)."""
+    g = torch.load(path, map_location="cpu", weights_only=True)
+    m = g["meta"]
+    spec = ModelSpec.preset(m["dataset"])
+    sd = synthetic.make_acoustic_state_dict(spec, m["weight_seed"])
+    assert synthetic.state_dict_digest(sd) == m["digest"], "synthetic weight RNG stream drifted"
+    batch = {"speakers": torch.zeros(m["batch"], dtype=torch.int64), "texts": g["texts"], "src_lens": g["src_lens"],
+             "spker_embeds": g["spker_embeds"]}
+    W = O.Weights(sd)
+    gen = torch.Generator().manual_seed(m["noise_seed"])
+    with torch.no_grad():
+        mel, d = O.sample(W, spec, batch, m["T"], lambda s: torch.randn(*s, generator=gen))
+    assert d["cond"].shape[1] == m["L"]
+    assert torch.equal(d["d_rounded"].to(torch.int16), g["d_rounded"]) and torch.equal(d["mel_lens"], g["mel_lens"])
+    assert torch.equal(d["e_idx"].to(torch.int16), g["e_idx"]) and torch.equal(d["pitch_idx"].to(torch.int16), g["pitch_idx"])
+    assert torch.equal(d["mel2ph"].to(torch.int16), g["mel2ph"])
+    assert (d["log_d_predictions"] - g["log_d"]).abs().max() <= 5e-6
+    assert (d["e_predictions"] - g["e_pred"]).abs().max() <= 5e-6
+    assert (mel[m["mel_rows"]] - g["mel_rows"]).abs().max() <= 2e-5
