@@ -1,45 +1,45 @@
-"""Summarise an ncu launch list (gpu__time_duration.sum CSV): time per kernel family and share of the step.
+"""Per-kernel totals of an ncu launch list (`ncu --metrics gpu__time_duration.sum --csv --log-file X.csv ...`):
 
-    python tools/launch_summary.py gpurun_out/launches.csv [--by-grid]
-"""
+    python tools/launch_summary.py gpurun_out/launches.csv [--skip N]
+
+Prints kernel, launches, total us, share — cold-cache, serialised times: compare SHARES, not absolutes."""
 import csv
 import re
 import sys
-from collections import defaultdict
+from collections import OrderedDict
 
 
-def short(name: str) -> str:
-    name = re.sub(r"<unnamed>::", "", name)
-    name = re.sub(r"^void\s+", "", name)
-    m = re.match(r"([\w:]+)(<[^>]*>)?", name)
-    return (m.group(1) + (m.group(2) or "")) if m else name[:60]
+def short(name):
+    m = re.search(r"(\w+)<([^(]*)>\(", name)
+    if m:
+        return f"{m.group(1)}<{m.group(2)}>"
+    return name.split("(")[0][-70:]
 
 
 def main():
     path = sys.argv[1]
-    by_grid = "--by-grid" in sys.argv
-    rows = []
-    with open(path) as f:
-        lines = [l for l in f if l.startswith('"')]
-    for r in csv.DictReader(lines):
+    skip = int(sys.argv[sys.argv.index("--skip") + 1]) if "--skip" in sys.argv else 0
+    lines = [l for l in open(path, errors="replace") if l.startswith('"')]
+    rows = list(csv.DictReader(lines))
+    agg = OrderedDict()
+    n = 0
+    for r in rows:
         if r.get("Metric Name") != "gpu__time_duration.sum":
             continue
-        rows.append((short(r["Kernel Name"]), r["Grid Size"], r["Block Size"], float(r["Metric Value"]) / 1e3))
-    # one step of the hot path = from one embed_tokens launch (first kernel of the encoder) to the next
-    starts = [i for i, r in enumerate(rows) if r[0].startswith("embed_tokens")]
-    if "--step" in sys.argv and len(starts) >= 2:
-        k = int(sys.argv[sys.argv.index("--step") + 1])
-        rows = rows[starts[k]:starts[k + 1]]
-    tot = sum(r[3] for r in rows)
-    agg = defaultdict(lambda: [0, 0.0])
-    for n, g, b, t in rows:
-        k = (n, g) if by_grid else (n,)
-        agg[k][0] += 1
-        agg[k][1] += t
-    print(f"{len(rows)} launches, {tot / 1e3:.3f} ms total (ncu per-launch times are serialised and cold-cache)")
-    print(f"{'kernel':70s} {'launches':>8s} {'us total':>10s} {'us avg':>8s} {'share':>6s}")
-    for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print(f"{' '.join(k)[:70]:70s} {c:8d} {t:10.1f} {t / c:8.1f} {100 * t / tot:5.1f}%")
+        n += 1
+        if n <= skip:
+            continue
+        v = float(r["Metric Value"].replace(",", ""))
+        u = r["Metric Unit"].lower()
+        us = v * {"nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0, "msecond": 1e3, "ms": 1e3}.get(u, 1e-3)
+        k = short(r["Kernel Name"])
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += us
+    tot = sum(a[1] for a in agg.values()) or 1.0
+    print(f"{n - skip} launches, {tot / 1e3:.3f} ms total")
+    for k, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{us:10.1f} us  {100 * us / tot:5.1f} %  x{c:<4d} {us / c:8.1f} us/launch  {k}")
 
 
 if __name__ == "__main__":
