@@ -21,6 +21,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import _lib
+from . import ops  # noqa: F401  (registers torch.ops.cmtts_b200.*)
 from .config import ModelSpec
 from .weights import PackedAcoustic
 
@@ -87,6 +88,7 @@ class CMTotalTTS:
         self.training = False
         self.duration_pitch_energy_net = DurationPitchSpeakerNet(self)
         self._ws: Optional[_Workspace] = None
+        self.handle: Optional[int] = None        # names this model in the torch.ops.cmtts_b200 custom ops (cmtts_b200/ops.py)
         self.lib = _lib.load()
 
     # ---- nn.Module-like surface used by synthesize.py:79-86 ---------------------------------
@@ -126,9 +128,12 @@ class CMTotalTTS:
         return iter(())
 
     def _repack(self):
+        from . import ops
         self.packed = PackedAcoustic(self.spec, self._sd, self.device)
         self._dims = self.packed.dims()
         self._ws = _Workspace(self.device)
+        if self.handle is None:
+            self.handle = ops.register(self)
 
     def _ready(self):
         if self.packed is None:
@@ -157,83 +162,34 @@ class CMTotalTTS:
         B, T = texts.shape
         spk_in = None if spker_embeds is None or not s.multi_speaker else \
             spker_embeds.to(dev, torch.float32).contiguous()
-        self.packed_check_rows(T)
-        d = C.byref(self._dims)
-        st = _lib.stream_ptr(dev)
-        f32 = dict(dtype=torch.float32, device=dev)
-        i64 = dict(dtype=torch.int64, device=dev)
-        H = s.hidden
-        with torch.cuda.device(dev):
-            enc = torch.empty(B, T, H, **f32)
-            tc = self.precision == "tc" and self.tc_frontend
-            if tc:
-                ws = self._ws.get("enc", lib.cmtts_encoder_tc_workspace_bytes(d, B, T))
-                _lib.check(lib.cmtts_encoder_forward_tc(d, self.packed.enc.ptrs, self.packed.enc16.ptrs, _lib.ptr(texts),
-                                                        _lib.ptr(src_lens), B, T, _lib.ptr(enc), _lib.ptr(ws), ws.numel(), st),
-                           "encoder_forward_tc")
-            else:
-                ws = self._ws.get("enc", lib.cmtts_encoder_workspace_bytes(d, B, T))
-                _lib.check(lib.cmtts_encoder_forward(d, self.packed.enc.ptrs, _lib.ptr(texts), _lib.ptr(src_lens), B, T,
-                                                     _lib.ptr(enc), _lib.ptr(ws), ws.numel(), st), "encoder_forward")
-            out1 = torch.empty(B, T, H, **f32)
-            log_d = torch.empty(B, T, **f32)
-            d_rounded = torch.empty(B, T, **f32)
-            e_pred = torch.empty(B, T, **f32)
-            e_idx = torch.empty(B, T, **i64)
-            cumsum = torch.empty(B, 2, T, **i64)
-            mel_lens = torch.empty(B, **i64)
-            spk = torch.empty(B, H, **f32) if s.multi_speaker else None
-            f0_stats = torch.empty(B, 4, **f32)
-            vt_args = (_lib.ptr(enc), _lib.ptr(src_lens), _lib.ptr(spk_in), e_control, d_control,
-                       B, T, _lib.ptr(out1), _lib.ptr(log_d), _lib.ptr(d_rounded), _lib.ptr(e_pred), _lib.ptr(e_idx),
-                       _lib.ptr(cumsum), _lib.ptr(mel_lens), _lib.ptr(spk), _lib.ptr(f0_stats))
-            if tc:
-                ws = self._ws.get("vat", lib.cmtts_variance_token_tc_workspace_bytes(d, B, T))
-                _lib.check(lib.cmtts_variance_token_tc(d, self.packed.va.ptrs, self.packed.va16.ptrs, *vt_args,
-                                                       _lib.ptr(ws), ws.numel(), st), "variance_token_tc")
-            else:
-                ws = self._ws.get("vat", lib.cmtts_variance_token_workspace_bytes(d, B, T))
-                _lib.check(lib.cmtts_variance_token(d, self.packed.va.ptrs, *vt_args, _lib.ptr(ws), ws.numel(), st),
-                           "variance_token")
-            # the one host round trip of the path: output length is data dependent.  The multi-GPU hook reduces the
-            # device scalar BEFORE it is read (cmtts_b200/dist.py), so there is still exactly one sync.
-            m = mel_lens.max() if B > 0 else torch.zeros((), dtype=torch.int64, device=dev)
-            extra = []
-            if l_max_hook is not None:
-                m = l_max_hook(m)
-            if isinstance(m, torch.Tensor):
-                if bad_tok is not None:
-                    m = torch.cat([m.reshape(-1).to(torch.int64), bad_tok.reshape(1).to(torch.int64)])
-                vals = m.reshape(-1).tolist()
-                if bad_tok is not None and vals.pop():
-                    raise IndexError(f"token id outside [0, {s.vocab}) (wrong symbol table?)")
-                local_max, extra = int(vals[0]), [int(v) for v in vals[1:]]
-            else:
-                local_max = int(m)
-            if max_mel_len and int(max_mel_len) < local_max:
-                # the reference's pad(output, max_len) fails here too (utils/tools.py:724-742: negative F.pad of a
-                # longer row); truncating silently would leave mel_lens / mel_masks inconsistent with cond
-                raise ValueError(f"dpen: max_mel_len={int(max_mel_len)} is shorter than the predicted length {local_max}")
-            L = int(max_mel_len) if max_mel_len else local_max
-            self.packed_check_rows(L)
-            cond = torch.empty(B, L, H, **f32)
-            mel2ph = torch.empty(B, L, **i64)
-            cwt = torch.empty(B, L, s.cwt_out, **f32)
-            f0_denorm = torch.empty(B, L, **f32)
-            pitch_idx = torch.empty(B, L, **i64)
-            if L > 0:
-                d = C.byref(self._dims)
-                vf_args = (_lib.ptr(out1), _lib.ptr(cumsum), _lib.ptr(mel_lens), _lib.ptr(f0_stats),
-                           p_control, B, T, L, _lib.ptr(cond), _lib.ptr(mel2ph), _lib.ptr(cwt), _lib.ptr(f0_denorm),
-                           _lib.ptr(pitch_idx))
-                if tc:
-                    ws = self._ws.get("vaf", lib.cmtts_variance_frame_tc_workspace_bytes(d, B, L))
-                    _lib.check(lib.cmtts_variance_frame_tc(d, self.packed.va.ptrs, self.packed.va16.ptrs, *vf_args,
-                                                           _lib.ptr(ws), ws.numel(), st), "variance_frame_tc")
-                else:
-                    ws = self._ws.get("vaf", lib.cmtts_variance_frame_workspace_bytes(d, B, L))
-                    _lib.check(lib.cmtts_variance_frame(d, self.packed.va.ptrs, *vf_args, _lib.ptr(ws), ws.numel(), st),
-                               "variance_frame")
+        ops = torch.ops.cmtts_b200
+        enc = ops.encoder_forward(self.handle, texts, src_lens)
+        out1, log_d, d_rounded, e_pred, e_idx, cumsum, mel_lens, spk, f0_stats = ops.variance_token(
+            self.handle, enc, src_lens, spk_in, float(e_control), float(d_control))
+        if not s.multi_speaker:
+            spk = None
+        # the one host round trip of the path: output length is data dependent.  The multi-GPU hook reduces the
+        # device scalar BEFORE it is read (cmtts_b200/dist.py), so there is still exactly one sync.
+        m = mel_lens.max() if B > 0 else torch.zeros((), dtype=torch.int64, device=dev)
+        extra = []
+        if l_max_hook is not None:
+            m = l_max_hook(m)
+        if isinstance(m, torch.Tensor):
+            if bad_tok is not None:
+                m = torch.cat([m.reshape(-1).to(torch.int64), bad_tok.reshape(1).to(torch.int64)])
+            vals = m.reshape(-1).tolist()
+            if bad_tok is not None and vals.pop():
+                raise IndexError(f"token id outside [0, {s.vocab}) (wrong symbol table?)")
+            local_max, extra = int(vals[0]), [int(v) for v in vals[1:]]
+        else:
+            local_max = int(m)
+        if max_mel_len and int(max_mel_len) < local_max:
+            # the reference's pad(output, max_len) fails here too (utils/tools.py:724-742: negative F.pad of a
+            # longer row); truncating silently would leave mel_lens / mel_masks inconsistent with cond
+            raise ValueError(f"dpen: max_mel_len={int(max_mel_len)} is shorter than the predicted length {local_max}")
+        L = int(max_mel_len) if max_mel_len else local_max
+        cond, mel2ph, cwt, f0_denorm, pitch_idx = ops.variance_frame(self.handle, out1, cumsum, mel_lens, f0_stats,
+                                                                      float(p_control), L)
         ar_t = torch.arange(T, device=dev)
         ar_l = torch.arange(local_max, device=dev)
         return {
@@ -263,20 +219,9 @@ class CMTotalTTS:
         """Step-embedding MLP and the per-layer diffusion/speaker projections (blocks.py:633-640,
         :669-674): sigma-only work, hoisted out of the solver loop."""
         self._ready()
-        lib, s, dev = self.lib, self.spec, self.device
-        t = timesteps.to(dev, torch.float32).contiguous()
-        B = t.shape[0]
-        n = s.res_layers * s.res_channels
-        ds_all = torch.empty(B, n, dtype=torch.float32, device=dev)
-        dsp_all = torch.empty(B, n, dtype=torch.float32, device=dev) if s.multi_speaker else ds_all
-        d = C.byref(self._dims)
-        ws = self._ws.get("dnp", lib.cmtts_denoiser_prepare_workspace_bytes(d, B))
-        with torch.cuda.device(dev):
-            _lib.check(lib.cmtts_denoiser_prepare(d, self.packed.dn.ptrs, _lib.ptr(t),
-                                                  _lib.ptr(speaker_emb) if s.multi_speaker else None, B,
-                                                  _lib.ptr(ds_all), _lib.ptr(dsp_all), _lib.ptr(ws), ws.numel(),
-                                                  _lib.stream_ptr(dev)), "denoiser_prepare")
-        return ds_all, dsp_all
+        t = timesteps.to(self.device, torch.float32).contiguous()
+        spk = None if (speaker_emb is None or not self.spec.multi_speaker) else speaker_emb.to(self.device, torch.float32).contiguous()
+        return torch.ops.cmtts_b200.denoiser_prepare(self.handle, t, spk)
 
     def denoise_step(self, x_t: torch.Tensor, cond: torch.Tensor, steps: Tuple[torch.Tensor, torch.Tensor],
                      c_in: float = 1.0, c_out: float = 1.0, c_skip: float = 0.0, want_model_out: bool = False,
@@ -295,24 +240,9 @@ class CMTotalTTS:
         if M != s.n_mels or tuple(cond.shape) != (B, L, s.hidden):
             raise ValueError(f"denoise_step: x {tuple(shape)} / cond {tuple(cond.shape)} mismatch")
         cond = cond.to(dev, torch.float32).contiguous()
-        out = torch.empty_like(x)
-        mo = torch.empty_like(x) if want_model_out else None
-        d = C.byref(self._dims)
-        with torch.cuda.device(dev):
-            if self.precision == "tc":
-                c_hi, c_lo = cond16 if cond16 is not None else self.split_cond(cond)
-                ws = self._ws.get("dn", lib.cmtts_denoiser_tc_workspace_bytes(d, B, L))
-                _lib.check(lib.cmtts_denoiser_forward_tc(d, self.packed.dn.ptrs, self.packed.dn16.ptrs, _lib.ptr(x),
-                                                         _lib.ptr(c_hi), _lib.ptr(c_lo), _lib.ptr(steps[0]),
-                                                         _lib.ptr(steps[1]), c_in, c_out, c_skip, B, L, _lib.ptr(out),
-                                                         _lib.ptr(mo), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
-                           "denoiser_forward_tc")
-            else:
-                ws = self._ws.get("dn", lib.cmtts_denoiser_workspace_bytes(d, B, L))
-                _lib.check(lib.cmtts_denoiser_forward(d, self.packed.dn.ptrs, _lib.ptr(x), _lib.ptr(cond),
-                                                      _lib.ptr(steps[0]), _lib.ptr(steps[1]), c_in, c_out, c_skip, B, L,
-                                                      _lib.ptr(out), _lib.ptr(mo), _lib.ptr(ws), ws.numel(),
-                                                      _lib.stream_ptr(dev)), "denoiser_forward")
+        c_hi, c_lo = cond16 if cond16 is not None else (None, None)
+        out, mo = torch.ops.cmtts_b200.denoiser_forward(self.handle, x, cond, c_hi, c_lo, steps[0], steps[1], float(c_in),
+                                                        float(c_out), float(c_skip), bool(want_model_out))
         out = out.view(shape)
         return (out, mo.view(shape)) if want_model_out else out
 
@@ -320,15 +250,7 @@ class CMTotalTTS:
         """fp16 hi/lo operand pair of the conditioner (B, L, hidden).  It is the same for every solver step
         (SURVEY.md App. C.1), so the sampler makes it once per call and hands it to `denoise_step`; nothing is cached
         behind the caller's back (a pointer-keyed cache goes stale when a buffer is refilled through raw pointers)."""
-        cond = cond.to(self.device, torch.float32).contiguous()
-        hi = torch.empty(cond.shape, dtype=torch.float16, device=cond.device)
-        lo = torch.empty_like(hi)
-        rows = cond.shape[0] * cond.shape[1]
-        if rows:
-            with torch.cuda.device(cond.device):
-                _lib.check(self.lib.cmtts_f32_to_f16(_lib.ptr(cond), _lib.ptr(hi), _lib.ptr(lo), rows, cond.shape[2],
-                                                     cond.shape[2], 1.0, _lib.stream_ptr(cond.device)), "f32_to_f16")
-        return hi, lo
+        return torch.ops.cmtts_b200.split_f16(cond.to(self.device, torch.float32).contiguous())
 
     def get_segmentation_model(self):
         """tts_net.py:66-73 -> (dpen callable, denoise_fun(mel[B,1,L,80]... ) in the reference's

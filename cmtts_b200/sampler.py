@@ -16,6 +16,7 @@ from typing import Optional
 import numpy as np
 import torch
 
+from . import ops  # noqa: F401  (registers torch.ops.cmtts_b200.*)
 from .model import CMTotalTTS, KarrasDenoiser
 
 
@@ -134,7 +135,6 @@ def karras_sample_tts(diffusion, model, shape, steps=2, clip_denoised=False, pro
         t_max_rho = t_max ** (1 / rho_)
         t_min_rho = t_min ** (1 / rho_)
         x = x_T
-        lib = model.lib
         for i in range(len(ts) - 1):
             t = (t_max_rho + ts[i] / (steps - 1) * (t_min_rho - t_max_rho)) ** rho_
             x0 = distiller(x, t)
@@ -144,10 +144,6 @@ def karras_sample_tts(diffusion, model, shape, steps=2, clip_denoised=False, pro
             # x = x0 + noise * np.sqrt(next_t**2 - t_min**2) * 0.85: two fp32 multiplies then an add
             s1 = float(np.float32(np.sqrt(next_t ** 2 - t_min ** 2)))
             s2 = float(np.float32(0.85))
-            x = torch.empty_like(x0)
-            from . import _lib
-            with torch.cuda.device(device):
-                _lib.check(lib.cmtts_renoise(_lib.ptr(x0.contiguous()), _lib.ptr(noise), s1, s2, _lib.ptr(x),
-                                             x.numel(), _lib.stream_ptr(device)), "renoise")
+            x = torch.ops.cmtts_b200.renoise(x0, noise, s1, s2)
         x_0 = x
     return x_0[:, 0]

@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import ops  # noqa: F401  (registers torch.ops.cmtts_b200.*)
 from .config import HifiGanSpec
 from .model import _Workspace
 from .weights import PackedHifiGan
@@ -57,6 +58,7 @@ class Generator:
         self._sd: Optional[Dict[str, torch.Tensor]] = None
         self.packed: Optional[PackedHifiGan] = None
         self._ws: Optional[_Workspace] = None
+        self.handle: Optional[int] = None        # names this vocoder in torch.ops.cmtts_b200.hifigan_forward
         self.lib = _lib.load()
 
     def load_state_dict(self, sd, strict: bool = True):
@@ -84,43 +86,26 @@ class Generator:
         return self
 
     def _repack(self):
+        from . import ops
         self.packed = PackedHifiGan(self.hspec, self._sd, self.device)
         self._ws = _Workspace(self.device)
+        if self.handle is None:
+            self.handle = ops.register(self)
 
     def run(self, mel_blc: torch.Tensor, want_float: bool = True, want_int16: bool = False,
             max_wav_value: float = 32768.0):
         """(B, L, 80) channels-last mels -> wav (B, hop L) fp32 and/or int16."""
         if self.packed is None:
             raise _lib.CmttsError("Generator: call load_state_dict(...) and .to('cuda') first")
-        dev, lib = self.device, self.lib
-        mel = mel_blc.to(dev, torch.float32).contiguous()
-        B, L, M = mel.shape
-        if M != self.hspec.n_mels:
-            raise ValueError(f"expected {self.hspec.n_mels} mel channels, got {M}")
-        n = L * self.packed.hop
-        wav = torch.empty(B, n, dtype=torch.float32, device=dev) if want_float else None
-        w16 = torch.empty(B, n, dtype=torch.int16, device=dev) if want_int16 else None
-        with torch.cuda.device(dev):
-            if self.precision == "tc":
-                ws = self._ws.get("hifi", lib.cmtts_hifigan_tc_workspace_bytes(self.packed.cfg, B, L))
-                _lib.check(lib.cmtts_hifigan_forward_tc(self.packed.cfg, self.packed.table16.ptrs, _lib.ptr(mel), B, L,
-                                                        _lib.ptr(wav), _lib.ptr(w16), max_wav_value, _lib.ptr(ws),
-                                                        ws.numel(), _lib.stream_ptr(dev)), "hifigan_forward_tc")
-            else:
-                ws = self._ws.get("hifi", lib.cmtts_hifigan_workspace_bytes(self.packed.cfg, B, L))
-                _lib.check(lib.cmtts_hifigan_forward(self.packed.cfg, self.packed.table.ptrs, _lib.ptr(mel), B, L,
-                                                     _lib.ptr(wav), _lib.ptr(w16), max_wav_value, _lib.ptr(ws), ws.numel(),
-                                                     _lib.stream_ptr(dev)), "hifigan_forward")
-        return wav, w16
+        mel = mel_blc.to(self.device, torch.float32).contiguous()
+        if mel.shape[2] != self.hspec.n_mels:
+            raise ValueError(f"expected {self.hspec.n_mels} mel channels, got {mel.shape[2]}")
+        wav, w16 = torch.ops.cmtts_b200.hifigan_forward(self.handle, mel, bool(want_float), bool(want_int16), float(max_wav_value))
+        return (wav if want_float else None), (w16 if want_int16 else None)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """hifigan.Generator.forward: (B, 80, L) -> (B, 1, 256 L)."""
-        dev, lib = self.device, self.lib
-        x = x.to(dev, torch.float32).contiguous()
-        B, M, L = x.shape
-        mel = torch.empty(B, L, M, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            _lib.check(lib.cmtts_transpose_bcl_blc(_lib.ptr(x), _lib.ptr(mel), B, M, L, _lib.stream_ptr(dev)), "transpose")
+        mel = torch.ops.cmtts_b200.transpose_bcl_blc(x.to(self.device, torch.float32).contiguous())
         wav, _ = self.run(mel)
         return wav.unsqueeze(1)
 
@@ -158,12 +143,9 @@ def vocoder_infer(mels: torch.Tensor, vocoder: Generator, model_config, preproce
     if model_config["vocoder"]["model"] != "HiFi-GAN":
         raise NotImplementedError("only HiFi-GAN")
     max_wav = float(preprocess_config["preprocessing"]["audio"]["max_wav_value"])
-    dev, lib = vocoder.device, vocoder.lib
-    x = mels.to(dev, torch.float32).contiguous()
-    B, M, L = x.shape
-    mel = torch.empty(B, L, M, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        _lib.check(lib.cmtts_transpose_bcl_blc(_lib.ptr(x), _lib.ptr(mel), B, M, L, _lib.stream_ptr(dev)), "transpose")
+    x = mels.to(vocoder.device, torch.float32).contiguous()
+    B = x.shape[0]
+    mel = torch.ops.cmtts_b200.transpose_bcl_blc(x)
     _, w16 = vocoder.run(mel, want_float=False, want_int16=True, max_wav_value=max_wav)
     host = w16.cpu().numpy()
     wavs = [host[i] for i in range(B)]

@@ -108,3 +108,19 @@ def test_sigma_plan_matches_reference_values():
     assert abs(t - 1095.5067) < 1e-3
     s = get_sigmas_karras(2, 0.002, 80.0)
     assert abs(float(s[0]) - 79.99998474121094) < 1e-9 and float(s[2]) == 0.0
+
+
+def test_custom_ops_are_registered_and_have_no_cpu_fallback():
+    """north_star: kernels bound as custom ops through the C ABI.  Every op of cmtts_b200/ops.py exists under
+    torch.ops.cmtts_b200 with a CUDA kernel only: CPU tensors are refused by the dispatcher, not silently computed."""
+    import pytest
+    import torch
+    from cmtts_b200 import ops
+    for name in ops.OPS:
+        assert hasattr(torch.ops.cmtts_b200, name), name
+        assert torch._C._dispatch_has_kernel_for_dispatch_key(f"cmtts_b200::{name}", "CUDA")
+        assert not torch._C._dispatch_has_kernel_for_dispatch_key(f"cmtts_b200::{name}", "CPU")
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.cmtts_b200.renoise(torch.zeros(4), torch.zeros(4), 1.0, 0.85)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.cmtts_b200.split_f16(torch.zeros(2, 8))
