@@ -34,8 +34,9 @@ def _cwd(path):
 class ReferenceRunner:
     """Builds the reference model + vocoder once; `step(batch, T)` runs one whole pass and returns timings."""
 
-    def __init__(self, dataset: str, spec, acoustic_sd: Dict[str, torch.Tensor], hifigan_sd: Optional[Dict] = None):
-        self.kind = "reference" if ref_shim.reference_available() else "port"
+    def __init__(self, dataset: str, spec, acoustic_sd: Dict[str, torch.Tensor], hifigan_sd: Optional[Dict] = None,
+                 force_port: bool = False):
+        self.kind = "reference" if (ref_shim.reference_available() and not force_port) else "port"
         self.spec = spec
         self.cores = os.cpu_count() or 1
         torch.set_num_threads(self.cores)

@@ -11,8 +11,9 @@ timeout 900 python -m pytest tests -m gpu -x -q -s > $OUT/gpu_tests_$TAG.log 2>&
 tail -3 $OUT/gpu_tests_$TAG.log
 timeout 120 python __graft_entry__.py --smoke 2>&1 | tail -2
 timeout 400 python bench.py --steps 20 --warmup 5 > $OUT/bench_${TAG}_C2_T4.json 2> $OUT/bench_${TAG}_C2_T4.err
-tail -c 600 $OUT/bench_${TAG}_C2_T4.err
+tail -c 3000 $OUT/bench_${TAG}_C2_T4.err
 timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_${TAG}_reference.json 2> $OUT/bench_${TAG}_reference.err
+tail -c 3000 $OUT/bench_${TAG}_reference.err
 run() { name=$1; shift; timeout 300 python bench.py --no-cpu-baseline --steps 20 --warmup 5 "$@" > $OUT/bench_${TAG}_$name.json 2> $OUT/bench_${TAG}_$name.err || tail -c 400 $OUT/bench_${TAG}_$name.err; }
 run C2_T1 --config C2 --T 1
 run C1 --config C1
@@ -44,4 +45,6 @@ python tools/launch_summary.py $OUT/launches_${TAG}_C3.csv > $OUT/launches_${TAG
 # full capture of the vocoder kernels at C2 size: second pass of the stage (skip the first = warm-up)
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:umma_ -s 64 -c 64 -o $OUT/prof_voc_$TAG -f \
     python tools/stage_only.py --stage vocoder --config C2 --reps 2 > $OUT/prof_voc_$TAG.log 2>&1
-ls -la $OUT | tail -50
+python tools/ncu_summary.py $OUT/prof_voc_$TAG.ncu-rep $OUT/ncu_${TAG}_voc_summary.csv
+rm -f $OUT/prof_voc_$TAG.ncu-rep          # 120 MB: over gpurun's 64 MiB return limit; the per-launch summary is what is kept
+du -sh $OUT; ls $OUT | wc -l
