@@ -134,6 +134,17 @@ def install() -> None:
     import model as _model_pkg
 
     _model_pkg.diffgantts = cmtts
+    # The reference picks its device once, at import: `device = cuda if available` module globals (utils/tools.py:22,
+    # model/modules.py:29) that get_mask_from_lengths (:280) and LengthRegulator.LR (:434) move tensors to.  The oracle
+    # and the CPU baseline run the reference on the HOST, also on a box that has a GPU: point those globals at the CPU
+    # (run-time state of the imported modules; no source is touched).
+    import torch
+
+    import model.modules as _mm
+    import utils.tools as _ut
+
+    _ut.device = torch.device("cpu")
+    _mm.device = torch.device("cpu")
     _INSTALLED = True
 
 
