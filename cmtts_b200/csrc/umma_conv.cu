@@ -693,12 +693,15 @@ conv_post_f16_kernel(const __half* __restrict__ x, const float* __restrict__ w, 
         for (int c8 = 0; c8 < cpr; ++c8) {
             const uint4 u = *reinterpret_cast<const uint4*>(xr + c8 * 16);
             const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(h[j]);
-                acc = fmaf(f.x, wk[c8 * 8 + 2 * j], acc);
-                acc = fmaf(f.y, wk[c8 * 8 + 2 * j + 1], acc);
-            }
+            // weights as two 16-byte broadcast reads per 8 channels (one LDS per weight made the shared-memory pipe,
+            // 252 loads per output sample, the limiter of this HBM-bound op); same FMA order, bit-identical result
+            const float4 w0 = *reinterpret_cast<const float4*>(wk + c8 * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(wk + c8 * 8 + 4);
+            const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+            acc = fmaf(f0.x, w0.x, acc); acc = fmaf(f0.y, w0.y, acc);
+            acc = fmaf(f1.x, w0.z, acc); acc = fmaf(f1.y, w0.w, acc);
+            acc = fmaf(f2.x, w1.x, acc); acc = fmaf(f2.y, w1.y, acc);
+            acc = fmaf(f3.x, w1.z, acc); acc = fmaf(f3.y, w1.w, acc);
         }
     }
     const float y = tanhf(acc / pre_div + bias[0]);

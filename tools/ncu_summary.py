@@ -61,7 +61,7 @@ def main():
             if "byte" in unit.lower():
                 v = to_bytes(v, unit) * scale
             elif name == "gpu__time_duration.sum":
-                v = v * {"nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}.get(unit.lower(), 1e-3)
+                v = v * {"nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0, "msecond": 1e3, "ms": 1e3, "second": 1e6, "s": 1e6}.get(unit.lower(), 1e-3)
             else:
                 v = v * scale
             line.append(f"{v:.3f}")
