@@ -70,6 +70,9 @@ def parse():
                     "arm, 8 = the reference's own DataLoader batch size in the reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel launch profile / roofline pass")
+    ap.add_argument("--graphs", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step from CUDA graphs (cmtts_b200.synthesize.Pipeline(graphs=True)); auto = on for the "
+                         "launch-latency-bound configs (C1, C3), off for the GPU-bound ones")
     ap.add_argument("--synthetic-vocoder", action="store_true",
                     help="synthetic HiFi-GAN weights even when the reference's generator_universal.pth.tar is staged")
     ap.add_argument("--ffma-frontend", action="store_true",
@@ -378,7 +381,8 @@ def main():
     from cmtts_b200.synthesize import Pipeline
 
     lib = _lib.load()
-    pipe = Pipeline(spec, sd, hifigan_sd, dev, precision=args.precision, tc_frontend=not args.ffma_frontend)
+    use_graphs = args.graphs == "on" or (args.graphs == "auto" and args.config in ("C1", "C3"))
+    pipe = Pipeline(spec, sd, hifigan_sd, dev, precision=args.precision, tc_frontend=not args.ffma_frontend, graphs=use_graphs)
 
     def barrier():
         if dist is not None:
@@ -465,7 +469,7 @@ def main():
         Tsrc = h_texts.shape[1]
 
     # ---- timed: device-resident inputs ----
-    launches0 = lib.cmtts_launch_count()
+    launches0 = lib.cmtts_launch_count() + pipe.graph_kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     wall0 = time.time()
@@ -477,7 +481,7 @@ def main():
     barrier()
     wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
-    launches = lib.cmtts_launch_count() - launches0
+    launches = lib.cmtts_launch_count() + pipe.graph_kernel_launches - launches0
     clk = clocks.stop(wall0, wall1, t_load0)
 
     # ---- timed: end to end with host buffers ----
@@ -511,7 +515,12 @@ def main():
         # RTF as p_rtf_cm.py defines it (informational; every rank computes its own, rank 0 reports)
         from cmtts_b200.synthesize import rtf_like_reference
         rtf = rtf_like_reference(pipe, d_texts, d_lens, d_spk, args.T) if B else None
-        prof_step = lambda: pipe(d_texts, d_lens, d_spk, T=args.T)       # noqa: E731
+        def prof_step():                 # the profiler times launches: one EAGER step (graph replays launch nothing through the library)
+            was, pipe.graphs = pipe.graphs, False
+            try:
+                pipe(d_texts, d_lens, d_spk, T=args.T)
+            finally:
+                pipe.graphs = was
     prof = None
     if not args.no_profile and B:
         prof = kernel_profile(lib, prof_step, dev)
@@ -548,6 +557,7 @@ def main():
                    "padding_mode": {"global": "global L_max (one 8-byte MAX all-reduce; bit-identical to the single-GPU batch)",
                                     "local": "per-shard L_max (length-bucketed shards; each shard = the reference run on its rows)",
                                     "n/a": "fixed-length mels"}[padding] if world > 1 else "single batch",
+                   "cuda_graphs": bool(use_graphs), "graph_replays": int(pipe.graph_replays),
                    "collation": "async gather of int16 wavs + mel_lens to rank 0, inside the timed region" if world > 1 else "none",
                    "l2_policy": "working set (GBs of activations per step) is far larger than the 126 MB L2; no flush needed"
                    if B * L >= 8000 else "small batch: activations of consecutive launches stay L2-resident by design "

@@ -237,13 +237,17 @@ few_rows_linear_kernel(const ConvParams p) {
     const int tx = threadIdx.x & 31, ky = threadIdx.x >> 5;
     const int n = blockIdx.x * FR_COLS + tx;
     const bool n_ok = n < p.N;
+    // rows are processed in chunks of FR_ROWS (blockIdx.y): a row's result does not depend on how many other rows the
+    // call holds, so a 64-utterance batch and its two 32-utterance shards agree bit for bit (multi-GPU global padding)
+    const int m0 = blockIdx.y * FR_ROWS;
+    const int rows = min(FR_ROWS, p.M - m0);
     float acc[FR_ROWS];
 #pragma unroll
     for (int m = 0; m < FR_ROWS; ++m) acc[m] = 0.f;
     for (int k0 = 0; k0 < p.Cin; k0 += FR_KC) {
         for (int i = threadIdx.x; i < FR_ROWS * FR_KC; i += blockDim.x) {
             const int m = i / FR_KC, kk = i - m * FR_KC;
-            s_x[m][kk] = (m < p.M && k0 + kk < p.Cin) ? p.x[(long long)m * p.x_ld + k0 + kk] : 0.f;
+            s_x[m][kk] = (m < rows && k0 + kk < p.Cin) ? p.x[(long long)(m0 + m) * p.x_ld + k0 + kk] : 0.f;
         }
         __syncthreads();
 #pragma unroll
@@ -263,22 +267,22 @@ few_rows_linear_kernel(const ConvParams p) {
         __syncthreads();
     }
     if (ky == 0 && n_ok) {
-        for (int m = 0; m < p.M; ++m) {
+        for (int m = 0; m < rows; ++m) {
             float v = fmaf(s_red[m][tx], p.alpha, p.bias ? p.bias[n] : 0.f);
             v *= p.beta;
             if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
-            if (p.res1) v = fmaf(p.res1[(long long)m * p.res1_ld + n], p.res1_scale, v);
-            p.out[(long long)m * p.out_ld + n] = v * p.out_scale;
+            if (p.res1) v = fmaf(p.res1[(long long)(m0 + m) * p.res1_ld + n], p.res1_scale, v);
+            p.out[(long long)(m0 + m) * p.out_ld + n] = v * p.out_scale;
         }
     }
 }
 }  // namespace
 
 int launch_conv1d_simt(const ConvParams& p, cudaStream_t s) {
-    if (p.few_rows_ok && p.B == 1 && p.M >= 1 && p.M <= FR_ROWS && p.taps == 1 && p.shift[0] == 0 && !p.pre_lrelu &&
+    if (p.few_rows_ok && p.B == 1 && p.M >= 1 && p.M <= FR_ROWS * 1024 && p.taps == 1 && p.shift[0] == 0 && !p.pre_lrelu &&
         (p.act == ACT_NONE || p.act == ACT_RELU) && !p.aux_out && !p.addvec && !p.lens && !p.accumulate && !p.out_h &&
         p.x && p.w && p.out && p.N > 0) {
-        few_rows_linear_kernel<<<(p.N + FR_COLS - 1) / FR_COLS, FR_COLS * FR_SLICES, 0, s>>>(p);
+        few_rows_linear_kernel<<<dim3((p.N + FR_COLS - 1) / FR_COLS, (p.M + FR_ROWS - 1) / FR_ROWS), FR_COLS * FR_SLICES, 0, s>>>(p);
         CMTTS_CHECK_LAUNCH();
         return CMTTS_OK;
     }

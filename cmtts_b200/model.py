@@ -140,6 +140,81 @@ class CMTotalTTS:
             raise _lib.CmttsError("CMTotalTTS: call load_state_dict(...) and .to('cuda') first")
 
     # ---- encoder + variance adaptor --------------------------------------------------------
+    def dpen_head(self, texts: torch.Tensor, src_lens: torch.Tensor, spker_embeds: Optional[torch.Tensor],
+                  e_control=1.0, d_control=1.0) -> dict:
+        """Token-rate half of dpen: encoder + the token-rate variance adaptor, everything BEFORE the host learns the
+        output length.  Inputs must already be contiguous CUDA tensors (int64 / fp32).  No host sync, no host-side
+        branching on device data: this piece is what a CUDA graph can hold (cmtts_b200/synthesize.py)."""
+        s = self.spec
+        ops = torch.ops.cmtts_b200
+        B, T = texts.shape
+        bad_tok = ((texts < 0) | (texts >= s.vocab)).any() if texts.numel() else None   # nn.Embedding would raise IndexError
+        enc = ops.encoder_forward(self.handle, texts, src_lens)
+        out1, log_d, d_rounded, e_pred, e_idx, cumsum, mel_lens, spk, f0_stats = ops.variance_token(
+            self.handle, enc, src_lens, spker_embeds if s.multi_speaker else None, float(e_control), float(d_control))
+        m = mel_lens.max() if B > 0 else torch.zeros((), dtype=torch.int64, device=self.device)
+        return {"texts": texts, "src_lens": src_lens, "enc": enc, "out1": out1, "log_d": log_d, "d_rounded": d_rounded,
+                "e_pred": e_pred, "e_idx": e_idx, "cumsum": cumsum, "mel_lens": mel_lens,
+                "spk": spk if s.multi_speaker else None, "f0_stats": f0_stats, "max_len": m, "bad_tok": bad_tok}
+
+    def dpen_tail(self, head: dict, L: int, local_max: int, p_control=1.0, extra=()) -> dict:
+        """Frame-rate half of dpen for a known padded length L (length regulator, CWT pitch path, conditioner)."""
+        ops = torch.ops.cmtts_b200
+        dev = self.device
+        src_lens, mel_lens, f0_stats = head["src_lens"], head["mel_lens"], head["f0_stats"]
+        T = head["texts"].shape[1]
+        cond, mel2ph, cwt, f0_denorm, pitch_idx = ops.variance_frame(self.handle, head["out1"], head["cumsum"], mel_lens,
+                                                                      f0_stats, float(p_control), int(L))
+        ar_t = torch.arange(T, device=dev)
+        ar_l = torch.arange(local_max, device=dev)
+        return {
+            "cond": cond,
+            "p_targets": None,
+            "p_predictions": {"pitch_pred": None, "f0_denorm": f0_denorm, "cwt": cwt,
+                              "f0_mean": f0_stats[:, 0], "f0_std": f0_stats[:, 1]},
+            "e_predictions": head["e_pred"],
+            "log_d_predictions": head["log_d"],
+            "d_rounded": head["d_rounded"],
+            "mel_lens": mel_lens,
+            "mel_masks": ar_l[None, :] >= mel_lens[:, None],       # get_mask_from_lengths(mel_len)
+            "src_masks": ar_t[None, :] >= src_lens[:, None],
+            "speaker_emb": head["spk"],
+            "src_lens": src_lens,
+            # extras (not in the reference dict)
+            "enc": head["enc"], "mel2ph": mel2ph, "e_idx": head["e_idx"], "pitch_idx": pitch_idx, "l_max_extra": list(extra),
+        }
+
+    def read_lengths(self, head: dict, l_max_hook=None):
+        """THE host round trip of the path: the padded output length (and the bad-token flag) in one read.  The
+        multi-GPU hook reduces the device scalar BEFORE it is read (cmtts_b200/dist.py).  -> (local_max, extra)."""
+        m = head["max_len"]
+        if l_max_hook is not None:
+            m = l_max_hook(m)
+        bad_tok = head["bad_tok"]
+        if isinstance(m, torch.Tensor):
+            if bad_tok is not None:
+                m = torch.cat([m.reshape(-1).to(torch.int64), bad_tok.reshape(1).to(torch.int64)])
+            vals = m.reshape(-1).tolist()
+            if bad_tok is not None and vals.pop():
+                raise IndexError(f"token id outside [0, {self.spec.vocab}) (wrong symbol table?)")
+            return int(vals[0]), [int(v) for v in vals[1:]]
+        if bad_tok is not None and bool(bad_tok.item()):
+            raise IndexError(f"token id outside [0, {self.spec.vocab}) (wrong symbol table?)")
+        return int(m), []
+
+    def prepare_inputs(self, texts, src_lens, spker_embeds):
+        """Host-side checks the reference makes, then contiguous device tensors."""
+        s, dev = self.spec, self.device
+        if s.multi_speaker and spker_embeds is None:
+            raise AssertionError("Speaker embedding should not be None")  # cmtts.py:80
+        if not texts.is_cuda and texts.numel() and (int(texts.min()) < 0 or int(texts.max()) >= s.vocab):
+            # nn.Embedding raises IndexError here (modules.py:145); the gather kernel would read out of bounds
+            raise IndexError(f"token id outside [0, {s.vocab}) (wrong symbol table?)")
+        texts = texts.to(dev, torch.int64).contiguous()
+        src_lens = src_lens.to(dev, torch.int64).contiguous()
+        spk_in = None if spker_embeds is None or not s.multi_speaker else spker_embeds.to(dev, torch.float32).contiguous()
+        return texts, src_lens, spk_in
+
     def dpen(self, texts: torch.Tensor, src_lens: torch.Tensor, spker_embeds: Optional[torch.Tensor],
              max_mel_len: Optional[int] = None, p_control=1.0, e_control=1.0, d_control=1.0,
              l_max_hook=None) -> dict:
@@ -148,66 +223,15 @@ class CMTotalTTS:
         the frame-rate tensors (the reference syncs B*T times in LengthRegulator.expand).
         `l_max_hook(local_max) -> global_max` lets the multi-GPU driver all-reduce L_max."""
         self._ready()
-        lib, s, dev = self.lib, self.spec, self.device
-        if s.multi_speaker and spker_embeds is None:
-            raise AssertionError("Speaker embedding should not be None")  # cmtts.py:80
-        if not texts.is_cuda and texts.numel() and (int(texts.min()) < 0 or int(texts.max()) >= s.vocab):
-            # nn.Embedding raises IndexError here (modules.py:145); the gather kernel would read out of bounds
-            raise IndexError(f"token id outside [0, {s.vocab}) (wrong symbol table?)")
-        bad_tok = None
-        if texts.is_cuda and texts.numel():
-            bad_tok = ((texts < 0) | (texts >= s.vocab)).any()     # read back with mel_lens.max(), same host sync
-        texts = texts.to(dev, torch.int64).contiguous()
-        src_lens = src_lens.to(dev, torch.int64).contiguous()
-        B, T = texts.shape
-        spk_in = None if spker_embeds is None or not s.multi_speaker else \
-            spker_embeds.to(dev, torch.float32).contiguous()
-        ops = torch.ops.cmtts_b200
-        enc = ops.encoder_forward(self.handle, texts, src_lens)
-        out1, log_d, d_rounded, e_pred, e_idx, cumsum, mel_lens, spk, f0_stats = ops.variance_token(
-            self.handle, enc, src_lens, spk_in, float(e_control), float(d_control))
-        if not s.multi_speaker:
-            spk = None
-        # the one host round trip of the path: output length is data dependent.  The multi-GPU hook reduces the
-        # device scalar BEFORE it is read (cmtts_b200/dist.py), so there is still exactly one sync.
-        m = mel_lens.max() if B > 0 else torch.zeros((), dtype=torch.int64, device=dev)
-        extra = []
-        if l_max_hook is not None:
-            m = l_max_hook(m)
-        if isinstance(m, torch.Tensor):
-            if bad_tok is not None:
-                m = torch.cat([m.reshape(-1).to(torch.int64), bad_tok.reshape(1).to(torch.int64)])
-            vals = m.reshape(-1).tolist()
-            if bad_tok is not None and vals.pop():
-                raise IndexError(f"token id outside [0, {s.vocab}) (wrong symbol table?)")
-            local_max, extra = int(vals[0]), [int(v) for v in vals[1:]]
-        else:
-            local_max = int(m)
+        texts, src_lens, spk_in = self.prepare_inputs(texts, src_lens, spker_embeds)
+        head = self.dpen_head(texts, src_lens, spk_in, e_control, d_control)
+        local_max, extra = self.read_lengths(head, l_max_hook)
         if max_mel_len and int(max_mel_len) < local_max:
             # the reference's pad(output, max_len) fails here too (utils/tools.py:724-742: negative F.pad of a
             # longer row); truncating silently would leave mel_lens / mel_masks inconsistent with cond
             raise ValueError(f"dpen: max_mel_len={int(max_mel_len)} is shorter than the predicted length {local_max}")
         L = int(max_mel_len) if max_mel_len else local_max
-        cond, mel2ph, cwt, f0_denorm, pitch_idx = ops.variance_frame(self.handle, out1, cumsum, mel_lens, f0_stats,
-                                                                      float(p_control), L)
-        ar_t = torch.arange(T, device=dev)
-        ar_l = torch.arange(local_max, device=dev)
-        return {
-            "cond": cond,
-            "p_targets": None,
-            "p_predictions": {"pitch_pred": None, "f0_denorm": f0_denorm, "cwt": cwt,
-                              "f0_mean": f0_stats[:, 0], "f0_std": f0_stats[:, 1]},
-            "e_predictions": e_pred,
-            "log_d_predictions": log_d,
-            "d_rounded": d_rounded,
-            "mel_lens": mel_lens,
-            "mel_masks": ar_l[None, :] >= mel_lens[:, None],       # get_mask_from_lengths(mel_len)
-            "src_masks": ar_t[None, :] >= src_lens[:, None],
-            "speaker_emb": spk,
-            "src_lens": src_lens,
-            # extras (not in the reference dict)
-            "enc": enc, "mel2ph": mel2ph, "e_idx": e_idx, "pitch_idx": pitch_idx, "l_max_extra": extra,
-        }
+        return self.dpen_tail(head, L, local_max, p_control, extra)
 
     def packed_check_rows(self, n: int):
         if n + 2 > self.packed.pe_rows:

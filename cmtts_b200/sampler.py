@@ -63,15 +63,33 @@ def sampler_plan(T: int):
     raise ValueError(f"T must be 1, 2 or 4 (synthesize.py:106-146), got {T}")
 
 
+def evaluation_sigma(sampler: str, steps: int, sigma_min: float, sigma_max: float, rho: float) -> float:
+    """The sigma every distiller evaluation of one karras_sample_tts call runs at: sigmas[0] of the fp32
+    Karras grid for `onestep` (karras_diffusion.py:800-811), the Python-float t of ts = 0 for `multistep` (:829-854)."""
+    if sampler == "onestep":
+        return float(get_sigmas_karras(steps, sigma_min, sigma_max, rho, device="cpu")[0])
+    t_max_rho, t_min_rho = sigma_max ** (1 / rho), sigma_min ** (1 / rho)
+    return (t_max_rho + 0 / (steps - 1) * (t_min_rho - t_max_rho)) ** rho
+
+
+def rescaled_timesteps(batch: int, sigma_value: float) -> torch.Tensor:
+    """`1000 * 0.25 * log(sigma + 1e-44)` as the reference computes it: an fp32 (B,) HOST tensor through torch.log
+    (karras_diffusion.py:404)."""
+    sig = torch.full((batch,), sigma_value, dtype=torch.float64).to(torch.float32)
+    return 1000 * 0.25 * torch.log(sig + 1e-44)
+
+
 class _FusedDistiller:
     """denoiser(x_t, sigma) of karras_sample_tts (karras_diffusion.py:560-566) on the device path."""
 
-    def __init__(self, diffusion: KarrasDenoiser, model: CMTotalTTS, model_kwargs: dict, cond: Optional[dict]):
+    def __init__(self, diffusion: KarrasDenoiser, model: CMTotalTTS, model_kwargs: dict, cond: Optional[dict],
+                 prepared_steps=None):
         self.diffusion, self.model = diffusion, model
         self.kw = model_kwargs
         self.cond = cond
         self._steps_key = None
         self._steps = None
+        self._prepared = prepared_steps      # (ds_all, dsp_all) made ahead by the caller for this call's sigma
         self._cond16 = None          # (cond tensor, fp16 hi/lo pair): made once per sampler call
         self.model_outputs = None  # set to a list to capture F per evaluation (parity tests)
 
@@ -86,11 +104,10 @@ class _FusedDistiller:
         B, _, L, _ = x_t.shape
         cond = self.conditioner(L)
         c_skip, c_out, c_in, _ = self.diffusion.scalar_plan(sigma_value)
-        if self._steps_key != sigma_value:
-            # rescaled_t as the reference computes it: an fp32 (B,) tensor through torch.log
-            sig = torch.full((B,), sigma_value, dtype=torch.float64).to(torch.float32)
-            rescaled_t = 1000 * 0.25 * torch.log(sig + 1e-44)
-            self._steps = self.model.prepare_steps(rescaled_t, cond["speaker_emb"])
+        if self._prepared is not None:
+            self._steps = self._prepared
+        elif self._steps_key != sigma_value:
+            self._steps = self.model.prepare_steps(rescaled_timesteps(B, sigma_value), cond["speaker_emb"])
             self._steps_key = sigma_value
         c16 = None
         if self.model.precision == "tc":
@@ -108,10 +125,13 @@ class _FusedDistiller:
 def karras_sample_tts(diffusion, model, shape, steps=2, clip_denoised=False, progress=False, callback=None,
                       model_kwargs=None, device=None, sigma_min=0.002, sigma_max=80, rho=7.0,
                       sampler="onestep", s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0,
-                      generator=None, ts=None, T=None, cond_dict: Optional[dict] = None, trace: Optional[dict] = None):
+                      generator=None, ts=None, T=None, cond_dict: Optional[dict] = None, trace: Optional[dict] = None,
+                      prepared_steps=None):
     """Drop-in for karras_diffusion.py:480-577 (samplers 'onestep' and 'multistep', the two
     synthesize.py uses).  Extra keyword `cond_dict`: the pre-pass output of
-    duration_pitch_energy_net, reused instead of recomputing the conditioner."""
+    duration_pitch_energy_net, reused instead of recomputing the conditioner; `prepared_steps`: the output of
+    `model.prepare_steps` for this call's evaluation sigma (`evaluation_sigma`), made ahead by a caller that keeps host
+    to device copies out of the solver loop (the CUDA-graph path of cmtts_b200.synthesize.Pipeline)."""
     if generator is None:
         generator = get_generator("dummy")
     if not isinstance(model, CMTotalTTS):
@@ -123,7 +143,7 @@ def karras_sample_tts(diffusion, model, shape, steps=2, clip_denoised=False, pro
     sigmas = get_sigmas_karras(steps, sigma_min, sigma_max, rho, device="cpu")
     x_T = generator.randn(*shape, device=device) * sigma_max
     x_T = x_T.to(device=device, dtype=torch.float32)
-    distiller = _FusedDistiller(diffusion, model, model_kwargs, cond_dict)
+    distiller = _FusedDistiller(diffusion, model, model_kwargs, cond_dict, prepared_steps)
     if trace is not None:
         distiller.model_outputs = trace.setdefault("model_output", [])
     if sampler == "onestep":

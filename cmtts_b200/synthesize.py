@@ -119,14 +119,41 @@ class CMTotalTTSSynthesize:
         return out_put
 
 
+class _GraphSlot:
+    """One captured piece of the step: eager on its first call (warm-up: sizes the grow-only workspaces, sets kernel
+    attributes), captured into a CUDA graph on the second, replayed from then on."""
+
+    _gen = [0]
+
+    def __init__(self):
+        self.calls = 0
+        self.graph = None
+        self.static_in = None
+        self.out = None
+        self.failed = False
+        self.n_kernels = 0
+        _GraphSlot._gen[0] += 1
+        self.gen = _GraphSlot._gen[0]          # names this slot's static buffers (a tail graph reads its head's by address)
+
+
 class Pipeline:
     """Whole hot path on one GPU: host phoneme ids (+ speaker embeddings) -> mels -> int16 wavs.
 
     Mirrors what p_rtf_cm.py:174-226 strings together (encoder + variance adaptor, T solver steps,
-    HiFi-GAN on the whole padded batch, x32768 -> int16, crop to mel_len * hop)."""
+    HiFi-GAN on the whole padded batch, x32768 -> int16, crop to mel_len * hop).
+
+    graphs=True: the step is replayed from two CUDA graphs per shape — the token-rate part before the single host
+    read of the output length, keyed on (B, Tsrc, T), and everything after it (length regulator ... int16 wavs, ~130
+    launches at T = 1), keyed on (B, Tsrc, L, T) — instead of being enqueued launch by launch.  It pays when the step is
+    launch-latency bound (single utterances, small batches: SURVEY.md 7.6); a big batch is GPU-bound either way.  Shapes are
+    not bucketed: the reference's results depend on the exact padded length (SURVEY.md 7 "padding semantics"), so a new
+    (B, Tsrc, L) runs eagerly once, is captured on its second appearance, and the `graph_cache` most recent shapes are
+    kept.  Only the built-in device RNG can be captured: a call with a `generator` (noise replay) or a trace runs eagerly.
+    Results are fresh tensors either way (the graphs' static outputs are cloned)."""
 
     def __init__(self, spec: ModelSpec, acoustic_sd: Dict[str, torch.Tensor], hifigan_sd: Dict[str, torch.Tensor],
-                 device, distillation: bool = True, precision: str = "tc", tc_frontend: bool = True):
+                 device, distillation: bool = True, precision: str = "tc", tc_frontend: bool = True,
+                 graphs: bool = False, graph_cache: int = 16):
         self.spec = spec
         self.precision = precision
         self.device = torch.device(device)
@@ -135,6 +162,13 @@ class Pipeline:
         self.diffusion = KarrasDenoiser(sigma_data=spec.sigma_data, sigma_max=spec.sigma_max,
                                         sigma_min=spec.sigma_min, rho=spec.rho, distillation=distillation)
         self.vocoder = Generator(hspec=spec.hifigan, precision=precision).load_state_dict(hifigan_sd).to(self.device)
+        self.graphs = bool(graphs)
+        self.graph_cache = int(graph_cache)
+        self._head_slots: "Dict[tuple, _GraphSlot]" = {}
+        self._tail_slots: "Dict[tuple, _GraphSlot]" = {}
+        self._t_cache: Dict[tuple, torch.Tensor] = {}
+        self.graph_replays = 0
+        self.graph_kernel_launches = 0     # kernels of this library executed through graph replays (not counted by the C side)
 
     def acoustic(self, texts, src_lens, spker_embeds, T: int, generator=None, l_max_hook=None, trace=None):
         out = self.model.dpen(texts, src_lens, spker_embeds, None, l_max_hook=l_max_hook)
@@ -149,10 +183,102 @@ class Pipeline:
 
     def __call__(self, texts, src_lens, spker_embeds=None, T: int = 1, generator=None, want_float_wav: bool = False,
                  l_max_hook=None):
+        if self.graphs and generator is None and not want_float_wav and texts.shape[0] > 0:
+            return self._call_graphed(texts, src_lens, spker_embeds, T, l_max_hook)
         mel, out = self.acoustic(texts, src_lens, spker_embeds, T, generator, l_max_hook)
         wav, w16 = self.vocoder.run(mel, want_float=want_float_wav, want_int16=True,
                                     max_wav_value=self.spec.max_wav_value)
         return {"mel": mel, "mel_lens": out["mel_lens"], "wav_i16": w16, "wav": wav, "dpen": out}
+
+    # ---- CUDA-graph path ---------------------------------------------------------------------------------------------
+    def _timesteps(self, B: int, T: int) -> torch.Tensor:
+        """Device copy of the reference's `rescaled_t` for this T's evaluation sigma (uploaded once per (B, T))."""
+        from .sampler import evaluation_sigma, rescaled_timesteps
+        t = self._t_cache.get((B, T))
+        if t is None:
+            sampler, steps, _ = sampler_plan(T)
+            sigma = evaluation_sigma(sampler, steps, self.spec.sigma_min, self.spec.sigma_max, self.diffusion.rho)
+            t = self._t_cache[(B, T)] = rescaled_timesteps(B, sigma).to(self.device)
+        return t
+
+    def _head(self, texts, src_lens, spk, T):
+        head = self.model.dpen_head(texts, src_lens, spk)
+        steps = self.model.prepare_steps(self._timesteps(texts.shape[0], T), head["spk"])
+        return head, steps
+
+    def _tail(self, head, steps, L, local_max, extra, T):
+        out = self.model.dpen_tail(head, L, local_max, 1.0, extra)
+        B = head["texts"].shape[0]
+        sampler, nsteps, ts = sampler_plan(T)
+        kw = {"texts": head["texts"], "src_lens": head["src_lens"], "spker_embeds": None}
+        mel = karras_sample_tts(self.diffusion, self.model, (B, 1, L, self.spec.n_mels), steps=nsteps, model_kwargs=kw,
+                                device=self.device, sigma_min=self.spec.sigma_min, sigma_max=self.spec.sigma_max,
+                                sampler=sampler, ts=ts, cond_dict=out, prepared_steps=steps)
+        _, w16 = self.vocoder.run(mel, want_float=False, want_int16=True, max_wav_value=self.spec.max_wav_value)
+        return out, mel, w16
+
+    def _slot(self, table, key):
+        slot = table.pop(key, None) or _GraphSlot()
+        table[key] = slot                                  # most recently used last
+        while len(table) > self.graph_cache:
+            table.pop(next(iter(table)))
+        return slot
+
+    def _run_slot(self, slot, fn, inputs):
+        """inputs: tuple of tensors (or None) handed to fn; copied into the slot's static buffers when a graph exists."""
+        slot.calls += 1
+        if slot.graph is not None:
+            for dst, src in zip(slot.static_in, inputs):
+                if dst is not None and dst is not src:
+                    dst.copy_(src, non_blocking=True)
+            slot.graph.replay()
+            self.graph_replays += 1
+            self.graph_kernel_launches += slot.n_kernels
+            return slot.out
+        if slot.calls < 2 or slot.failed:
+            return fn(*inputs)                             # first sight of this shape: eager (also the warm-up)
+        static_in = tuple(None if t is None else t.clone() for t in inputs)
+        torch.cuda.current_stream(self.device).synchronize()
+        g = torch.cuda.CUDAGraph()
+        n0 = self.model.lib.cmtts_launch_count()
+        try:
+            with torch.cuda.graph(g):
+                out = fn(*static_in)
+        except Exception as e:                             # not capturable on this driver: say so once, stay eager
+            slot.failed = True
+            import warnings
+            warnings.warn(f"cmtts_b200: CUDA-graph capture failed ({type(e).__name__}: {e}); running this shape eagerly")
+            torch.cuda.synchronize(self.device)
+            return fn(*inputs)
+        slot.static_in, slot.out, slot.graph = static_in, out, g
+        slot.n_kernels = int(self.model.lib.cmtts_launch_count() - n0)     # kernel nodes of this library in the graph
+        g.replay()                                         # capture only records: run it once for this call's result
+        self.graph_replays += 1
+        self.graph_kernel_launches += slot.n_kernels
+        return slot.out
+
+    def _call_graphed(self, texts, src_lens, spker_embeds, T, l_max_hook):
+        m = self.model
+        m._ready()
+        with torch.cuda.device(self.device):
+            texts, src_lens, spk = m.prepare_inputs(texts, src_lens, spker_embeds)
+            B, Tsrc = texts.shape
+            hslot = self._slot(self._head_slots, (B, Tsrc, T))
+            head, steps = self._run_slot(hslot, lambda a, b, c: self._head(a, b, c, T), (texts, src_lens, spk))
+            local_max, extra = m.read_lengths(head, l_max_hook)          # the one host round trip
+            L = local_max
+            tslot = self._slot(self._tail_slots, (B, Tsrc, L, T, hslot.gen))
+            if hslot.graph is None:
+                # the tail graph would read the head's tensors by address: only valid once the head is static too
+                out, mel, w16 = self._tail(head, steps, L, local_max, extra, T)
+            else:
+                out, mel, w16 = self._run_slot(tslot, lambda: self._tail(head, steps, L, local_max, extra, T), ())
+            # results are fresh tensors: the graphs' static outputs are overwritten by the next call of the same shape
+            # (the `dpen` dict is handed out as is: in graph mode its entries alias those static buffers)
+            fresh = tslot.graph is not None
+            return {"mel": mel.clone() if fresh else mel,
+                    "mel_lens": out["mel_lens"].clone() if hslot.graph is not None else out["mel_lens"],
+                    "wav_i16": w16.clone() if fresh else w16, "wav": None, "dpen": out}
 
     def crop(self, w16_host: np.ndarray, mel_lens: Sequence[int]) -> List[np.ndarray]:
         """utils/model.py:201-203."""
