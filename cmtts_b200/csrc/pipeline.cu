@@ -652,6 +652,7 @@ extern "C" size_t cmtts_denoiser_tc_workspace_bytes(const cmtts_dims* d, int64_t
            align_up(R * C * 2) * 2 * (size_t)d->res_layers +    // g hi, lo of every layer
            align_up(R * C * 2) * 2 +                            // skip sum hi, lo
            align_up(R * 128 * 2) * 2 +                          // x_t hi, lo (K padded to 128)
+           align_up(R * C) * 2 +                                // y as an e4m3 pair (cross terms of the gate conv)
            align_up((size_t)B * d->res_layers * C * 4);         // per-(utterance, layer) constants
 }
 
@@ -693,11 +694,17 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
     __half* sk_lo = cv.take<__half>((size_t)R * C);
     __half* xt_hi = cv.take<__half>((size_t)R * 128);
     __half* xt_lo = cv.take<__half>((size_t)R * 128);
+    unsigned char* y8_hi = cv.take<unsigned char>((size_t)R * C);      // e4m3(y_hi), e4m3(y_lo * 2^11): umma_gate.cu
+    unsigned char* y8_lo = cv.take<unsigned char>((size_t)R * C);
     float* yc = cv.take<float>((size_t)B * NLY * C);
     const long long NL = (long long)NLY * C;
     const void* const* wx = w16 + NLY * 7;                    // {in_w hi, lo [C][128]; skip_w hi, lo [C][C]}
     const void* const* wf = wx + 4;                           // per layer l < NLY-1: {y_w hi, lo [C][2C+H]; y_b [C]}
     const void* const* wsk = wf + 3 * (NLY - 1);              // {skip-stack w hi, lo [NLY*C][C]; summed bias [C]}
+    const void* const* w8 = wsk + 3 + 3;                      // per layer {gate conv w as e4m3: hi8, lo8 [3][2C][C] bytes}
+    static int fp8_env = -1;                                  // CMTTS_GATE_FP8=0: fp16 cross terms (A/B and fallback)
+    if (fp8_env < 0) { const char* e = getenv("CMTTS_GATE_FP8"); fp8_env = e ? atoi(e) : 1; }
+    const bool fp8x = fp8_env != 0 && C == 256;
     const float r = (float)(1.0 / sqrt(2.0));
 
     // flattened single-"utterance" problem of R rows; guard rows are never written by the epilogues
@@ -707,6 +714,10 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
     // zero the y part of the guard rows (the conv's padding); everything else in guard rows is never consumed
     cudaMemset2DAsync(yc_hi + (size_t)L * YC, (size_t)Lp * YC * 2, 0, (size_t)C * 2, B, s);
     cudaMemset2DAsync(yc_lo + (size_t)L * YC, (size_t)Lp * YC * 2, 0, (size_t)C * 2, B, s);
+    if (fp8x) {
+        cudaMemset2DAsync(y8_hi + (size_t)L * C, (size_t)Lp * C, 0, (size_t)C, B, s);
+        cudaMemset2DAsync(y8_lo + (size_t)L * C, (size_t)Lp * C, 0, (size_t)C, B, s);
+    }
     CMTTS_TRY(launch_pack_rows_f16((const __half*)cond_hi, yc_hi, B, L, Lp, H, YC, C, s));
     CMTTS_TRY(launch_pack_rows_f16((const __half*)cond_lo, yc_lo, B, L, Lp, H, YC, C, s));
     // input projection: relu(W (c_in x_t) + b).  c_in * x_t is formed in fp32 first, like the reference
@@ -732,6 +743,7 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
         u.addvec = dsp_all; u.addvec_bstride = NL;
         u.x_f32 = x; u.x_bstride = (long long)R * C; u.x_ld = C;
         u.out_h = yc_hi; u.out_lo = yc_lo; u.out_bstride = (long long)R * YC; u.out_ld = YC;
+        if (fp8x) { u.out8_hi = y8_hi; u.out8_lo = y8_lo; u.out8_ld = C; }
         CMTTS_TRY(launch_umma_conv(u, s));
     }
     for (int l = 0; l < NLY; ++l) {
@@ -748,6 +760,10 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
         u.w_hi = (const __half*)wl[2]; u.w_lo = (const __half*)wl[3];
         u.bias = F(w, o + 3);
         u.out_h = gl_hi; u.out_lo = gl_lo; u.out_bstride = (long long)R * C; u.out_ld = C;
+        if (fp8x) {
+            u.a8_hi = y8_hi; u.a8_lo = y8_lo;
+            u.w8_hi = (const unsigned char*)w8[2 * l]; u.w8_lo = (const unsigned char*)w8[2 * l + 1];
+        }
         CMTTS_TRY(launch_umma_conv(u, s));
         if (l + 1 < NLY) {
             // y_{l+1}, in place: K = C (g_l) + own 128 channels of y_l + H (cond); see the recurrence above
@@ -762,6 +778,7 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
             u.bias = (const float*)wf[3 * l + 2];
             u.addvec = yc + (long long)l * C; u.addvec_bstride = (long long)(NLY - 1) * C;
             u.out_h = yc_hi; u.out_lo = yc_lo; u.out_bstride = (long long)R * YC; u.out_ld = YC;
+            if (fp8x) { u.out8_hi = y8_hi; u.out8_lo = y8_lo; u.out8_ld = C; }
             CMTTS_TRY(launch_umma_conv(u, s));
         }
     }

@@ -3,6 +3,7 @@
 #pragma once
 #include "umma_conv.cuh"
 #include <cuda.h>
+#include <cuda_fp8.h>
 #include <cudaTypedefs.h>
 #include <math.h>
 #include <stdlib.h>
@@ -78,6 +79,16 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// kind::f8f6f4 with e4m3 x e4m3 -> f32: the instruction descriptor has the same bit pattern as f16 x f16 -> f32 (format
+// codes 0), K = 32 per instruction (32 bytes of a K-major row: the descriptor start address advances by 2 like fp16's K = 16)
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
@@ -215,6 +226,25 @@ __device__ __forceinline__ void store16_hilo(__half* hi, __half* lo, const float
     store16h(hi, h);
     store16h(lo, l);
 }
+// e4m3 pair of 16 values for the fp8 cross terms: hi8 = e4m3(fp16(v)), lo8 = e4m3((v - fp16(v)) * 2^11)   (16 bytes each)
+__device__ __forceinline__ void store16_f8pair(unsigned char* hi8, unsigned char* lo8, const float (&f)[16]) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t hw = 0, lw = 0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float a = f[4 * i + 2 * j], b = f[4 * i + 2 * j + 1];
+            const float ah = __half2float(__float2half_rn(a)), bh = __half2float(__float2half_rn(b));
+            const uint32_t ph = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(ah, bh), __NV_SATFINITE, __NV_E4M3);
+            const uint32_t pl = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((a - ah) * 2048.f, (b - bh) * 2048.f), __NV_SATFINITE, __NV_E4M3);
+            hw |= ph << (16 * j); lw |= pl << (16 * j);
+        }
+        h[i] = hw; l[i] = lw;
+    }
+    *reinterpret_cast<uint4*>(hi8) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo8) = make_uint4(l[0], l[1], l[2], l[3]);
+}
 __device__ __forceinline__ void load16f(const float* p, float (&f)[16]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -258,6 +288,29 @@ static inline bool make_act_map(CUtensorMap* m, const __half* base, int C, int L
     const CUtensorMapSwizzle sw = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// byte tensors (e4m3 operands) [B][L][C]: box {128 bytes, box_rows, 1}, 128B swizzle
+static inline bool make_act_map8(CUtensorMap* m, const unsigned char* base, int C, int L, int B, int ld, long long bstride, int box_rows) {
+    auto enc = get_encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)bstride};
+    cuuint32_t box[3] = {128u, (cuuint32_t)box_rows, 1u};
+    cuuint32_t es[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<unsigned char*>(base), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static inline bool make_w_map8(CUtensorMap* m, const unsigned char* base, int Cin, int rows, int BN) {
+    auto enc = get_encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Cin};
+    cuuint32_t box[2] = {128u, (cuuint32_t)BN};
+    cuuint32_t es[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<unsigned char*>(base), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // weights [taps*N][Cin] fp16: box {BK, BN}

@@ -423,11 +423,13 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             for (int j = 0; j < 16; ++j) v[j] += av[j] + x[j];
                             const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
                             store16_hilo(p.out_h + o, p.out_lo + o, v);
+                            if (p.out8_hi) store16_f8pair(p.out8_hi + (long long)t * p.out8_ld + n, p.out8_lo + (long long)t * p.out8_ld + n, v);
                         } else if (EPI == UEPI_DN_OUTY) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] += av[j];
                             const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
                             store16_hilo(p.out_h + o, p.out_lo + o, v);
+                            if (p.out8_hi) store16_f8pair(p.out8_hi + (long long)t * p.out8_ld + n, p.out8_lo + (long long)t * p.out8_ld + n, v);
                         } else {  // UEPI_DN_OUT
                             const int half_n = p.N >> 1;
                             if (n < half_n) {

@@ -56,7 +56,12 @@ struct UmmaConvParams {
     // non-zero weights in taps [0, taps-1), columns >= tap_split_n only in taps [1, taps) -> the all-zero tap of a tile
     // is skipped (identical results: it would add exact zeros).  0 = off.
     int tap_split_n;
-    int dbg;              // experiment bits (CMTTS_UMMA_DBG): 1 = descriptor base_offset, 2 = disable the halo kernel, 128 = disable the gate kernel
+    // fp8 (e4m3) operand copies for the CROSS TERMS of the denoiser's gate conv (umma_gate.cu, umma_gate8_kernel):
+    // activations [M][Cin] bytes and weights [taps*N][Cin] bytes, each as (e4m3(hi), e4m3(lo * 2^11)).  NULL = fp16 cross terms.
+    const unsigned char* a8_hi; const unsigned char* a8_lo; const unsigned char* w8_hi; const unsigned char* w8_lo;
+    // UEPI_DN_COND / UEPI_DN_OUTY: also write that e4m3 pair of the output rows (row pitch out8_ld bytes, flattened rows)
+    unsigned char* out8_hi; unsigned char* out8_lo; int out8_ld;
+    int dbg;              // experiment bits (CMTTS_UMMA_DBG): 1 = descriptor base_offset, 2 = disable the halo kernel, 128 = disable the gate kernel, 256 = fp16 (not fp8) cross terms in the gate kernel
 };
 
 static inline UmmaConvParams umma_params_default() {

@@ -277,6 +277,353 @@ umma_gate_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
 }
 
+// ==========================================================================================================================
+// fp8 CROSS TERMS.  The hi/lo scheme spends two of its three MMAs on A_hi W_lo + A_lo W_hi, which is 2^-11 of the product:
+// that part does not need 11-bit operands.  Here it runs as kind::f8f6f4 on e4m3 copies of the operands (hi8 = e4m3(hi),
+// lo8 = e4m3(lo * 2^11); written next to the fp16 pair by the epilogues that produce y, and packed once for the weights):
+// K = 32 per instruction at twice the fp16 rate, i.e. 12 -> 8 MMA issue slots per 64 channels.  e4m3's 2^-4 relative
+// rounding on a 2^-11 term leaves ~2^-15 of the product (fp16 alone: 2^-11): measured on the whole residual stack the mel
+// error is 1.4e-4 (fp16 cross terms 4e-6, none 3.6e-3; contract 1e-3).
+//
+// The main products and the cross terms now read DIFFERENT tiles, so each issuing warp has its own two rings and its own
+// two producer warps: main  — A_hi16 halo tile per 64-channel block (2 stages) + W_hi16 blocks (3 stages);
+//                     cross — {A_hi8, A_lo8} halo tiles per 128-channel block (128-byte rows again, 2 stages)
+//                             + {W_hi8, W_lo8} blocks per (128-channel block, tap) (2 stages).
+// Every ring depth divides its per-tile use count, so ring indices and phases stay compile-time (see issue_tiles).
+// Roles (448 threads): warp 0 A16 producer, 1 main issuer, 2 TMEM allocator + W16 producer, 3 cross issuer,
+// 4-11 epilogue, 12 A8 producer, 13 W8 producer.
+constexpr int G8_A16_STAGES = 2, G8_W16_STAGES = 3, G8_A8_STAGES = 2, G8_W8_STAGES = 2;
+constexpr int G8_THREADS = 448;
+constexpr int G8_W8_STAGE = 2 * G_B_BYTES;            // hi8 + lo8 block: 128 rows x 128 bytes each
+constexpr float G8_LO_SCALE_INV = 1.0f / 2048.0f;     // weights.py: F8_LO_SCALE (both cross terms carry one factor 2^11)
+
+template <int TAPS>
+__global__ void __launch_bounds__(G8_THREADS, 1)
+umma_gate8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant__ CUtensorMap tmA8h,
+                  const __grid_constant__ CUtensorMap tmA8l, const __grid_constant__ CUtensorMap tmW16,
+                  const __grid_constant__ CUtensorMap tmW8h, const __grid_constant__ CUtensorMap tmW8l,
+                  const UmmaConvParams p, const int rows_alloc, const int box_rows) {
+    constexpr int BM = G_BM, BN = G_BN;
+    constexpr int CB = 4, CB8 = 2;                    // 256 channels: four 64-channel fp16 blocks / two 128-channel e4m3 blocks
+    constexpr int ACC_COLS = 2 * BN;                  // main | cross-term accumulator
+    constexpr int TMEM_COLS = 2 * ACC_COLS;           // double-buffered: 512 columns
+    static_assert(CB % G8_A16_STAGES == 0 && (CB * TAPS) % G8_W16_STAGES == 0 && CB8 % G8_A8_STAGES == 0 &&
+                  (CB8 * TAPS) % G8_W8_STAGES == 0, "every tile must start at ring stage 0");
+
+    const int a_half = rows_alloc * G_ROW_BYTES;      // one halo tile (128-byte rows), 1024-byte multiple
+    const int a8_stage = 2 * a_half;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smA16 = smem;
+    uint8_t* smW16 = smA16 + G8_A16_STAGES * a_half;
+    uint8_t* smA8 = smW16 + G8_W16_STAGES * G_B_BYTES;
+    uint8_t* smW8 = smA8 + G8_A8_STAGES * a8_stage;
+    uint64_t* a16_full = reinterpret_cast<uint64_t*>(smW8 + G8_W8_STAGES * G8_W8_STAGE);
+    uint64_t* a16_empty = a16_full + G8_A16_STAGES;
+    uint64_t* w16_full = a16_empty + G8_A16_STAGES;
+    uint64_t* w16_empty = w16_full + G8_W16_STAGES;
+    uint64_t* a8_full = w16_empty + G8_W16_STAGES;
+    uint64_t* a8_empty = a8_full + G8_A8_STAGES;
+    uint64_t* w8_full = a8_empty + G8_A8_STAGES;
+    uint64_t* w8_empty = w8_full + G8_W8_STAGES;
+    uint64_t* tfull = w8_empty + G8_W8_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int m_tiles = (p.M + BM - 1) / BM;
+    const int n_tiles = p.N / BN;
+    const int tiles = p.B * m_tiles * n_tiles;        // n-tile fastest
+    const int shift0 = p.shift[0];
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < G8_A16_STAGES; ++i) { mbar_init(&a16_full[i], 1); mbar_init(&a16_empty[i], 1); }
+        for (int i = 0; i < G8_W16_STAGES; ++i) { mbar_init(&w16_full[i], 1); mbar_init(&w16_empty[i], 1); }
+        for (int i = 0; i < G8_A8_STAGES; ++i) { mbar_init(&a8_full[i], 1); mbar_init(&a8_empty[i], 1); }
+        for (int i = 0; i < G8_W8_STAGES; ++i) { mbar_init(&w8_full[i], 1); mbar_init(&w8_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 2); mbar_init(&tempty[i], 8); }     // both issuers commit tfull
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    if (warp != 2 && warp != 13) pdl_wait();          // the weight producers read constants only
+
+    constexpr uint32_t DESC_HI = (uint32_t)((8 * G_ROW_BYTES) >> 4) | (1u << 14) | (2u << 29);   // SBO | version | SWIZZLE_128B
+    constexpr uint64_t HI = (uint64_t)DESC_HI << 32;
+
+    if (warp == 0) {
+        // ================= A16 producer: A_hi16 halo tile per 64-channel block =================
+        prefetch_tmap(&tmA16);
+        int stage = 0; uint32_t phase = 0;
+        const uint32_t bytes = (uint32_t)(box_rows * G_ROW_BYTES);
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int rest = tile / n_tiles;
+            const int mt = rest % m_tiles, b = rest / m_tiles;
+#pragma unroll 1
+            for (int cb = 0; cb < CB; ++cb) {
+                mbar_wait(&a16_empty[stage], phase ^ 1);
+                mbar_expect_tx_elect(&a16_full[stage], bytes);
+                tma_load_3d_elect(smA16 + stage * a_half, &tmA16, &a16_full[stage], cb * G_BK, mt * BM + shift0, b);
+                if (++stage == G8_A16_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 12) {
+        // ================= A8 producer: {A_hi8, A_lo8} halo tiles per 128-channel block =================
+        prefetch_tmap(&tmA8h); prefetch_tmap(&tmA8l);
+        int stage = 0; uint32_t phase = 0;
+        const uint32_t bytes = (uint32_t)(2 * box_rows * G_ROW_BYTES);
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int rest = tile / n_tiles;
+            const int mt = rest % m_tiles, b = rest / m_tiles;
+#pragma unroll 1
+            for (int cb = 0; cb < CB8; ++cb) {
+                mbar_wait(&a8_empty[stage], phase ^ 1);
+                mbar_expect_tx_elect(&a8_full[stage], bytes);
+                uint8_t* sa = smA8 + stage * a8_stage;
+                tma_load_3d_elect(sa, &tmA8h, &a8_full[stage], cb * 128, mt * BM + shift0, b);
+                tma_load_3d_elect(sa + a_half, &tmA8l, &a8_full[stage], cb * 128, mt * BM + shift0, b);
+                if (++stage == G8_A8_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 2) {
+        // ================= W16 producer: W_hi16 blocks per (64-channel block, tap) =================
+        prefetch_tmap(&tmW16);
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int nt = tile % n_tiles;
+#pragma unroll 1
+            for (int cb = 0; cb < CB; ++cb) {
+#pragma unroll 1
+                for (int tap = 0; tap < TAPS; ++tap) {
+                    mbar_wait(&w16_empty[stage], phase ^ 1);
+                    mbar_expect_tx_elect(&w16_full[stage], G_B_BYTES);
+                    tma_load_2d_elect(smW16 + stage * G_B_BYTES, &tmW16, &w16_full[stage], cb * G_BK, tap * p.N + nt * BN);
+                    if (++stage == G8_W16_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 13) {
+        // ================= W8 producer: {W_hi8, W_lo8} blocks per (128-channel block, tap) =================
+        prefetch_tmap(&tmW8h); prefetch_tmap(&tmW8l);
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int nt = tile % n_tiles;
+#pragma unroll 1
+            for (int cb = 0; cb < CB8; ++cb) {
+#pragma unroll 1
+                for (int tap = 0; tap < TAPS; ++tap) {
+                    mbar_wait(&w8_empty[stage], phase ^ 1);
+                    mbar_expect_tx_elect(&w8_full[stage], G8_W8_STAGE);
+                    uint8_t* sb = smW8 + stage * G8_W8_STAGE;
+                    tma_load_2d_elect(sb, &tmW8h, &w8_full[stage], cb * 128, tap * p.N + nt * BN);
+                    tma_load_2d_elect(sb + G_B_BYTES, &tmW8l, &w8_full[stage], cb * 128, tap * p.N + nt * BN);
+                    if (++stage == G8_W8_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= main issuer: A_hi16 W_hi16 -> accumulator 0 =================
+        constexpr int A_USES = CB / G8_A16_STAGES, B_USES = CB * TAPS / G8_W16_STAGES;
+        const uint32_t tmem_u = make_uniform(tmem_base);
+        const uint32_t idesc = make_idesc(BM, BN);
+        const uint32_t tap_step = make_uniform((uint32_t)(((TAPS > 1 ? p.shift[1] - p.shift[0] : 0) * G_ROW_BYTES) >> 4));
+        const uint32_t a_half16 = make_uniform((uint32_t)(a_half >> 4));
+        const uint32_t a_base = make_uniform(((smem_u32(smA16) >> 4) & 0x3FFF) | (1u << 16));
+        const uint32_t b_base = make_uniform(((smem_u32(smW16) >> 4) & 0x3FFF) | (1u << 16));
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+            const uint32_t abuf = it & 1u, tphase = (it >> 1) & 1u;
+            mbar_wait(&tempty[abuf], tphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = make_uniform(tmem_u + abuf * (uint32_t)ACC_COLS);
+#pragma unroll
+            for (int cb = 0; cb < CB; ++cb) {
+                const int as = cb % G8_A16_STAGES;
+                mbar_wait(&a16_full[as], (uint32_t)((it * A_USES + cb / G8_A16_STAGES) & 1u));
+                tc_fence_after();
+                const uint32_t a0 = a_base + (uint32_t)as * a_half16;
+#pragma unroll
+                for (int tap = 0; tap < TAPS; ++tap) {
+                    const int idx = cb * TAPS + tap;
+                    const int bs = idx % G8_W16_STAGES;
+                    mbar_wait(&w16_full[bs], (uint32_t)((it * B_USES + idx / G8_W16_STAGES) & 1u));
+                    tc_fence_after();
+                    const uint32_t ah = a0 + (uint32_t)tap * tap_step;
+                    const uint32_t wh = b_base + (uint32_t)((bs * G_B_BYTES) >> 4);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < G_BK / 16; ++k)
+                            umma_f16(d_tmem, HI | (ah + 2 * k), HI | (wh + 2 * k), idesc, (cb | tap | k) ? 1u : 0u);
+                        umma_commit(&w16_empty[bs]);
+                        if (tap == TAPS - 1) umma_commit(&a16_empty[as]);
+                        if (tap == TAPS - 1 && cb == CB - 1) umma_commit(&tfull[abuf]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ================= cross issuer (e4m3): A_hi8 W_lo8 + A_lo8 W_hi8 -> accumulator 1 =================
+        constexpr int A_USES = CB8 / G8_A8_STAGES, B_USES = CB8 * TAPS / G8_W8_STAGES;
+        const uint32_t tmem_u = make_uniform(tmem_base);
+        const uint32_t idesc = make_idesc(BM, BN);        // e4m3 x e4m3 -> f32: same bits as f16 x f16 -> f32
+        const uint32_t tap_step = make_uniform((uint32_t)(((TAPS > 1 ? p.shift[1] - p.shift[0] : 0) * G_ROW_BYTES) >> 4));
+        const uint32_t a_half16 = make_uniform((uint32_t)(a_half >> 4));
+        const uint32_t a_base = make_uniform(((smem_u32(smA8) >> 4) & 0x3FFF) | (1u << 16));
+        const uint32_t b_base = make_uniform(((smem_u32(smW8) >> 4) & 0x3FFF) | (1u << 16));
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+            const uint32_t abuf = it & 1u, tphase = (it >> 1) & 1u;
+            mbar_wait(&tempty[abuf], tphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = make_uniform(tmem_u + abuf * (uint32_t)ACC_COLS + (uint32_t)BN);
+#pragma unroll
+            for (int cb = 0; cb < CB8; ++cb) {
+                const int as = cb % G8_A8_STAGES;
+                mbar_wait(&a8_full[as], (uint32_t)((it * A_USES + cb / G8_A8_STAGES) & 1u));
+                tc_fence_after();
+                const uint32_t a0 = a_base + (uint32_t)as * 2u * a_half16;
+#pragma unroll
+                for (int tap = 0; tap < TAPS; ++tap) {
+                    const int idx = cb * TAPS + tap;
+                    const int bs = idx % G8_W8_STAGES;
+                    mbar_wait(&w8_full[bs], (uint32_t)((it * B_USES + idx / G8_W8_STAGES) & 1u));
+                    tc_fence_after();
+                    const uint32_t ah = a0 + (uint32_t)tap * tap_step, al = ah + a_half16;
+                    const uint32_t wh = b_base + (uint32_t)((bs * G8_W8_STAGE) >> 4), wl = wh + (uint32_t)(G_B_BYTES >> 4);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < 128 / 32; ++k)                                   // A_hi8 W_lo8
+                            umma_f8(d_tmem, HI | (ah + 2 * k), HI | (wl + 2 * k), idesc, (cb | tap | k) ? 1u : 0u);
+#pragma unroll
+                        for (int k = 0; k < 128 / 32; ++k)                                   // A_lo8 W_hi8
+                            umma_f8(d_tmem, HI | (al + 2 * k), HI | (wh + 2 * k), idesc, 1u);
+                        umma_commit(&w8_empty[bs]);
+                        if (tap == TAPS - 1) umma_commit(&a8_empty[as]);
+                        if (tap == TAPS - 1 && cb == CB8 - 1) umma_commit(&tfull[abuf]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ================= epilogue (UEPI_DN_GATE), as umma_gate_kernel's, cross accumulator scaled by 2^-11 =================
+        constexpr int GH = BN / 4;
+        const int q = warp & 3;
+        const int h = (warp - 4) >> 2;
+        const int row = q * 32 + lane;
+        int abuf = 0; uint32_t tphase = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int nt = tile % n_tiles, rest = tile / n_tiles;
+            const int mt = rest % m_tiles, b = rest / m_tiles;
+            const int t = mt * BM + row;
+            bool valid = t < p.M;
+            if (p.rows_per_utt > 0) {
+                const int ub = t / p.rows_per_utt;
+                valid = valid && (t - ub * p.rows_per_utt) < p.rows_per_utt - 1;
+            }
+            float bg[GH], bf[GH];
+            {
+                const float4* pg = reinterpret_cast<const float4*>(p.bias + nt * BN + h * GH);
+                const float4* pf = reinterpret_cast<const float4*>(p.bias + nt * BN + BN / 2 + h * GH);
+#pragma unroll
+                for (int i = 0; i < GH / 4; ++i) {
+                    const float4 x = __ldg(pg + i), y = __ldg(pf + i);
+                    bg[4 * i] = x.x; bg[4 * i + 1] = x.y; bg[4 * i + 2] = x.z; bg[4 * i + 3] = x.w;
+                    bf[4 * i] = y.x; bf[4 * i + 1] = y.y; bf[4 * i + 2] = y.z; bf[4 * i + 3] = y.w;
+                }
+            }
+            mbar_wait(&tfull[abuf], tphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t)(abuf * ACC_COLS) + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+            for (int c = 0; c < GH / 16; ++c) {
+                uint32_t rg[16], rf[16], rg2[16], rf2[16];
+                const int g0 = h * GH + c * 16;
+                tmem_ld16(taddr + g0, rg);
+                tmem_ld16(taddr + BN / 2 + g0, rf);
+                tmem_ld16(taddr + BN + g0, rg2);
+                tmem_ld16(taddr + BN + BN / 2 + g0, rf2);
+                tmem_ld_wait();
+                if (valid) {
+                    const int ch = nt * (BN / 2) + g0;
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float g = fmaf(fmaf(__uint_as_float(rg2[j]), G8_LO_SCALE_INV, __uint_as_float(rg[j])), p.alpha, bg[c * 16 + j]);
+                        const float f = fmaf(fmaf(__uint_as_float(rf2[j]), G8_LO_SCALE_INV, __uint_as_float(rf[j])), p.alpha, bf[c * 16 + j]);
+                        v[j] = gate_fast(g, f);
+                    }
+                    const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + ch;
+                    store16_hilo(p.out_h + o, p.out_lo + o, v);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[abuf]);
+            abuf ^= 1; if (abuf == 0) tphase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+template <int TAPS>
+int launch_gate8_cfg(const UmmaConvParams& p, cudaStream_t s) {
+    const int span = p.shift[p.taps - 1] - p.shift[0];
+    const int box_rows = 128 + span;
+    const int rows_alloc = (box_rows + 7) / 8 * 8;
+    const size_t a_half = (size_t)rows_alloc * G_ROW_BYTES;
+    const size_t smem = G8_A16_STAGES * a_half + (size_t)G8_W16_STAGES * G_B_BYTES + G8_A8_STAGES * 2 * a_half +
+                        (size_t)G8_W8_STAGES * G8_W8_STAGE +
+                        (2 * (G8_A16_STAGES + G8_W16_STAGES + G8_A8_STAGES + G8_W8_STAGES) + 4) * 8 + 16 + 1024;
+    if (smem > 227 * 1024 || box_rows > 256) return CMTTS_ERR_UNSUPPORTED;
+    auto kern = umma_gate8_kernel<TAPS>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+            cmtts_set_error("umma_gate8: cannot set dynamic shared memory size", __FILE__, __LINE__);
+            return CMTTS_ERR_CUDA;
+        }
+        attr_done = true;
+    }
+    CUtensorMap a16, a8h, a8l, w16, w8h, w8l;
+    if (!make_act_map(&a16, p.a_hi, p.Cin, p.Lin, p.B, p.a_ld, p.a_bstride, G_BK, box_rows) ||
+        !make_act_map8(&a8h, p.a8_hi, p.Cin, p.Lin, p.B, p.Cin, (long long)p.Lin * p.Cin, box_rows) ||
+        !make_act_map8(&a8l, p.a8_lo, p.Cin, p.Lin, p.B, p.Cin, (long long)p.Lin * p.Cin, box_rows) ||
+        !make_w_map(&w16, p.w_hi, p.Cin, p.taps * p.N, G_BK, G_BN) ||
+        !make_w_map8(&w8h, p.w8_hi, p.Cin, p.taps * p.N, G_BN) || !make_w_map8(&w8l, p.w8_lo, p.Cin, p.taps * p.N, G_BN)) {
+        cmtts_set_error("umma_gate8: cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
+        return CMTTS_ERR_CUDA;
+    }
+    const int tiles = p.B * ((p.M + 127) / 128) * (p.N / G_BN);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    if (g_cmtts_prof_on) {
+        const double rows = (double)p.B * p.M;
+        char lbl[96];
+        snprintf(lbl, sizeof(lbl), "umma_gate8<%d> t%d %d->%d (hi/lo, e4m3 cross terms)", p.taps, p.taps, p.Cin, p.N);
+        cmtts_prof_note(lbl, 2.0 * rows * p.N * p.taps * p.Cin,
+                        rows * p.Cin * 4.0 + rows * (p.N / 2) * 4.0 + (double)p.taps * p.N * p.Cin * 4.0);
+    }
+    launch_pdl(kern, grid, G8_THREADS, smem, s, a16, a8h, a8l, w16, w8h, w8l, p, rows_alloc, box_rows);
+    CMTTS_CHECK_LAUNCH();
+    return CMTTS_OK;
+}
+
+
 template <int TAPS, int CB>
 int launch_gate_cfg(const UmmaConvParams& p, cudaStream_t s) {
     const int span = p.shift[p.taps - 1] - p.shift[0];
@@ -326,5 +673,7 @@ int launch_umma_gate(const UmmaConvParams& p, cudaStream_t s) {
     if (p.shift[1] - p.shift[0] != p.shift[2] - p.shift[1] || p.shift[1] <= p.shift[0]) return CMTTS_ERR_UNSUPPORTED;
     if (((uintptr_t)p.bias % 16) != 0) return CMTTS_ERR_UNSUPPORTED;      // float4 bias loads
     if (p.B == 0 || p.M == 0) return CMTTS_OK;
+    // e4m3 cross terms when the caller supplies the fp8 operand copies (CMTTS_UMMA_DBG bit 256 keeps them in fp16)
+    if (p.a8_hi && p.a8_lo && p.w8_hi && p.w8_lo && !(p.dbg & 256) && p.B == 1 && p.a_bstride >= 0) return launch_gate8_cfg<3>(p, s);
     return launch_gate_cfg<3, 4>(p, s);
 }

@@ -210,7 +210,10 @@ int cmtts_f32_to_f16(const float* x, void* hi, void* lo, int64_t rows, int64_t C
  * l < res_layers-1 the y-recurrence operands {y_w hi, lo [C][2C+H]; y_b fp32 [C]} with
  * y_w = [r Wo_l[:C] | r I | Wc_{l+1} - r Wc_l], r = 1/sqrt(2), then the stacked skip projection
  * {skip_stack_w hi, lo [res_layers*C][C] (row l*C+n = Wo_l[C+n]); summed bias fp32 [C]}, then the output
- * projection {out_w hi, lo [128][C] (rows >= n_mels zero); out_b fp32 [128]} (cmtts_b200/weights.py);
+ * projection {out_w hi, lo [128][C] (rows >= n_mels zero); out_b fp32 [128]}, then per layer the k3 conv's weights
+ * once more as an e4m3 pair {hi8 = e4m3(hi), lo8 = e4m3(lo * 2^11), bytes [3*2C][C]}: the operands of the gate conv's
+ * cross terms A_hi W_lo + A_lo W_hi, which run as kind::f8f6f4 MMAs (csrc/umma_gate.cu; CMTTS_GATE_FP8=0 keeps them
+ * in fp16) (cmtts_b200/weights.py);
  * cond_hi/cond_lo are the fp16 split of the conditioner (cmtts_f32_to_f16). */
 size_t cmtts_denoiser_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t L);
 int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const* w, const void* const* w16,

@@ -4,6 +4,10 @@ set -u
 TAG=${1:-r2_p3}
 OUT=gpurun_out
 mkdir -p $OUT
+CMTTS_GATE_FP8=0 timeout 1200 python -m pytest tests -m gpu -q -s > $OUT/gpu_tests_${TAG}_fp16x.log 2>&1
+tail -12 $OUT/gpu_tests_${TAG}_fp16x.log
+grep -E "mel max-abs|vocoder \[|RNG stream|Warning|warn" $OUT/gpu_tests_${TAG}_fp16x.log | head -20
+echo "=== e4m3 cross terms in the gate conv (default) ==="
 timeout 1200 python -m pytest tests -m gpu -q -s > $OUT/gpu_tests_$TAG.log 2>&1
 tail -12 $OUT/gpu_tests_$TAG.log
 grep -E "mel max-abs|vocoder \[|RNG stream|Warning|warn" $OUT/gpu_tests_$TAG.log | head -20
@@ -16,6 +20,7 @@ run C3_eager --config C3 --graphs off
 run C3T4_graphs --config C3 --T 4 --graphs on
 run C2T1_graphs --config C2 --T 1 --graphs on
 run C2T1_eager --config C2 --T 1 --graphs off
+CMTTS_GATE_FP8=0 timeout 400 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $OUT/bench_${TAG}_C2_T4_fp16x.json 2> $OUT/bench_${TAG}_C2_T4_fp16x.err
 timeout 400 python bench.py --steps 20 --warmup 5 > $OUT/bench_${TAG}_C2_T4.json 2> $OUT/bench_${TAG}_C2_T4.err
 tail -c 300 $OUT/bench_${TAG}_C2_T4.err
 python - <<PY
