@@ -233,7 +233,11 @@ def roofline_blocks(rows, total_us, peaks, step_ms, total_flops, stage_ms, stage
             ach = r["flops"] / sec / 1e12
             b = {"kernel": r["kernel"], "bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"],
                  "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"]}
-            if "hi/lo" in r["kernel"] or ",1,e" in r["kernel"]:
+            if "e4m3" in r["kernel"]:
+                b["mma_frac"] = 2.0 * b["frac"]
+                b["note"] = ("fp16 hi/lo operand pairs with e4m3 cross terms: per algorithmic MAC one f16 MMA + two f8f6f4 MMAs at "
+                             "twice the rate = 2 f16-equivalents (mma_frac = executed tensor work / f16 peak)")
+            elif "hi/lo" in r["kernel"] or ",1,e" in r["kernel"]:
                 b["mma_frac"] = 3.0 * b["frac"]
                 b["note"] = "fp16 hi/lo operand pairs: 3 tcgen05.mma per algorithmic MAC (mma_frac = executed MMA rate / peak)"
         else:
