@@ -61,7 +61,7 @@ struct UmmaConvParams {
     const unsigned char* a8_hi; const unsigned char* a8_lo; const unsigned char* w8_hi; const unsigned char* w8_lo;
     // UEPI_DN_COND / UEPI_DN_OUTY: also write that e4m3 pair of the output rows (row pitch out8_ld bytes, flattened rows)
     unsigned char* out8_hi; unsigned char* out8_lo; int out8_ld;
-    int dbg;              // experiment bits (CMTTS_UMMA_DBG): 1 = descriptor base_offset, 2 = disable the halo kernel, 128 = disable the gate kernel, 256 = fp16 (not fp8) cross terms in the gate kernel
+    int dbg;              // experiment bits (CMTTS_UMMA_DBG): 1 = descriptor base_offset, 2 = disable the halo kernel, 128 = disable the gate kernel, 256 = fp16 (not fp8) cross terms in the gate kernel, 512 = no CTA-pair halo kernel
 };
 
 static inline UmmaConvParams umma_params_default() {
@@ -73,6 +73,8 @@ static inline UmmaConvParams umma_params_default() {
 int launch_umma_conv(const UmmaConvParams& p, cudaStream_t s);
 // halo-tile / resident-weight variant for Cin == N in {32, 64, 128}; CMTTS_ERR_UNSUPPORTED if not applicable
 int launch_umma_halo(const UmmaConvParams& p, cudaStream_t s);
+// CTA-pair (tcgen05 cta_group::2) variant of the halo kernel for C = 128 with streamed weights (k = 7, 11); see umma_halo2.cu
+int launch_umma_halo2(const UmmaConvParams& p, cudaStream_t s);
 // halo-A variant of the split (hi/lo) kernel for the denoiser's gate conv (UEPI_DN_GATE, 3 taps, Cin == 256);
 // CMTTS_ERR_UNSUPPORTED if not applicable
 int launch_umma_gate(const UmmaConvParams& p, cudaStream_t s);
