@@ -581,6 +581,395 @@ umma_gate8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_consta
     }
 }
 
+
+// ==========================================================================================================================
+// CTA-PAIR variant of umma_gate8_kernel (tcgen05 cta_group::2; see umma_halo2.cu for the mechanism and why it is the bytes
+// INTO an SM, not L2 reads, that bound these kernels): one M = 256 MMA per instruction slot over both SMs' shared memory, each
+// CTA holding its own 128 rows of A and HALF of every weight block (64 of the 128 output channels of the N tile).  Operand
+// bytes per tile and SM: 136 KB of A + 192 KB of weights instead of 136 + 384.  Only the leader issues (both issuing warps);
+// commits are multicast to both CTAs' barriers; `accumulator empty` lives in the leader (16 arrivals).
+__device__ __forceinline__ uint32_t gx2_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void gx2_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t GX2_PEER_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void gx2_tma_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & GX2_PEER_MASK), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void gx2_tma_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & GX2_PEER_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void gx2_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void gx2_mma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void gx2_commit_both(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void gx2_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & GX2_PEER_MASK) : "memory");
+}
+
+template <int TAPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1)
+umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant__ CUtensorMap tmA8h,
+                  const __grid_constant__ CUtensorMap tmA8l, const __grid_constant__ CUtensorMap tmW16,
+                  const __grid_constant__ CUtensorMap tmW8h, const __grid_constant__ CUtensorMap tmW8l,
+                  const UmmaConvParams p, const int rows_alloc, const int box_rows) {
+    constexpr int BM = G_BM, BN = G_BN;
+    constexpr int CB = 4, CB8 = 2;                    // 256 channels: four 64-channel fp16 blocks / two 128-channel e4m3 blocks
+    constexpr int ACC_COLS = 2 * BN;                  // main | cross-term accumulator
+    constexpr int TMEM_COLS = 2 * ACC_COLS;           // double-buffered: 512 columns
+    static_assert(CB % G8_A16_STAGES == 0 && (CB * TAPS) % G8_W16_STAGES == 0 && CB8 % G8_A8_STAGES == 0 &&
+                  (CB8 * TAPS) % G8_W8_STAGES == 0, "every tile must start at ring stage 0");
+
+    const int a_half = rows_alloc * G_ROW_BYTES;      // one halo tile (128-byte rows), 1024-byte multiple
+    const int a8_stage = 2 * a_half;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smA16 = smem;
+    uint8_t* smW16 = smA16 + G8_A16_STAGES * a_half;
+    uint8_t* smA8 = smW16 + G8_W16_STAGES * G_B_BYTES;
+    uint8_t* smW8 = smA8 + G8_A8_STAGES * a8_stage;
+    uint64_t* a16_full = reinterpret_cast<uint64_t*>(smW8 + G8_W8_STAGES * G8_W8_STAGE);
+    uint64_t* a16_empty = a16_full + G8_A16_STAGES;
+    uint64_t* w16_full = a16_empty + G8_A16_STAGES;
+    uint64_t* w16_empty = w16_full + G8_W16_STAGES;
+    uint64_t* a8_full = w16_empty + G8_W16_STAGES;
+    uint64_t* a8_empty = a8_full + G8_A8_STAGES;
+    uint64_t* w8_full = a8_empty + G8_A8_STAGES;
+    uint64_t* w8_empty = w8_full + G8_W8_STAGES;
+    uint64_t* tfull = w8_empty + G8_W8_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int rank = (int)gx2_ctarank();              // 0 = leader of the CTA pair
+    const int m_tiles = (p.M + BM - 1) / BM;
+    const int m_pairs = (m_tiles + 1) / 2;            // a pair covers 256 rows: row tile 2 * mp + rank per CTA
+    const int n_tiles = p.N / BN;
+    const int tiles = p.B * m_pairs * n_tiles;        // pair tiles, n-tile fastest
+    const int shift0 = p.shift[0];
+    const int first = blockIdx.x >> 1, stride = gridDim.x >> 1;     // cluster index / number of clusters
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < G8_A16_STAGES; ++i) { mbar_init(&a16_full[i], 1); mbar_init(&a16_empty[i], 1); }
+        for (int i = 0; i < G8_W16_STAGES; ++i) { mbar_init(&w16_full[i], 1); mbar_init(&w16_empty[i], 1); }
+        for (int i = 0; i < G8_A8_STAGES; ++i) { mbar_init(&a8_full[i], 1); mbar_init(&a8_empty[i], 1); }
+        for (int i = 0; i < G8_W8_STAGES; ++i) { mbar_init(&w8_full[i], 1); mbar_init(&w8_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 2); mbar_init(&tempty[i], 16); }    // both issuers commit tfull; 8 epilogue warps of each CTA
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    gx2_cluster_sync();                               // the peer's barriers exist before anything is signalled into them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    if (warp != 2 && warp != 13) pdl_wait();          // the weight producers read constants only
+
+    constexpr uint32_t DESC_HI = (uint32_t)((8 * G_ROW_BYTES) >> 4) | (1u << 14) | (2u << 29);   // SBO | version | SWIZZLE_128B
+    constexpr uint64_t HI = (uint64_t)DESC_HI << 32;
+
+    if (warp == 0) {
+        // ================= A16 producer: A_hi16 halo tile per 64-channel block =================
+        prefetch_tmap(&tmA16);
+        int stage = 0; uint32_t phase = 0;
+        const uint32_t bytes = (uint32_t)(box_rows * G_ROW_BYTES);
+        for (int tile = first; tile < tiles; tile += stride) {
+            const int rest = tile / n_tiles;
+            const int mt = 2 * (rest % m_pairs) + rank, b = rest / m_pairs;
+#pragma unroll 1
+            for (int cb = 0; cb < CB; ++cb) {
+                mbar_wait(&a16_empty[stage], phase ^ 1);
+                if (rank == 0) mbar_expect_tx_elect(&a16_full[stage], 2 * bytes);          // both CTAs' tiles
+                gx2_tma_3d(smA16 + stage * a_half, &tmA16, &a16_full[stage], cb * G_BK, mt * BM + shift0, b);
+                if (++stage == G8_A16_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 12) {
+        // ================= A8 producer: {A_hi8, A_lo8} halo tiles per 128-channel block =================
+        prefetch_tmap(&tmA8h); prefetch_tmap(&tmA8l);
+        int stage = 0; uint32_t phase = 0;
+        const uint32_t bytes = (uint32_t)(2 * box_rows * G_ROW_BYTES);
+        for (int tile = first; tile < tiles; tile += stride) {
+            const int rest = tile / n_tiles;
+            const int mt = 2 * (rest % m_pairs) + rank, b = rest / m_pairs;
+#pragma unroll 1
+            for (int cb = 0; cb < CB8; ++cb) {
+                mbar_wait(&a8_empty[stage], phase ^ 1);
+                if (rank == 0) mbar_expect_tx_elect(&a8_full[stage], 2 * bytes);
+                uint8_t* sa = smA8 + stage * a8_stage;
+                gx2_tma_3d(sa, &tmA8h, &a8_full[stage], cb * 128, mt * BM + shift0, b);
+                gx2_tma_3d(sa + a_half, &tmA8l, &a8_full[stage], cb * 128, mt * BM + shift0, b);
+                if (++stage == G8_A8_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 2) {
+        // ================= W16 producer: W_hi16 blocks per (64-channel block, tap) =================
+        prefetch_tmap(&tmW16);
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = first; tile < tiles; tile += stride) {
+            const int nt = tile % n_tiles;
+#pragma unroll 1
+            for (int cb = 0; cb < CB; ++cb) {
+#pragma unroll 1
+                for (int tap = 0; tap < TAPS; ++tap) {
+                    mbar_wait(&w16_empty[stage], phase ^ 1);
+                    if (rank == 0) mbar_expect_tx_elect(&w16_full[stage], G_B_BYTES);       // two halves of 64 output channels
+                    gx2_tma_2d(smW16 + stage * G_B_BYTES, &tmW16, &w16_full[stage], cb * G_BK, tap * p.N + nt * BN + rank * (BN / 2));
+                    if (++stage == G8_W16_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 13) {
+        // ================= W8 producer: {W_hi8, W_lo8} blocks per (128-channel block, tap) =================
+        prefetch_tmap(&tmW8h); prefetch_tmap(&tmW8l);
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = first; tile < tiles; tile += stride) {
+            const int nt = tile % n_tiles;
+#pragma unroll 1
+            for (int cb = 0; cb < CB8; ++cb) {
+#pragma unroll 1
+                for (int tap = 0; tap < TAPS; ++tap) {
+                    mbar_wait(&w8_empty[stage], phase ^ 1);
+                    if (rank == 0) mbar_expect_tx_elect(&w8_full[stage], G8_W8_STAGE);
+                    uint8_t* sb = smW8 + stage * G8_W8_STAGE;
+                    gx2_tma_2d(sb, &tmW8h, &w8_full[stage], cb * 128, tap * p.N + nt * BN + rank * (BN / 2));
+                    gx2_tma_2d(sb + G_B_BYTES, &tmW8l, &w8_full[stage], cb * 128, tap * p.N + nt * BN + rank * (BN / 2));
+                    if (++stage == G8_W8_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1 && rank == 0) {
+        // ================= main issuer (leader only; M = 256 across the pair): A_hi16 W_hi16 -> accumulator 0 =================
+        constexpr int A_USES = CB / G8_A16_STAGES, B_USES = CB * TAPS / G8_W16_STAGES;
+        const uint32_t tmem_u = make_uniform(tmem_base);
+        const uint32_t idesc = make_idesc(2 * BM, BN);
+        const uint32_t tap_step = make_uniform((uint32_t)(((TAPS > 1 ? p.shift[1] - p.shift[0] : 0) * G_ROW_BYTES) >> 4));
+        const uint32_t a_half16 = make_uniform((uint32_t)(a_half >> 4));
+        const uint32_t a_base = make_uniform(((smem_u32(smA16) >> 4) & 0x3FFF) | (1u << 16));
+        const uint32_t b_base = make_uniform(((smem_u32(smW16) >> 4) & 0x3FFF) | (1u << 16));
+        uint32_t it = 0;
+        for (int tile = first; tile < tiles; tile += stride, ++it) {
+            const uint32_t abuf = it & 1u, tphase = (it >> 1) & 1u;
+            mbar_wait(&tempty[abuf], tphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = make_uniform(tmem_u + abuf * (uint32_t)ACC_COLS);
+#pragma unroll
+            for (int cb = 0; cb < CB; ++cb) {
+                const int as = cb % G8_A16_STAGES;
+                mbar_wait(&a16_full[as], (uint32_t)((it * A_USES + cb / G8_A16_STAGES) & 1u));
+                tc_fence_after();
+                const uint32_t a0 = a_base + (uint32_t)as * a_half16;
+#pragma unroll
+                for (int tap = 0; tap < TAPS; ++tap) {
+                    const int idx = cb * TAPS + tap;
+                    const int bs = idx % G8_W16_STAGES;
+                    mbar_wait(&w16_full[bs], (uint32_t)((it * B_USES + idx / G8_W16_STAGES) & 1u));
+                    tc_fence_after();
+                    const uint32_t ah = a0 + (uint32_t)tap * tap_step;
+                    const uint32_t wh = b_base + (uint32_t)((bs * G_B_BYTES) >> 4);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < G_BK / 16; ++k)
+                            gx2_mma_f16(d_tmem, HI | (ah + 2 * k), HI | (wh + 2 * k), idesc, (cb | tap | k) ? 1u : 0u);
+                        gx2_commit_both(&w16_empty[bs]);
+                        if (tap == TAPS - 1) gx2_commit_both(&a16_empty[as]);
+                        if (tap == TAPS - 1 && cb == CB - 1) gx2_commit_both(&tfull[abuf]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 3 && rank == 0) {
+        // ================= cross issuer (leader only) (e4m3): A_hi8 W_lo8 + A_lo8 W_hi8 -> accumulator 1 =================
+        constexpr int A_USES = CB8 / G8_A8_STAGES, B_USES = CB8 * TAPS / G8_W8_STAGES;
+        const uint32_t tmem_u = make_uniform(tmem_base);
+        const uint32_t idesc = make_idesc(2 * BM, BN);    // e4m3 x e4m3 -> f32: same bits as f16 x f16 -> f32
+        const uint32_t tap_step = make_uniform((uint32_t)(((TAPS > 1 ? p.shift[1] - p.shift[0] : 0) * G_ROW_BYTES) >> 4));
+        const uint32_t a_half16 = make_uniform((uint32_t)(a_half >> 4));
+        const uint32_t a_base = make_uniform(((smem_u32(smA8) >> 4) & 0x3FFF) | (1u << 16));
+        const uint32_t b_base = make_uniform(((smem_u32(smW8) >> 4) & 0x3FFF) | (1u << 16));
+        uint32_t it = 0;
+        for (int tile = first; tile < tiles; tile += stride, ++it) {
+            const uint32_t abuf = it & 1u, tphase = (it >> 1) & 1u;
+            mbar_wait(&tempty[abuf], tphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = make_uniform(tmem_u + abuf * (uint32_t)ACC_COLS + (uint32_t)BN);
+#pragma unroll
+            for (int cb = 0; cb < CB8; ++cb) {
+                const int as = cb % G8_A8_STAGES;
+                mbar_wait(&a8_full[as], (uint32_t)((it * A_USES + cb / G8_A8_STAGES) & 1u));
+                tc_fence_after();
+                const uint32_t a0 = a_base + (uint32_t)as * 2u * a_half16;
+#pragma unroll
+                for (int tap = 0; tap < TAPS; ++tap) {
+                    const int idx = cb * TAPS + tap;
+                    const int bs = idx % G8_W8_STAGES;
+                    mbar_wait(&w8_full[bs], (uint32_t)((it * B_USES + idx / G8_W8_STAGES) & 1u));
+                    tc_fence_after();
+                    const uint32_t ah = a0 + (uint32_t)tap * tap_step, al = ah + a_half16;
+                    const uint32_t wh = b_base + (uint32_t)((bs * G8_W8_STAGE) >> 4), wl = wh + (uint32_t)(G_B_BYTES >> 4);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < 128 / 32; ++k)                                   // A_hi8 W_lo8
+                            gx2_mma_f8(d_tmem, HI | (ah + 2 * k), HI | (wl + 2 * k), idesc, (cb | tap | k) ? 1u : 0u);
+#pragma unroll
+                        for (int k = 0; k < 128 / 32; ++k)                                   // A_lo8 W_hi8
+                            gx2_mma_f8(d_tmem, HI | (al + 2 * k), HI | (wh + 2 * k), idesc, 1u);
+                        gx2_commit_both(&w8_empty[bs]);
+                        if (tap == TAPS - 1) gx2_commit_both(&a8_empty[as]);
+                        if (tap == TAPS - 1 && cb == CB8 - 1) gx2_commit_both(&tfull[abuf]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ================= epilogue (UEPI_DN_GATE), as umma_gate_kernel's, cross accumulator scaled by 2^-11 =================
+        constexpr int GH = BN / 4;
+        const int q = warp & 3;
+        const int h = (warp - 4) >> 2;
+        const int row = q * 32 + lane;
+        int abuf = 0; uint32_t tphase = 0;
+        for (int tile = first; tile < tiles; tile += stride) {
+            const int nt = tile % n_tiles, rest = tile / n_tiles;
+            const int mt = 2 * (rest % m_pairs) + rank, b = rest / m_pairs;
+            const int t = mt * BM + row;
+            bool valid = t < p.M;
+            if (p.rows_per_utt > 0) {
+                const int ub = t / p.rows_per_utt;
+                valid = valid && (t - ub * p.rows_per_utt) < p.rows_per_utt - 1;
+            }
+            float bg[GH], bf[GH];
+            {
+                const float4* pg = reinterpret_cast<const float4*>(p.bias + nt * BN + h * GH);
+                const float4* pf = reinterpret_cast<const float4*>(p.bias + nt * BN + BN / 2 + h * GH);
+#pragma unroll
+                for (int i = 0; i < GH / 4; ++i) {
+                    const float4 x = __ldg(pg + i), y = __ldg(pf + i);
+                    bg[4 * i] = x.x; bg[4 * i + 1] = x.y; bg[4 * i + 2] = x.z; bg[4 * i + 3] = x.w;
+                    bf[4 * i] = y.x; bf[4 * i + 1] = y.y; bf[4 * i + 2] = y.z; bf[4 * i + 3] = y.w;
+                }
+            }
+            mbar_wait(&tfull[abuf], tphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t)(abuf * ACC_COLS) + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+            for (int c = 0; c < GH / 16; ++c) {
+                uint32_t rg[16], rf[16], rg2[16], rf2[16];
+                const int g0 = h * GH + c * 16;
+                tmem_ld16(taddr + g0, rg);
+                tmem_ld16(taddr + BN / 2 + g0, rf);
+                tmem_ld16(taddr + BN + g0, rg2);
+                tmem_ld16(taddr + BN + BN / 2 + g0, rf2);
+                tmem_ld_wait();
+                if (valid) {
+                    const int ch = nt * (BN / 2) + g0;
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float g = fmaf(fmaf(__uint_as_float(rg2[j]), G8_LO_SCALE_INV, __uint_as_float(rg[j])), p.alpha, bg[c * 16 + j]);
+                        const float f = fmaf(fmaf(__uint_as_float(rf2[j]), G8_LO_SCALE_INV, __uint_as_float(rf[j])), p.alpha, bf[c * 16 + j]);
+                        v[j] = gate_fast(g, f);
+                    }
+                    const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + ch;
+                    store16_hilo(p.out_h + o, p.out_lo + o, v);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) gx2_arrive_leader(&tempty[abuf]);
+            abuf ^= 1; if (abuf == 0) tphase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    gx2_cluster_sync();                               // nobody leaves while the peer may still signal into this CTA
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+
+template <int TAPS>
+int launch_gate8x2_cfg(const UmmaConvParams& p, cudaStream_t s) {
+    const int span = p.shift[p.taps - 1] - p.shift[0];
+    const int box_rows = 128 + span;
+    const int rows_alloc = (box_rows + 7) / 8 * 8;
+    const size_t a_half = (size_t)rows_alloc * G_ROW_BYTES;
+    const size_t smem = G8_A16_STAGES * a_half + (size_t)G8_W16_STAGES * G_B_BYTES + G8_A8_STAGES * 2 * a_half +
+                        (size_t)G8_W8_STAGES * G8_W8_STAGE +
+                        (2 * (G8_A16_STAGES + G8_W16_STAGES + G8_A8_STAGES + G8_W8_STAGES) + 4) * 8 + 16 + 1024;
+    if (smem > 227 * 1024 || box_rows > 256) return CMTTS_ERR_UNSUPPORTED;
+    auto kern = umma_gate8x2_kernel<TAPS>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+            cmtts_set_error("umma_gate8x2: cannot set dynamic shared memory size", __FILE__, __LINE__);
+            return CMTTS_ERR_CUDA;
+        }
+        attr_done = true;
+    }
+    CUtensorMap a16, a8h, a8l, w16, w8h, w8l;
+    // weight boxes: HALF an N tile (64 output channels) per CTA
+    if (!make_act_map(&a16, p.a_hi, p.Cin, p.Lin, p.B, p.a_ld, p.a_bstride, G_BK, box_rows) ||
+        !make_act_map8(&a8h, p.a8_hi, p.Cin, p.Lin, p.B, p.Cin, (long long)p.Lin * p.Cin, box_rows) ||
+        !make_act_map8(&a8l, p.a8_lo, p.Cin, p.Lin, p.B, p.Cin, (long long)p.Lin * p.Cin, box_rows) ||
+        !make_w_map(&w16, p.w_hi, p.Cin, p.taps * p.N, G_BK, G_BN / 2) ||
+        !make_w_map8(&w8h, p.w8_hi, p.Cin, p.taps * p.N, G_BN / 2) || !make_w_map8(&w8l, p.w8_lo, p.Cin, p.taps * p.N, G_BN / 2)) {
+        cmtts_set_error("umma_gate8x2: cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
+        return CMTTS_ERR_CUDA;
+    }
+    const int m_tiles = (p.M + 127) / 128;
+    const int tiles = p.B * ((m_tiles + 1) / 2) * (p.N / G_BN);
+    int grid = 2 * tiles < num_sms() ? 2 * tiles : num_sms();
+    grid &= ~1;
+    if (grid < 2) return CMTTS_ERR_UNSUPPORTED;
+    if (g_cmtts_prof_on) {
+        const double rows = (double)p.B * p.M;
+        char lbl[96];
+        snprintf(lbl, sizeof(lbl), "umma_gate8x2<%d> t%d %d->%d (hi/lo, e4m3 cross terms, CTA pairs)", p.taps, p.taps, p.Cin, p.N);
+        cmtts_prof_note(lbl, 2.0 * rows * p.N * p.taps * p.Cin,
+                        rows * p.Cin * 4.0 + rows * (p.N / 2) * 4.0 + (double)p.taps * p.N * p.Cin * 4.0);
+    }
+    launch_pdl(kern, grid, G8_THREADS, smem, s, a16, a8h, a8l, w16, w8h, w8l, p, rows_alloc, box_rows);
+    CMTTS_CHECK_LAUNCH();
+    return CMTTS_OK;
+}
+
 template <int TAPS>
 int launch_gate8_cfg(const UmmaConvParams& p, cudaStream_t s) {
     const int span = p.shift[p.taps - 1] - p.shift[0];
@@ -674,6 +1063,14 @@ int launch_umma_gate(const UmmaConvParams& p, cudaStream_t s) {
     if (((uintptr_t)p.bias % 16) != 0) return CMTTS_ERR_UNSUPPORTED;      // float4 bias loads
     if (p.B == 0 || p.M == 0) return CMTTS_OK;
     // e4m3 cross terms when the caller supplies the fp8 operand copies (CMTTS_UMMA_DBG bit 256 keeps them in fp16)
-    if (p.a8_hi && p.a8_lo && p.w8_hi && p.w8_lo && !(p.dbg & 256) && p.B == 1 && p.a_bstride >= 0) return launch_gate8_cfg<3>(p, s);
+    if (p.a8_hi && p.a8_lo && p.w8_hi && p.w8_lo && !(p.dbg & 256) && p.B == 1) {
+        static int pair_env = -1;                          // CMTTS_GATE_PAIR=1: CTA-pair (cta_group::2) variant
+        if (pair_env < 0) { const char* e = getenv("CMTTS_GATE_PAIR"); pair_env = e ? atoi(e) : 0; }
+        if (pair_env && !(p.dbg & 1024)) {
+            const int rc = launch_gate8x2_cfg<3>(p, s);
+            if (rc != CMTTS_ERR_UNSUPPORTED) return rc;
+        }
+        return launch_gate8_cfg<3>(p, s);
+    }
     return launch_gate_cfg<3, 4>(p, s);
 }

@@ -103,9 +103,9 @@ def model_diffusion(spec):
 def test_fullsize_vocoder_rows_vs_oracle():
     """C2-size vocoder call (B=32, L=810: every CTA of the persistent kernels runs many tiles) against the oracle run
     on four of its rows alone (HiFi-GAN is per-row), real universal weights when staged.  Rows 1 / 30 hold log-mel-like
-    inputs (N(-5, 2^2) clipped): the fp16-operand tensor-core path must stay within 48 dB and within its
-    usual 4e-3 max-abs scaled to the signal level (that bound was set on outputs of rms ~0.25; the trained generator
-    answers these random mels with a saturated signal of rms 0.8, measured 4.2e-3 at 49.5 dB).
+    inputs (N(-5, 2^2) clipped): the fp16-operand tensor-core path must stay above 48 dB and within 6e-3
+    max-abs (measured 4.2e-3 at 49.5 dB with the trained universal weights at this length; the 4e-3 of the short
+    fixtures was set on synthetic weights).
     Rows 0 / 31 hold the mels the reference's sampler produced from the SYNTHETIC acoustic weights — not speech-like, they
     drive the trained generator into saturation, where fp16 storage of large activations costs absolute accuracy (3.7e-2
     max-abs measured at 50.8 dB): for them the tensor-core path is held to the SNR only, and the fp32 FFMA path (same
@@ -148,7 +148,6 @@ def test_fullsize_vocoder_rows_vs_oracle():
         if precision == "fp32":
             assert e_easy <= 2e-5 and e_hard <= 2e-4, (e_easy, e_hard)
         else:
-            level = max(1.0, float(ref[2:].pow(2).mean().sqrt()) / 0.25)
-            assert e_easy <= 4e-3 * level and s_easy >= 48.0, (e_easy, s_easy, level)
+            assert e_easy <= 6e-3 and s_easy >= 48.0, (e_easy, s_easy)      # measured 4.2e-3 at 49.5 dB (real weights, L = 810)
             assert s_hard >= 48.0, s_hard
         del voc
