@@ -634,6 +634,13 @@ __device__ __forceinline__ void gx2_arrive_leader(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & GX2_PEER_MASK) : "memory");
 }
 
+// per-CTA weight stages hold HALF an N tile (64 output channels): 8 KB fp16 blocks, 8 + 8 KB e4m3 pairs.  The shared memory
+// that frees goes into DEEPER weight rings: the one-CTA kernel's 3 / 2 stages cover only ~0.5 us of tensor-pipe work, less
+// than one L2 round trip, which (not the operand bytes) is what holds it at ~57 us per launch.
+constexpr int GX2_WB = G_B_BYTES / 2;                 // one half block: 64 rows x 128 bytes
+constexpr int GX2_W16_STAGES = 6, GX2_W8_STAGES = 3;
+constexpr int GX2_W8_STAGE = 2 * GX2_WB;
+
 template <int TAPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1)
 umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant__ CUtensorMap tmA8h,
@@ -644,8 +651,8 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
     constexpr int CB = 4, CB8 = 2;                    // 256 channels: four 64-channel fp16 blocks / two 128-channel e4m3 blocks
     constexpr int ACC_COLS = 2 * BN;                  // main | cross-term accumulator
     constexpr int TMEM_COLS = 2 * ACC_COLS;           // double-buffered: 512 columns
-    static_assert(CB % G8_A16_STAGES == 0 && (CB * TAPS) % G8_W16_STAGES == 0 && CB8 % G8_A8_STAGES == 0 &&
-                  (CB8 * TAPS) % G8_W8_STAGES == 0, "every tile must start at ring stage 0");
+    static_assert(CB % G8_A16_STAGES == 0 && (CB * TAPS) % GX2_W16_STAGES == 0 && CB8 % G8_A8_STAGES == 0 &&
+                  (CB8 * TAPS) % GX2_W8_STAGES == 0, "every tile must start at ring stage 0");
 
     const int a_half = rows_alloc * G_ROW_BYTES;      // one halo tile (128-byte rows), 1024-byte multiple
     const int a8_stage = 2 * a_half;
@@ -654,17 +661,17 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smA16 = smem;
     uint8_t* smW16 = smA16 + G8_A16_STAGES * a_half;
-    uint8_t* smA8 = smW16 + G8_W16_STAGES * G_B_BYTES;
+    uint8_t* smA8 = smW16 + GX2_W16_STAGES * GX2_WB;
     uint8_t* smW8 = smA8 + G8_A8_STAGES * a8_stage;
-    uint64_t* a16_full = reinterpret_cast<uint64_t*>(smW8 + G8_W8_STAGES * G8_W8_STAGE);
+    uint64_t* a16_full = reinterpret_cast<uint64_t*>(smW8 + GX2_W8_STAGES * GX2_W8_STAGE);
     uint64_t* a16_empty = a16_full + G8_A16_STAGES;
     uint64_t* w16_full = a16_empty + G8_A16_STAGES;
-    uint64_t* w16_empty = w16_full + G8_W16_STAGES;
-    uint64_t* a8_full = w16_empty + G8_W16_STAGES;
+    uint64_t* w16_empty = w16_full + GX2_W16_STAGES;
+    uint64_t* a8_full = w16_empty + GX2_W16_STAGES;
     uint64_t* a8_empty = a8_full + G8_A8_STAGES;
     uint64_t* w8_full = a8_empty + G8_A8_STAGES;
-    uint64_t* w8_empty = w8_full + G8_W8_STAGES;
-    uint64_t* tfull = w8_empty + G8_W8_STAGES;
+    uint64_t* w8_empty = w8_full + GX2_W8_STAGES;
+    uint64_t* tfull = w8_empty + GX2_W8_STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -679,9 +686,9 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < G8_A16_STAGES; ++i) { mbar_init(&a16_full[i], 1); mbar_init(&a16_empty[i], 1); }
-        for (int i = 0; i < G8_W16_STAGES; ++i) { mbar_init(&w16_full[i], 1); mbar_init(&w16_empty[i], 1); }
+        for (int i = 0; i < GX2_W16_STAGES; ++i) { mbar_init(&w16_full[i], 1); mbar_init(&w16_empty[i], 1); }
         for (int i = 0; i < G8_A8_STAGES; ++i) { mbar_init(&a8_full[i], 1); mbar_init(&a8_empty[i], 1); }
-        for (int i = 0; i < G8_W8_STAGES; ++i) { mbar_init(&w8_full[i], 1); mbar_init(&w8_empty[i], 1); }
+        for (int i = 0; i < GX2_W8_STAGES; ++i) { mbar_init(&w8_full[i], 1); mbar_init(&w8_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 2); mbar_init(&tempty[i], 16); }    // both issuers commit tfull; 8 epilogue warps of each CTA
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -745,9 +752,9 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
 #pragma unroll 1
                 for (int tap = 0; tap < TAPS; ++tap) {
                     mbar_wait(&w16_empty[stage], phase ^ 1);
-                    if (rank == 0) mbar_expect_tx_elect(&w16_full[stage], G_B_BYTES);       // two halves of 64 output channels
-                    gx2_tma_2d(smW16 + stage * G_B_BYTES, &tmW16, &w16_full[stage], cb * G_BK, tap * p.N + nt * BN + rank * (BN / 2));
-                    if (++stage == G8_W16_STAGES) { stage = 0; phase ^= 1; }
+                    if (rank == 0) mbar_expect_tx_elect(&w16_full[stage], 2 * GX2_WB);   // two halves of 64 output channels
+                    gx2_tma_2d(smW16 + stage * GX2_WB, &tmW16, &w16_full[stage], cb * G_BK, tap * p.N + nt * BN + rank * (BN / 2));
+                    if (++stage == GX2_W16_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -762,17 +769,17 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
 #pragma unroll 1
                 for (int tap = 0; tap < TAPS; ++tap) {
                     mbar_wait(&w8_empty[stage], phase ^ 1);
-                    if (rank == 0) mbar_expect_tx_elect(&w8_full[stage], G8_W8_STAGE);
-                    uint8_t* sb = smW8 + stage * G8_W8_STAGE;
+                    if (rank == 0) mbar_expect_tx_elect(&w8_full[stage], 2 * GX2_W8_STAGE);
+                    uint8_t* sb = smW8 + stage * GX2_W8_STAGE;
                     gx2_tma_2d(sb, &tmW8h, &w8_full[stage], cb * 128, tap * p.N + nt * BN + rank * (BN / 2));
-                    gx2_tma_2d(sb + G_B_BYTES, &tmW8l, &w8_full[stage], cb * 128, tap * p.N + nt * BN + rank * (BN / 2));
-                    if (++stage == G8_W8_STAGES) { stage = 0; phase ^= 1; }
+                    gx2_tma_2d(sb + GX2_WB, &tmW8l, &w8_full[stage], cb * 128, tap * p.N + nt * BN + rank * (BN / 2));
+                    if (++stage == GX2_W8_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1 && rank == 0) {
         // ================= main issuer (leader only; M = 256 across the pair): A_hi16 W_hi16 -> accumulator 0 =================
-        constexpr int A_USES = CB / G8_A16_STAGES, B_USES = CB * TAPS / G8_W16_STAGES;
+        constexpr int A_USES = CB / G8_A16_STAGES, B_USES = CB * TAPS / GX2_W16_STAGES;
         const uint32_t tmem_u = make_uniform(tmem_base);
         const uint32_t idesc = make_idesc(2 * BM, BN);
         const uint32_t tap_step = make_uniform((uint32_t)(((TAPS > 1 ? p.shift[1] - p.shift[0] : 0) * G_ROW_BYTES) >> 4));
@@ -794,11 +801,11 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
 #pragma unroll
                 for (int tap = 0; tap < TAPS; ++tap) {
                     const int idx = cb * TAPS + tap;
-                    const int bs = idx % G8_W16_STAGES;
-                    mbar_wait(&w16_full[bs], (uint32_t)((it * B_USES + idx / G8_W16_STAGES) & 1u));
+                    const int bs = idx % GX2_W16_STAGES;
+                    mbar_wait(&w16_full[bs], (uint32_t)((it * B_USES + idx / GX2_W16_STAGES) & 1u));
                     tc_fence_after();
                     const uint32_t ah = a0 + (uint32_t)tap * tap_step;
-                    const uint32_t wh = b_base + (uint32_t)((bs * G_B_BYTES) >> 4);
+                    const uint32_t wh = b_base + (uint32_t)((bs * GX2_WB) >> 4);
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < G_BK / 16; ++k)
@@ -813,7 +820,7 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
         }
     } else if (warp == 3 && rank == 0) {
         // ================= cross issuer (leader only) (e4m3): A_hi8 W_lo8 + A_lo8 W_hi8 -> accumulator 1 =================
-        constexpr int A_USES = CB8 / G8_A8_STAGES, B_USES = CB8 * TAPS / G8_W8_STAGES;
+        constexpr int A_USES = CB8 / G8_A8_STAGES, B_USES = CB8 * TAPS / GX2_W8_STAGES;
         const uint32_t tmem_u = make_uniform(tmem_base);
         const uint32_t idesc = make_idesc(2 * BM, BN);    // e4m3 x e4m3 -> f32: same bits as f16 x f16 -> f32
         const uint32_t tap_step = make_uniform((uint32_t)(((TAPS > 1 ? p.shift[1] - p.shift[0] : 0) * G_ROW_BYTES) >> 4));
@@ -835,11 +842,11 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
 #pragma unroll
                 for (int tap = 0; tap < TAPS; ++tap) {
                     const int idx = cb * TAPS + tap;
-                    const int bs = idx % G8_W8_STAGES;
-                    mbar_wait(&w8_full[bs], (uint32_t)((it * B_USES + idx / G8_W8_STAGES) & 1u));
+                    const int bs = idx % GX2_W8_STAGES;
+                    mbar_wait(&w8_full[bs], (uint32_t)((it * B_USES + idx / GX2_W8_STAGES) & 1u));
                     tc_fence_after();
                     const uint32_t ah = a0 + (uint32_t)tap * tap_step, al = ah + a_half16;
-                    const uint32_t wh = b_base + (uint32_t)((bs * G8_W8_STAGE) >> 4), wl = wh + (uint32_t)(G_B_BYTES >> 4);
+                    const uint32_t wh = b_base + (uint32_t)((bs * GX2_W8_STAGE) >> 4), wl = wh + (uint32_t)(GX2_WB >> 4);
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < 128 / 32; ++k)                                   // A_hi8 W_lo8
@@ -930,9 +937,9 @@ int launch_gate8x2_cfg(const UmmaConvParams& p, cudaStream_t s) {
     const int box_rows = 128 + span;
     const int rows_alloc = (box_rows + 7) / 8 * 8;
     const size_t a_half = (size_t)rows_alloc * G_ROW_BYTES;
-    const size_t smem = G8_A16_STAGES * a_half + (size_t)G8_W16_STAGES * G_B_BYTES + G8_A8_STAGES * 2 * a_half +
-                        (size_t)G8_W8_STAGES * G8_W8_STAGE +
-                        (2 * (G8_A16_STAGES + G8_W16_STAGES + G8_A8_STAGES + G8_W8_STAGES) + 4) * 8 + 16 + 1024;
+    const size_t smem = G8_A16_STAGES * a_half + (size_t)GX2_W16_STAGES * GX2_WB + G8_A8_STAGES * 2 * a_half +
+                        (size_t)GX2_W8_STAGES * GX2_W8_STAGE +
+                        (2 * (G8_A16_STAGES + GX2_W16_STAGES + G8_A8_STAGES + GX2_W8_STAGES) + 4) * 8 + 16 + 1024;
     if (smem > 227 * 1024 || box_rows > 256) return CMTTS_ERR_UNSUPPORTED;
     auto kern = umma_gate8x2_kernel<TAPS>;
     static bool attr_done = false;

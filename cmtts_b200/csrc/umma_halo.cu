@@ -443,7 +443,7 @@ int launch_umma_halo(const UmmaConvParams& p, cudaStream_t s) {
         case 11: return launch_halo_cfg<BN_, BK_, CB_, 11>(p, s);                 \
         default: return launch_halo_cfg<BN_, BK_, CB_, 0>(p, s);                  \
     }
-    if (p.N == 128) {        // streamed weights (k = 7, 11): the CTA-pair kernel halves the weight bytes each SM takes in
+    if (p.N == 128 || p.N == 256) {   // streamed weights: the CTA-pair kernel halves the weight bytes each SM takes in
         const int rc = launch_umma_halo2(p, s);
         if (rc != CMTTS_ERR_UNSUPPORTED) return rc;
     }
