@@ -1071,8 +1071,8 @@ int launch_umma_gate(const UmmaConvParams& p, cudaStream_t s) {
     if (p.B == 0 || p.M == 0) return CMTTS_OK;
     // e4m3 cross terms when the caller supplies the fp8 operand copies (CMTTS_UMMA_DBG bit 256 keeps them in fp16)
     if (p.a8_hi && p.a8_lo && p.w8_hi && p.w8_lo && !(p.dbg & 256) && p.B == 1) {
-        static int pair_env = -1;                          // CMTTS_GATE_PAIR=1: CTA-pair (cta_group::2) variant
-        if (pair_env < 0) { const char* e = getenv("CMTTS_GATE_PAIR"); pair_env = e ? atoi(e) : 0; }
+        static int pair_env = -1;                          // CMTTS_GATE_PAIR=0: one-CTA kernel instead of the CTA-pair (cta_group::2) one
+        if (pair_env < 0) { const char* e = getenv("CMTTS_GATE_PAIR"); pair_env = e ? atoi(e) : 1; }
         if (pair_env && !(p.dbg & 1024)) {
             const int rc = launch_gate8x2_cfg<3>(p, s);
             if (rc != CMTTS_ERR_UNSUPPORTED) return rc;
