@@ -244,14 +244,17 @@ def roofline_blocks(rows, total_us, peaks, step_ms, total_flops, stage_ms, stage
             ach = r["bytes"] / sec / 1e9 if r["bytes"] > 0 else 0.0
             b = {"kernel": r["kernel"], "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                  "frac": ach / peaks["hbm_gbs"]}
-        t = tr.get(r["kernel"], {})
-        b.update({"traffic": t.get("dram_bytes_per_launch"), "launches_per_step": r["launches"],
+        keys = [k for k in tr if not k.startswith("_") and r["kernel"].startswith(k)]
+        t = tr[max(keys, key=len)] if keys else {}
+        b.update({"traffic": t.get("dram_bytes_per_launch"), "traffic_tensor_pipe_pct_ncu": t.get("tensor_pipe_pct"), "launches_per_step": r["launches"],
                   "us_per_launch": r["us"] / r["launches"], "share_of_step": r["share"],
                   "algorithmic_flops_per_launch": r["flops"] / r["launches"],
                   "algorithmic_bytes_per_launch": r["bytes"] / r["launches"]})
         return b
 
     top = block(rows[0])
+    stamp_file = os.path.join(ROOT, "cmtts_b200", "lib", "libcmtts_b200.so.stamp")
+    top["traffic_same_build"] = bool(tr.get("_build_stamp")) and os.path.isfile(stamp_file) and open(stamp_file).read().strip() == tr.get("_build_stamp")
     top["peak_source"] = peaks["source"] + ", sustained (kernel timed inside the step)"
     top["step_frac"] = total_flops / (step_ms * 1e-3) / 1e12 / peaks["tflops_sustained"]
     top["stage_fracs"] = {k: (stage_flops[k] / (v * 1e-3) / 1e12 / peaks["tflops_sustained"]) for k, v in stage_ms.items()
