@@ -41,7 +41,7 @@ for cfg in C2 C3; do
   python tools/launch_summary.py $OUT/launches_${TAG}_$cfg.csv > $OUT/launches_${TAG}_${cfg}_summary.txt; head -14 $OUT/launches_${TAG}_${cfg}_summary.txt
 done
 # ncu --set full: (1) one denoiser evaluation's tcgen05 kernels (skip dpen + the first evaluation), (2) the vocoder, (3) row kernels
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:umma_ -s 120 -c 12 -o $OUT/prof_dn_$TAG -f \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:umma_ -s 70 -c 12 -o $OUT/prof_dn_$TAG -f \
     python tools/stage_only.py --stage sampler --config C2 --T 2 --reps 1 > $OUT/prof_dn_$TAG.log 2>&1
 python tools/ncu_summary.py $OUT/prof_dn_$TAG.ncu-rep $OUT/ncu_${TAG}_denoiser_summary.csv
 timeout 500 ncu --set full --clock-control none -k regex:umma_ -s 64 -c 64 -o $OUT/prof_voc_$TAG -f \
