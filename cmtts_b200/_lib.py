@@ -92,7 +92,10 @@ PROTOTYPES = {
     "cmtts_umma_conv1d": (C.c_int, [C.POINTER(UmmaDesc)] + [vp] * 13),
     "cmtts_f32_to_f16": (C.c_int, [vp, vp, vp, i64, i64, i64, f32, vp]),
     "cmtts_denoiser_tc_workspace_bytes": (szt, [PD, i64, i64]),
-    "cmtts_denoiser_forward_tc": (C.c_int, [PD, PV, PV, vp, vp, vp, vp, vp, f32, f32, f32, i64, i64, vp, vp, vp, szt, vp]),
+    "cmtts_denoiser_cond_tc_bytes": (szt, [PD, i64, i64]),
+    "cmtts_denoiser_cond_tc_workspace_bytes": (szt, [PD, i64, i64]),
+    "cmtts_denoiser_cond_tc": (C.c_int, [PD, PV, PV, vp, i64, i64, vp, vp, szt, vp]),
+    "cmtts_denoiser_forward_tc": (C.c_int, [PD, PV, PV, vp, vp, vp, vp, f32, f32, f32, i64, i64, vp, vp, vp, szt, vp]),
     "cmtts_encoder_tc_workspace_bytes": (szt, [PD, i64, i64]),
     "cmtts_encoder_forward_tc": (C.c_int, [PD, PV, PV, vp, vp, i64, i64, vp, vp, szt, vp]),
     "cmtts_variance_token_tc_workspace_bytes": (szt, [PD, i64, i64]),
@@ -121,7 +124,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.cmtts_abi_version() != 1:
+    if lib.cmtts_abi_version() != 2:
         raise CmttsError("libcmtts_b200.so ABI version mismatch")
     _lib = lib
     return lib

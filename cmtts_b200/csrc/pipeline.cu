@@ -646,9 +646,9 @@ extern "C" int cmtts_f32_to_f16(const float* x, void* hi, void* lo, int64_t rows
 
 extern "C" size_t cmtts_denoiser_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t L) {
     const size_t R = (size_t)B * (L + 1);                       // flattened rows, one guard row per utterance
-    const size_t C = d->res_channels, H = d->hidden;
-    return align_up(R * C * 4) * 2 +                            // x, v (fp32)
-           align_up(R * (C + H) * 2) * 2 +                      // [y | cond] hi, lo
+    const size_t C = d->res_channels;
+    return align_up(R * C * 4) +                                // v (fp32; only the fp32 output projection reads it)
+           align_up(R * C * 2) * 2 +                            // y hi, lo
            align_up(R * C * 2) * 2 * (size_t)d->res_layers +    // g hi, lo of every layer
            align_up(R * C * 2) * 2 +                            // skip sum hi, lo
            align_up(R * 128 * 2) * 2 +                          // x_t hi, lo (K padded to 128)
@@ -656,22 +656,65 @@ extern "C" size_t cmtts_denoiser_tc_workspace_bytes(const cmtts_dims* d, int64_t
            align_up((size_t)B * d->res_layers * C * 4);         // per-(utterance, layer) constants
 }
 
+// Conditioner projections of ALL residual layers, once per batch.  The conditioner is the same for every solver
+// step and every layer only sees it through a 1x1 projection (blocks.py:675), so everything that depends on it is
+// ONE GEMM over the stacked projection weights (weights.py: cond_stack_weights), run once per batch:
+//     P[0]   = Wc_0 cond + bc_0                       (the conditioner term of y_0)
+//     P[l>0] = (Wc_l - r Wc_{l-1}) cond               (the conditioner term of the y-recurrence below)
+// as fp32 [layer][flattened row][C].  The per-layer GEMMs of the solver steps then contract over the gate output and y
+// only (K = 384 instead of 640) and add their P row in the epilogue.
+extern "C" size_t cmtts_denoiser_cond_tc_bytes(const cmtts_dims* d, int64_t B, int64_t L) {
+    return (size_t)d->res_layers * (size_t)B * (size_t)(L + 1) * (size_t)d->res_channels * 4;
+}
+extern "C" size_t cmtts_denoiser_cond_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t L) {
+    return align_up((size_t)B * (L + 1) * d->hidden * 2) * 2;   // cond hi, lo in the flattened layout
+}
+extern "C" int cmtts_denoiser_cond_tc(const cmtts_dims* d, const void* const* w, const void* const* w16,
+                                      const float* cond, int64_t B_, int64_t L_, float* cond_proj, void* ws,
+                                      size_t ws_bytes, void* stream) {
+    (void)w;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = (int)B_, L = (int)L_, C = d->res_channels, H = d->hidden, NLY = d->res_layers;
+    CMTTS_REQUIRE(ws_bytes >= cmtts_denoiser_cond_tc_workspace_bytes(d, B_, L_), "denoiser_cond_tc: workspace too small");
+    CMTTS_REQUIRE(C % 128 == 0 && H % 64 == 0, "denoiser_cond_tc: channel counts must suit the 128x128x64 UMMA tiling");
+    CMTTS_REQUIRE((long long)B * (L + 1) < (1ll << 31), "denoiser_cond_tc: too many rows");
+    CMTTS_REQUIRE(cond && cond_proj && ((uintptr_t)cond_proj % 16) == 0, "denoiser_cond_tc: null or misaligned tensor");
+    if (B == 0 || L == 0) return CMTTS_OK;
+    const int Lp = L + 1, R = B * Lp;
+    Carver cv(ws, ws_bytes);
+    __half* c_hi = cv.take<__half>((size_t)R * H);
+    __half* c_lo = cv.take<__half>((size_t)R * H);
+    // guard rows of the operand are never written: zero them so the (unused) guard rows of P stay finite
+    cudaMemset2DAsync(c_hi + (size_t)L * H, (size_t)Lp * H * 2, 0, (size_t)H * 2, B, s);
+    cudaMemset2DAsync(c_lo + (size_t)L * H, (size_t)Lp * H * 2, 0, (size_t)H * 2, B, s);
+    CMTTS_TRY(launch_f32_to_f16_rows(cond, c_hi, c_lo, B, L, Lp, H, H, H, 1.f, s));
+    const void* const* wcs = w16 + NLY * 7 + 4 + 3 * (NLY - 1) + 3 + 3 + 2 * NLY;   // {cond stack w hi, lo [NLY*C][H]; bias [NLY*C]}
+    UmmaConvParams u = tc_same(HL{c_hi, c_lo}, 1, R, H, wcs[0], wcs[1], (const float*)wcs[2], NLY * C, 1, 1);
+    u.rows_per_utt = Lp;
+    u.out_f32 = cond_proj; u.out32_bstride = 0; u.out32_ld = C;
+    u.out32_ncols = C; u.out32_plane = (long long)R * C;
+    CMTTS_TRY(launch_umma_conv(u, s));
+    return CMTTS_OK;
+}
+
 // The residual stack on tensor cores, restructured (same algebra as the reference, fp32-class rounding):
 //
 // * a recurrence in y_l = x_l + c_l, c_l = Wc_l cond + bc_l + step_l[b] + spk_l[b] (what the k=3 conv consumes,
 //   blocks.py:669-678).  With r = 1/sqrt(2), x_{l+1} = r (Wo_l[:C] g_l + bo_l + step_l[b] + x_l) (blocks.py:676,:683-686):
-//       y_{l+1} = [r Wo_l[:C] | r I | Wc_{l+1} - r Wc_l] [g_l ; y_l ; cond] + const_l[b]
+//       y_{l+1} = [r Wo_l[:C] | r I] [g_l ; y_l] + (Wc_{l+1} - r Wc_l) cond + const_l[b]
 //   ONE GEMM per layer (weights.py: fused_recurrence_weights) instead of an output projection, a conditioner
 //   projection and two read-modify-write passes over x.  y_l enters through the operand pipeline (block-diagonal
-//   r I: a tile only loads its own 128 channels of y), so the epilogue reads nothing from global memory — with
-//   epilogue reads the kernel sat on exposed DRAM latency (ncu / tools/ablate.py).  x_l itself is never needed;
+//   r I: a tile only loads its own 128 channels of y); the conditioner term is the layer's plane of the per-batch
+//   projections P (cmtts_denoiser_cond_tc above), fetched into registers BEFORE the accumulator wait so its latency
+//   hides behind the tile's MMAs — with unprefetched epilogue reads the kernel sat on exposed DRAM latency (ncu /
+//   tools/ablate.py).  x_l itself is never needed;
 // * the skip sum (modules.py:629-637) is ONE GEMM at the end over the stacked gate outputs, K = layers * C
 //   (weights.py: skip_stack_weights), instead of a fp32 read-modify-write of `skip` in every layer;
 // * utterances are FLATTENED into one row axis with a zero guard row after each (row b (L+1) + t): the k=3 conv's
 //   zero padding between neighbours is the guard row, tiles are 128 consecutive rows regardless of L (L = 793 would
 //   otherwise waste 11 % of every 7th tile and, worse, quantise 896 tiles onto 148 SMs as 7 rounds instead of 6).
 extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const* w, const void* const* w16,
-                                         const float* x_t, const void* cond_hi, const void* cond_lo,
+                                         const float* x_t, const float* cond_proj,
                                          const float* ds_all, const float* dsp_all, float c_in, float c_out,
                                          float c_skip, int64_t B_, int64_t L_, float* out, float* model_out,
                                          void* ws, size_t ws_bytes, void* stream) {
@@ -681,13 +724,13 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
     CMTTS_REQUIRE(C % 128 == 0 && H % 64 == 0, "denoiser_tc: channel counts must suit the 128x128x64 UMMA tiling");
     CMTTS_REQUIRE(M <= 128, "denoiser_tc: n_mels must be <= 128");
     CMTTS_REQUIRE((long long)B * (L + 1) < (1ll << 31), "denoiser_tc: too many rows");
+    CMTTS_REQUIRE(cond_proj != nullptr && ((uintptr_t)cond_proj % 16) == 0, "denoiser_tc: conditioner projections (cmtts_denoiser_cond_tc) missing");
     if (B == 0 || L == 0) return CMTTS_OK;
-    const int Lp = L + 1, R = B * Lp, YC = C + H;
+    const int Lp = L + 1, R = B * Lp;
     Carver cv(ws, ws_bytes);
-    float* x = cv.take<float>((size_t)R * C);
     float* v = cv.take<float>((size_t)R * C);
-    __half* yc_hi = cv.take<__half>((size_t)R * YC);          // row = [y (C) | cond (H)]
-    __half* yc_lo = cv.take<__half>((size_t)R * YC);
+    __half* y_hi = cv.take<__half>((size_t)R * C);            // y_l, in place over the layers
+    __half* y_lo = cv.take<__half>((size_t)R * C);
     __half* g_hi = cv.take<__half>((size_t)R * C * NLY);      // [layer][row][C]
     __half* g_lo = cv.take<__half>((size_t)R * C * NLY);
     __half* sk_hi = cv.take<__half>((size_t)R * C);
@@ -698,8 +741,9 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
     unsigned char* y8_lo = cv.take<unsigned char>((size_t)R * C);
     float* yc = cv.take<float>((size_t)B * NLY * C);
     const long long NL = (long long)NLY * C;
+    const long long PL = (long long)R * C;                    // one layer's plane of cond_proj
     const void* const* wx = w16 + NLY * 7;                    // {in_w hi, lo [C][128]; skip_w hi, lo [C][C]}
-    const void* const* wf = wx + 4;                           // per layer l < NLY-1: {y_w hi, lo [C][2C+H]; y_b [C]}
+    const void* const* wf = wx + 4;                           // per layer l < NLY-1: {y_w hi, lo [C][2C]; y_b [C]}
     const void* const* wsk = wf + 3 * (NLY - 1);              // {skip-stack w hi, lo [NLY*C][C]; summed bias [C]}
     const void* const* w8 = wsk + 3 + 3;                      // per layer {gate conv w as e4m3: hi8, lo8 [3][2C][C] bytes}
     static int fp8_env = -1;                                  // CMTTS_GATE_FP8=0: fp16 cross terms (A/B and fallback)
@@ -711,16 +755,15 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
     auto flat = [&](UmmaConvParams& u) { u.B = 1; u.M = R; u.Lin = R; u.rows_per_utt = Lp; };
 
     CMTTS_TRY(launch_dn_fuse_steps(ds_all, dsp_all, yc, B, NLY, C, r, s));
-    // zero the y part of the guard rows (the conv's padding); everything else in guard rows is never consumed
-    cudaMemset2DAsync(yc_hi + (size_t)L * YC, (size_t)Lp * YC * 2, 0, (size_t)C * 2, B, s);
-    cudaMemset2DAsync(yc_lo + (size_t)L * YC, (size_t)Lp * YC * 2, 0, (size_t)C * 2, B, s);
+    // zero the guard rows of y (the conv's padding)
+    cudaMemset2DAsync(y_hi + (size_t)L * C, (size_t)Lp * C * 2, 0, (size_t)C * 2, B, s);
+    cudaMemset2DAsync(y_lo + (size_t)L * C, (size_t)Lp * C * 2, 0, (size_t)C * 2, B, s);
     if (fp8x) {
         cudaMemset2DAsync(y8_hi + (size_t)L * C, (size_t)Lp * C, 0, (size_t)C, B, s);
         cudaMemset2DAsync(y8_lo + (size_t)L * C, (size_t)Lp * C, 0, (size_t)C, B, s);
     }
-    CMTTS_TRY(launch_pack_rows_f16((const __half*)cond_hi, yc_hi, B, L, Lp, H, YC, C, s));
-    CMTTS_TRY(launch_pack_rows_f16((const __half*)cond_lo, yc_lo, B, L, Lp, H, YC, C, s));
-    // input projection: relu(W (c_in x_t) + b).  c_in * x_t is formed in fp32 first, like the reference
+    // input projection + y_0 in one launch: y_0 = relu(W (c_in x_t) + b) + P_0 + (step + speaker)_0[b]
+    // (modules.py:622-623, blocks.py:669-678).  c_in * x_t is formed in fp32 first, like the reference
     // (karras_diffusion.py:405), and THEN split into an fp16 hi/lo pair zero-padded to 128 channels: the operand is
     // O(1) whatever sigma_max the config holds (raw x_t ~ 6 sigma_max would overflow fp16 for sigma_max > 1e4)
     CMTTS_TRY(launch_f32_to_f16_rows(x_t, xt_hi, xt_lo, B, L, Lp, M, 128, 128, c_in, s));
@@ -728,21 +771,9 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
         UmmaConvParams u = tc_same(HL{xt_hi, xt_lo}, 1, R, 128, wx[0], wx[1], F(w, CMTTS_DN_IN_B), C, 1, 1);
         flat(u);
         u.alpha = TC_W_SCALE_INV; u.act = ACT_RELU;
-        tc_out32(u, x, R, C);
-        CMTTS_TRY(launch_umma_conv(u, s));
-    }
-    {
-        // y_0 = Wc_0 cond + bc_0 + (step + speaker)_0[b] + x_0                blocks.py:669-678
-        UmmaConvParams u = umma_params_default();
-        flat(u);
-        u.N = C; u.Cin = H; u.taps = 1; u.shift[0] = 0; u.split = 1; u.epi = UEPI_DN_COND;
-        u.alpha = TC_W_SCALE_INV;
-        u.a_hi = yc_hi + C; u.a_lo = yc_lo + C; u.a_bstride = (long long)R * YC; u.a_ld = YC;
-        u.w_hi = (const __half*)w16[0]; u.w_lo = (const __half*)w16[1];
-        u.bias = F(w, CMTTS_DN_LAYER0 + 1);
         u.addvec = dsp_all; u.addvec_bstride = NL;
-        u.x_f32 = x; u.x_bstride = (long long)R * C; u.x_ld = C;
-        u.out_h = yc_hi; u.out_lo = yc_lo; u.out_bstride = (long long)R * YC; u.out_ld = YC;
+        u.x_f32 = const_cast<float*>(cond_proj); u.x_bstride = 0; u.x_ld = C; u.res_scale = 1.f;
+        u.out_h = y_hi; u.out_lo = y_lo; u.out_bstride = (long long)R * C; u.out_ld = C;
         if (fp8x) { u.out8_hi = y8_hi; u.out8_lo = y8_lo; u.out8_ld = C; }
         CMTTS_TRY(launch_umma_conv(u, s));
     }
@@ -756,7 +787,7 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
         flat(u);
         u.N = 2 * C; u.Cin = C; u.taps = 3; u.shift[0] = -1; u.shift[1] = 0; u.shift[2] = 1;
         u.split = 1; u.epi = UEPI_DN_GATE; u.alpha = TC_W_SCALE_INV;
-        u.a_hi = yc_hi; u.a_lo = yc_lo; u.a_bstride = (long long)R * YC; u.a_ld = YC;
+        u.a_hi = y_hi; u.a_lo = y_lo; u.a_bstride = (long long)R * C; u.a_ld = C;
         u.w_hi = (const __half*)wl[2]; u.w_lo = (const __half*)wl[3];
         u.bias = F(w, o + 3);
         u.out_h = gl_hi; u.out_lo = gl_lo; u.out_bstride = (long long)R * C; u.out_ld = C;
@@ -766,18 +797,19 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
         }
         CMTTS_TRY(launch_umma_conv(u, s));
         if (l + 1 < NLY) {
-            // y_{l+1}, in place: K = C (g_l) + own 128 channels of y_l + H (cond); see the recurrence above
+            // y_{l+1}, in place: K = C (g_l) + own 128 channels of y_l, + P_{l+1} in the epilogue; see the recurrence above
             u = umma_params_default();
             flat(u);
             u.N = C; u.Cin = C; u.taps = 1; u.shift[0] = 0; u.split = 1; u.epi = UEPI_DN_OUTY;
             u.alpha = TC_W_SCALE_INV;
             u.a_hi = gl_hi; u.a_lo = gl_lo; u.a_bstride = (long long)R * C; u.a_ld = C;
-            u.a2_hi = yc_hi; u.a2_lo = yc_lo; u.a2_bstride = (long long)R * YC; u.a2_ld = YC;
-            u.Cin2 = YC; u.n_k2 = C; u.a2_diag = C;
+            u.a2_hi = y_hi; u.a2_lo = y_lo; u.a2_bstride = (long long)R * C; u.a2_ld = C;
+            u.Cin2 = C; u.n_k2 = C; u.a2_diag = C;
             u.w_hi = (const __half*)wf[3 * l]; u.w_lo = (const __half*)wf[3 * l + 1];
             u.bias = (const float*)wf[3 * l + 2];
             u.addvec = yc + (long long)l * C; u.addvec_bstride = (long long)(NLY - 1) * C;
-            u.out_h = yc_hi; u.out_lo = yc_lo; u.out_bstride = (long long)R * YC; u.out_ld = YC;
+            u.x_f32 = const_cast<float*>(cond_proj) + (long long)(l + 1) * PL; u.x_bstride = 0; u.x_ld = C;
+            u.out_h = y_hi; u.out_lo = y_lo; u.out_bstride = (long long)R * C; u.out_ld = C;
             if (fp8x) { u.out8_hi = y8_hi; u.out8_lo = y8_lo; u.out8_ld = C; }
             CMTTS_TRY(launch_umma_conv(u, s));
         }

@@ -260,7 +260,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if constexpr (SPLIT) {
                 const float* src = nullptr;
                 const long long t_io = p.io_unguard ? (long long)(t - ub) : (long long)t;   // row in un-guarded fp32 tensors
-                if (EPI == UEPI_DN_COND || (EPI == UEPI_F32 && p.x_f32 != nullptr && n0 < p.n_valid))
+                if (EPI == UEPI_DN_COND || (EPI == UEPI_DN_OUTY && p.x_f32 != nullptr) ||
+                    (EPI == UEPI_F32 && p.x_f32 != nullptr && n0 < p.n_valid))
                     src = p.x_f32 + (long long)b * p.x_bstride + t_io * p.x_ld + n0;
                 else if (EPI == UEPI_DN_OUT) {
                     const int half_n = p.N >> 1;
@@ -411,12 +412,15 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             for (int j = 0; j < 16; ++j) v[j] = keep ? fmaf(x[j], p.res_scale, v[j]) * p.out_scale : 0.f;
                             if (p.out_f32) {
                                 const long long t_o = p.io_unguard ? (long long)(t - ub) : (long long)t;
-                                store16f(p.out_f32 + (long long)b * p.out32_bstride + t_o * p.out32_ld + n, v);
+                                long long col = n;
+                                if (p.out32_ncols > 0) { const int pl = n / p.out32_ncols; col = (long long)pl * p.out32_plane + (n - pl * p.out32_ncols); }
+                                store16f(p.out_f32 + (long long)b * p.out32_bstride + t_o * p.out32_ld + col, v);
                             }
                             if (p.out_h) {
                                 const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
                                 if (p.out_lo) store16_hilo(p.out_h + o, p.out_lo + o, v);
                                 else store16h(p.out_h + o, v);          // plain fp16 (vocoder activated storage)
+                                if (p.out8_hi) store16_f8pair(p.out8_hi + (long long)t * p.out8_ld + n, p.out8_lo + (long long)t * p.out8_ld + n, v);
                             }
                         } else if (EPI == UEPI_DN_COND) {
 #pragma unroll
@@ -426,7 +430,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             if (p.out8_hi) store16_f8pair(p.out8_hi + (long long)t * p.out8_ld + n, p.out8_lo + (long long)t * p.out8_ld + n, v);
                         } else if (EPI == UEPI_DN_OUTY) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] += av[j];
+                            for (int j = 0; j < 16; ++j) v[j] += av[j] + x[j];     // x[]: conditioner projection row (or zeros)
                             const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + n;
                             store16_hilo(p.out_h + o, p.out_lo + o, v);
                             if (p.out8_hi) store16_f8pair(p.out8_hi + (long long)t * p.out8_ld + n, p.out8_lo + (long long)t * p.out8_ld + n, v);
@@ -554,6 +558,12 @@ int launch_umma_conv(const UmmaConvParams& p_in, cudaStream_t s) {
         CMTTS_REQUIRE(!p.a_tap_dim || (p.B == 1 && !p.a2_hi), "umma_conv: a_tap_dim needs B == 1 and no second operand");
         CMTTS_REQUIRE(!p.io_unguard || (p.rows_per_utt > 0 && p.epi == UEPI_F32 && p.n_valid % 16 == 0),
                       "umma_conv: io_unguard needs the flattened layout, the generic epilogue and n_valid % 16 == 0");
+        CMTTS_REQUIRE(p.out32_ncols == 0 || (p.epi == UEPI_F32 && p.out32_ncols % 16 == 0 && p.out_f32 != nullptr),
+                      "umma_conv: out32_ncols needs the generic epilogue, an fp32 output and a multiple of 16");
+        CMTTS_REQUIRE(p.out8_hi == nullptr || (p.out8_lo && p.out_h && p.out_lo && p.rows_per_utt > 0),
+                      "umma_conv: the e4m3 output pair needs the hi/lo output and the flattened layout");
+        CMTTS_REQUIRE(p.x_f32 == nullptr || ((uintptr_t)p.x_f32 % 16 == 0 && p.x_ld % 4 == 0 && p.x_bstride % 4 == 0),
+                      "umma_conv: x_f32 must be 16-byte aligned");
         if (p.epi == UEPI_DN_GATE && !(p.dbg & 128)) {      // halo-A variant for the denoiser's k=3 gate conv (umma_gate.cu)
             const int rc = launch_umma_gate(p, s);
             if (rc != CMTTS_ERR_UNSUPPORTED) return rc;
@@ -711,6 +721,89 @@ conv_post_f16_kernel(const __half* __restrict__ x, const float* __restrict__ w, 
     if (wav_i16) wav_i16[(long long)b * L + n] = (short)(int)__fmul_rn(y, max_wav);
 }
 
+// Same op, FOUR adjacent output samples per thread (template: compile-time C and K so the windows live in registers).
+// The one-sample kernel above issues 84 16-byte shared-memory loads per output sample (7 rows x 4 chunks of x + 56 of
+// weights) and ran at 0.29 of the copy bandwidth, bound by the shared-memory pipe (ncu).  Adjacent outputs share K - 1
+// of their K input rows and all of the weights: per 8-channel chunk a thread loads its K + 3 rows once and each weight
+// chunk once, 24 loads per output.  Rows are staged in the order (r & 3, r >> 2) so that a warp's accesses to
+// "row 4 t + m" are consecutive 80-byte slots (distinct banks per quarter warp).  Summation order per output: channel
+// chunk outer, tap inner (the one-sample kernel: tap outer) — fixed, so results stay run-to-run and batch invariant.
+constexpr int POST4_THREADS = 128, POST4_OUT = 4, POST4_TILE = POST4_THREADS * POST4_OUT;
+template <int C, int K>
+__global__ void __launch_bounds__(POST4_THREADS)
+conv_post_f16x4_kernel(const __half* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                       float pre_div, float* __restrict__ wav, short* __restrict__ wav_i16, float max_wav, int L) {
+    constexpr int ROWS = POST4_TILE + K - 1;
+    constexpr int QP = (((ROWS + 3) / 4 + 3) & ~7) + 4;                     // slots per residue class, = 4 mod 8: classes 64 B apart mod 128
+    constexpr int PITCH = C * 2 + 16;
+    constexpr int CPR = C / 8;
+    constexpr int NW = POST4_OUT + K - 1;                                   // rows one thread touches
+    static_assert(QP * 4 >= ROWS && C % 8 == 0, "conv_post_f16x4: staging layout");
+    __shared__ __align__(16) float s_w[K * C];
+    __shared__ __align__(16) uint8_t s_x[4 * QP * PITCH];
+    const int b = blockIdx.y;
+    const int n0 = blockIdx.x * POST4_TILE;
+    constexpr int pad = (K - 1) / 2;
+    for (int i = threadIdx.x; i < K * C; i += POST4_THREADS) s_w[i] = w[i];
+    const __half* xb = x + (long long)b * L * C;
+    for (int i = threadIdx.x; i < ROWS * CPR; i += POST4_THREADS) {
+        const int r = i / CPR, ch = i - r * CPR;
+        const int src = n0 - pad + r;
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (src >= 0 && src < L) u = reinterpret_cast<const uint4*>(xb + (long long)src * C)[ch];
+        *reinterpret_cast<uint4*>(s_x + ((r & 3) * QP + (r >> 2)) * PITCH + ch * 16) = u;
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    float acc[POST4_OUT];
+#pragma unroll
+    for (int j = 0; j < POST4_OUT; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int c8 = 0; c8 < CPR; ++c8) {
+        uint4 xr[NW];
+#pragma unroll
+        for (int m = 0; m < NW; ++m)                                        // row 4 t + m of the tile
+            xr[m] = *reinterpret_cast<const uint4*>(s_x + ((m & 3) * QP + t + (m >> 2)) * PITCH + c8 * 16);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float4 w0 = *reinterpret_cast<const float4*>(s_w + k * C + c8 * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(s_w + k * C + c8 * 8 + 4);
+#pragma unroll
+            for (int j = 0; j < POST4_OUT; ++j) {
+                const __half2* h = reinterpret_cast<const __half2*>(&xr[j + k]);
+                const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+                float a = acc[j];
+                a = fmaf(f0.x, w0.x, a); a = fmaf(f0.y, w0.y, a);
+                a = fmaf(f1.x, w0.z, a); a = fmaf(f1.y, w0.w, a);
+                a = fmaf(f2.x, w1.x, a); a = fmaf(f2.y, w1.y, a);
+                a = fmaf(f3.x, w1.z, a); a = fmaf(f3.y, w1.w, a);
+                acc[j] = a;
+            }
+        }
+    }
+    const int n = n0 + t * POST4_OUT;
+    const float bz = bias[0];
+    float y[POST4_OUT];
+#pragma unroll
+    for (int j = 0; j < POST4_OUT; ++j) y[j] = tanhf(acc[j] / pre_div + bz);
+    if (n + POST4_OUT <= L && (L % POST4_OUT) == 0) {
+        if (wav) *reinterpret_cast<float4*>(wav + (long long)b * L + n) = make_float4(y[0], y[1], y[2], y[3]);
+        if (wav_i16) {
+            short4 q;
+            q.x = (short)(int)__fmul_rn(y[0], max_wav); q.y = (short)(int)__fmul_rn(y[1], max_wav);
+            q.z = (short)(int)__fmul_rn(y[2], max_wav); q.w = (short)(int)__fmul_rn(y[3], max_wav);
+            *reinterpret_cast<short4*>(wav_i16 + (long long)b * L + n) = q;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < POST4_OUT; ++j) {
+            if (n + j >= L) break;
+            if (wav) wav[(long long)b * L + n + j] = y[j];
+            if (wav_i16) wav_i16[(long long)b * L + n + j] = (short)(int)__fmul_rn(y[j], max_wav);
+        }
+    }
+}
+
 }  // namespace
 
 int launch_f32_to_f16(const float* x, __half* hi, __half* lo, long long rows, int C, int Cpad, float slope, cudaStream_t s) {
@@ -749,10 +842,18 @@ int launch_conv_post_f16(const __half* x, const float* w, const float* bias, flo
     if (B == 0 || L == 0) return CMTTS_OK;
     const size_t smem = (size_t)((K * C * 4 + 15) & ~15) + (size_t)(POST_TILE + K - 1) * (C * 2 + 16);
     CMTTS_REQUIRE(C % 8 == 0 && smem <= 48 * 1024, "conv_post_f16: shape");
-    dim3 grid((L + POST_TILE - 1) / POST_TILE, B);
     if (g_cmtts_prof_on)
         cmtts_prof_note("conv_post_f16 (k7 conv + tanh + int16)", 2.0 * B * L * C * K,
                         (double)B * L * (C * 2.0 + (wav ? 4.0 : 0.0) + (wav_i16 ? 2.0 : 0.0)));
+    static int one_env = -1;                                   // CMTTS_POST1=1: the one-sample-per-thread kernel (A/B)
+    if (one_env < 0) { const char* e = getenv("CMTTS_POST1"); one_env = e ? atoi(e) : 0; }
+    if (C == 32 && K == 7 && !one_env && ((uintptr_t)wav % 16) == 0 && ((uintptr_t)wav_i16 % 8) == 0) {
+        dim3 grid4((L + POST4_TILE - 1) / POST4_TILE, B);
+        conv_post_f16x4_kernel<32, 7><<<grid4, POST4_THREADS, 0, s>>>(x, w, bias, pre_div, wav, wav_i16, max_wav, L);
+        CMTTS_CHECK_LAUNCH();
+        return CMTTS_OK;
+    }
+    dim3 grid((L + POST_TILE - 1) / POST_TILE, B);
     conv_post_f16_kernel<<<grid, POST_TILE, smem, s>>>(x, w, bias, pre_div, wav, wav_i16, max_wav, L, C, K);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;

@@ -10,7 +10,8 @@ enum UmmaEpi {
     UEPI_DN_OUT = 3,   // cols <  N/2: x = (acc + b + addvec[b] + x) * out_scale (fp32, in place)
                        // cols >= N/2: skip (+)= acc + b                 (fp32)
     UEPI_DN_OUTY = 5,  // y-recurrence of the residual stack (see pipeline.cu): y = acc + bias + addvec[utterance]
-                       // -> fp16 hi/lo, written in place over the y operand (out_h/out_lo)
+                       // + x_f32[row] (the layer's precomputed conditioner projection, fp32, read ahead of the
+                       // accumulator wait) -> fp16 hi/lo, written in place over the y operand (out_h/out_lo)
     UEPI_F32 = 4,      // generic: v = act((acc*alpha + bias) * beta) + addvec[b] + res*res_scale ; v *= out_scale ;
                        // rows >= lens[b] -> 0 ; written as fp32 (out_f32) and/or fp16 hi/lo ; cols >= n_valid dropped
 };
@@ -52,6 +53,10 @@ struct UmmaConvParams {
     float* skip_f32; int skip_accumulate; float out_scale;
     // UEPI_F32 extras (res = x_f32 with x_bstride / x_ld)
     int act; float beta; float res_scale; const long long* lens; float* out_f32; long long out32_bstride; int out32_ld; int n_valid;
+    // UEPI_F32: out_f32 as a stack of column planes — column n goes to plane n / out32_ncols (plane stride out32_plane
+    // elements) at column n % out32_ncols (out32_ncols % 16 == 0; 0 = one plane).  One GEMM over stacked weights
+    // [layers * C][K] then writes [layer][row][C].
+    int out32_ncols; long long out32_plane;
     // transposed convs packed as 3-tap convs (weights.py: pack_conv_transpose): output columns < tap_split_n only have
     // non-zero weights in taps [0, taps-1), columns >= tap_split_n only in taps [1, taps) -> the all-zero tap of a tile
     // is skipped (identical results: it would add exact zeros).  0 = off.
@@ -59,7 +64,7 @@ struct UmmaConvParams {
     // fp8 (e4m3) operand copies for the CROSS TERMS of the denoiser's gate conv (umma_gate.cu, umma_gate8_kernel):
     // activations [M][Cin] bytes and weights [taps*N][Cin] bytes, each as (e4m3(hi), e4m3(lo * 2^11)).  NULL = fp16 cross terms.
     const unsigned char* a8_hi; const unsigned char* a8_lo; const unsigned char* w8_hi; const unsigned char* w8_lo;
-    // UEPI_DN_COND / UEPI_DN_OUTY: also write that e4m3 pair of the output rows (row pitch out8_ld bytes, flattened rows)
+    // UEPI_DN_COND / UEPI_DN_OUTY / UEPI_F32 (with out_h + out_lo): also write that e4m3 pair of the output rows (row pitch out8_ld bytes, flattened rows)
     unsigned char* out8_hi; unsigned char* out8_lo; int out8_ld;
     int dbg;              // experiment bits (CMTTS_UMMA_DBG): 1 = descriptor base_offset, 2 = disable the halo kernel, 128 = disable the gate kernel, 256 = fp16 (not fp8) cross terms in the gate kernel, 512 = no CTA-pair halo kernel
 };

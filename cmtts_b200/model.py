@@ -249,10 +249,10 @@ class CMTotalTTS:
 
     def denoise_step(self, x_t: torch.Tensor, cond: torch.Tensor, steps: Tuple[torch.Tensor, torch.Tensor],
                      c_in: float = 1.0, c_out: float = 1.0, c_skip: float = 0.0, want_model_out: bool = False,
-                     cond16: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+                     cond_proj: Optional[torch.Tensor] = None):
         """out = c_out * F(c_in * x_t) + c_skip * x_t on (B,1,L,M) / (B,L,M) channels-last mels.
-        `cond16`: the conditioner's fp16 hi/lo pair from `split_cond(cond)` when the caller evaluates several solver
-        steps on one conditioner (the sampler does); made here per call otherwise."""
+        `cond_proj`: the conditioner's per-layer projections from `project_cond(cond)` when the caller evaluates several
+        solver steps on one conditioner (the sampler does); made here per call otherwise."""
         self._ready()
         lib, s, dev = self.lib, self.spec, self.device
         shape = tuple(x_t.shape)
@@ -264,17 +264,17 @@ class CMTotalTTS:
         if M != s.n_mels or tuple(cond.shape) != (B, L, s.hidden):
             raise ValueError(f"denoise_step: x {tuple(shape)} / cond {tuple(cond.shape)} mismatch")
         cond = cond.to(dev, torch.float32).contiguous()
-        c_hi, c_lo = cond16 if cond16 is not None else (None, None)
-        out, mo = torch.ops.cmtts_b200.denoiser_forward(self.handle, x, cond, c_hi, c_lo, steps[0], steps[1], float(c_in),
+        out, mo = torch.ops.cmtts_b200.denoiser_forward(self.handle, x, cond, cond_proj, steps[0], steps[1], float(c_in),
                                                         float(c_out), float(c_skip), bool(want_model_out))
         out = out.view(shape)
         return (out, mo.view(shape)) if want_model_out else out
 
-    def split_cond(self, cond: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """fp16 hi/lo operand pair of the conditioner (B, L, hidden).  It is the same for every solver step
-        (SURVEY.md App. C.1), so the sampler makes it once per call and hands it to `denoise_step`; nothing is cached
-        behind the caller's back (a pointer-keyed cache goes stale when a buffer is refilled through raw pointers)."""
-        return torch.ops.cmtts_b200.split_f16(cond.to(self.device, torch.float32).contiguous())
+    def project_cond(self, cond: torch.Tensor) -> torch.Tensor:
+        """Conditioner projections of all residual layers (blocks.py:675) for a conditioner (B, L, hidden): one GEMM per
+        batch.  The conditioner is the same for every solver step, so the sampler makes this once
+        per call and hands it to `denoise_step`; nothing is cached behind the caller's back (a pointer-keyed cache goes
+        stale when a buffer is refilled through raw pointers)."""
+        return torch.ops.cmtts_b200.denoiser_cond(self.handle, cond.to(self.device, torch.float32).contiguous())
 
     def get_segmentation_model(self):
         """tts_net.py:66-73 -> (dpen callable, denoise_fun(mel[B,1,L,80]... ) in the reference's

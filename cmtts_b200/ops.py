@@ -8,7 +8,8 @@ SURVEY.md §7.2).
                                                                               -> cond, mel2ph, cwt, f0_denorm, pitch_idx
     torch.ops.cmtts_b200.denoiser_prepare(handle, t, spk?)                    -> ds_all, dsp_all
     torch.ops.cmtts_b200.split_f16(x)                                         -> hi, lo
-    torch.ops.cmtts_b200.denoiser_forward(handle, x, cond, cond_hi?, cond_lo?, ds, dsp, c_in, c_out, c_skip, want_F)
+    torch.ops.cmtts_b200.denoiser_cond(handle, cond)                          -> cond_proj (per-batch conditioner projections)
+    torch.ops.cmtts_b200.denoiser_forward(handle, x, cond, cond_proj?, ds, dsp, c_in, c_out, c_skip, want_F)
                                                                               -> out, model_out
     torch.ops.cmtts_b200.renoise(x0, noise, s1, s2)                           -> x
     torch.ops.cmtts_b200.hifigan_forward(handle, mel_blc, want_float, want_int16, max_wav) -> wav, wav_i16
@@ -65,7 +66,8 @@ _DEF.define("variance_token(int handle, Tensor enc, Tensor src_lens, Tensor? spk
 _DEF.define("variance_frame(int handle, Tensor out1, Tensor cumsum, Tensor mel_lens, Tensor f0_stats, float p_control, int L) -> Tensor[]")
 _DEF.define("denoiser_prepare(int handle, Tensor t, Tensor? speaker_emb) -> (Tensor, Tensor)")
 _DEF.define("split_f16(Tensor x) -> (Tensor, Tensor)")
-_DEF.define("denoiser_forward(int handle, Tensor x, Tensor cond, Tensor? cond_hi, Tensor? cond_lo, Tensor ds_all, Tensor dsp_all, "
+_DEF.define("denoiser_cond(int handle, Tensor cond) -> Tensor")
+_DEF.define("denoiser_forward(int handle, Tensor x, Tensor cond, Tensor? cond_proj, Tensor ds_all, Tensor dsp_all, "
             "float c_in, float c_out, float c_skip, bool want_model_out) -> (Tensor, Tensor)")
 _DEF.define("renoise(Tensor x0, Tensor noise, float s1, float s2) -> Tensor")
 _DEF.define("hifigan_forward(int handle, Tensor mel, bool want_float, bool want_int16, float max_wav_value) -> (Tensor, Tensor)")
@@ -179,8 +181,28 @@ def _split_f16(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return hi, lo
 
 
-def _denoiser_forward(handle: int, x: torch.Tensor, cond: torch.Tensor, cond_hi: Optional[torch.Tensor],
-                      cond_lo: Optional[torch.Tensor], ds_all: torch.Tensor, dsp_all: torch.Tensor, c_in: float, c_out: float,
+def _denoiser_cond(handle: int, cond: torch.Tensor) -> torch.Tensor:
+    """Conditioner projections of all residual layers, once per batch: fp32 [layers][B*(L+1)][C] on the tensor-core path
+    (cmtts_denoiser_cond_tc); the fp32 path projects inside cmtts_denoiser_forward and gets an empty tensor."""
+    o = _owner(handle)
+    lib, s, dev, st = _ctx(o)
+    B, L, H = cond.shape
+    if o.precision != "tc":
+        return torch.empty(0, dtype=torch.float32, device=dev)
+    d = C.byref(o._dims)
+    cond = cond.contiguous()
+    proj = torch.empty(s.res_layers, B * (L + 1), s.res_channels, dtype=torch.float32, device=dev)
+    assert proj.numel() * 4 == lib.cmtts_denoiser_cond_tc_bytes(d, B, L)
+    if proj.numel():
+        with torch.cuda.device(dev):
+            ws = o._ws.get("dnc", lib.cmtts_denoiser_cond_tc_workspace_bytes(d, B, L))
+            _lib.check(lib.cmtts_denoiser_cond_tc(d, o.packed.dn.ptrs, o.packed.dn16.ptrs, _lib.ptr(cond), B, L, _lib.ptr(proj),
+                                                  _lib.ptr(ws), ws.numel(), st), "denoiser_cond_tc")
+    return proj
+
+
+def _denoiser_forward(handle: int, x: torch.Tensor, cond: torch.Tensor, cond_proj: Optional[torch.Tensor],
+                      ds_all: torch.Tensor, dsp_all: torch.Tensor, c_in: float, c_out: float,
                       c_skip: float, want_model_out: bool) -> Tuple[torch.Tensor, torch.Tensor]:
     o = _owner(handle)
     lib, s, dev, st = _ctx(o)
@@ -190,11 +212,13 @@ def _denoiser_forward(handle: int, x: torch.Tensor, cond: torch.Tensor, cond_hi:
     d = C.byref(o._dims)
     with torch.cuda.device(dev):
         if o.precision == "tc":
-            if cond_hi is None or cond_lo is None:
-                cond_hi, cond_lo = _split_f16(cond)
+            if cond_proj is None:
+                cond_proj = _denoiser_cond(handle, cond)
+            if tuple(cond_proj.shape) != (s.res_layers, B * (L + 1), s.res_channels):
+                raise ValueError(f"denoiser_forward: cond_proj {tuple(cond_proj.shape)} does not belong to a ({B}, {L}) batch")
             ws = o._ws.get("dn", lib.cmtts_denoiser_tc_workspace_bytes(d, B, L))
-            _lib.check(lib.cmtts_denoiser_forward_tc(d, o.packed.dn.ptrs, o.packed.dn16.ptrs, _lib.ptr(x), _lib.ptr(cond_hi),
-                                                     _lib.ptr(cond_lo), _lib.ptr(ds_all), _lib.ptr(dsp_all), c_in, c_out, c_skip, B, L,
+            _lib.check(lib.cmtts_denoiser_forward_tc(d, o.packed.dn.ptrs, o.packed.dn16.ptrs, _lib.ptr(x), _lib.ptr(cond_proj),
+                                                     _lib.ptr(ds_all), _lib.ptr(dsp_all), c_in, c_out, c_skip, B, L,
                                                      _lib.ptr(out), _lib.ptr(mo) if want_model_out else None, _lib.ptr(ws),
                                                      ws.numel(), st), "denoiser_forward_tc")
         else:
@@ -252,9 +276,10 @@ def _transpose_bcl_blc(x: torch.Tensor) -> torch.Tensor:
 
 _IMPL = torch.library.Library("cmtts_b200", "IMPL", "CUDA")
 for _name, _fn in (("encoder_forward", _encoder_forward), ("variance_token", _variance_token), ("variance_frame", _variance_frame),
-                   ("denoiser_prepare", _denoiser_prepare), ("split_f16", _split_f16), ("denoiser_forward", _denoiser_forward),
+                   ("denoiser_prepare", _denoiser_prepare), ("split_f16", _split_f16), ("denoiser_cond", _denoiser_cond),
+                   ("denoiser_forward", _denoiser_forward),
                    ("renoise", _renoise), ("hifigan_forward", _hifigan_forward), ("transpose_bcl_blc", _transpose_bcl_blc)):
     _IMPL.impl(_name, _fn)
 
-OPS = ("encoder_forward", "variance_token", "variance_frame", "denoiser_prepare", "split_f16", "denoiser_forward", "renoise",
+OPS = ("encoder_forward", "variance_token", "variance_frame", "denoiser_prepare", "split_f16", "denoiser_cond", "denoiser_forward", "renoise",
        "hifigan_forward", "transpose_bcl_blc")

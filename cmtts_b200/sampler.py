@@ -90,7 +90,7 @@ class _FusedDistiller:
         self._steps_key = None
         self._steps = None
         self._prepared = prepared_steps      # (ds_all, dsp_all) made ahead by the caller for this call's sigma
-        self._cond16 = None          # (cond tensor, fp16 hi/lo pair): made once per sampler call
+        self._cond_proj = None       # (cond tensor, its per-layer projections): made once per sampler call
         self.model_outputs = None  # set to a list to capture F per evaluation (parity tests)
 
     def conditioner(self, L: int) -> dict:
@@ -109,17 +109,17 @@ class _FusedDistiller:
         elif self._steps_key != sigma_value:
             self._steps = self.model.prepare_steps(rescaled_timesteps(B, sigma_value), cond["speaker_emb"])
             self._steps_key = sigma_value
-        c16 = None
+        cp = None
         if self.model.precision == "tc":
-            if self._cond16 is None or self._cond16[0] is not cond["cond"]:
-                self._cond16 = (cond["cond"], self.model.split_cond(cond["cond"]))
-            c16 = self._cond16[1]
+            if self._cond_proj is None or self._cond_proj[0] is not cond["cond"]:
+                self._cond_proj = (cond["cond"], self.model.project_cond(cond["cond"]))
+            cp = self._cond_proj[1]
         if self.model_outputs is not None:
             out, mo = self.model.denoise_step(x_t, cond["cond"], self._steps, c_in, c_out, c_skip, want_model_out=True,
-                                              cond16=c16)
+                                              cond_proj=cp)
             self.model_outputs.append(mo)
             return out
-        return self.model.denoise_step(x_t, cond["cond"], self._steps, c_in, c_out, c_skip, cond16=c16)
+        return self.model.denoise_step(x_t, cond["cond"], self._steps, c_in, c_out, c_skip, cond_proj=cp)
 
 
 def karras_sample_tts(diffusion, model, shape, steps=2, clip_denoised=False, progress=False, callback=None,

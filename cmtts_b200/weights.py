@@ -143,6 +143,21 @@ def fused_recurrence_weights(sd: Dict[str, torch.Tensor], l: int, C: int, H: int
     return wf, bf
 
 
+def cond_stack_weights(sd: Dict[str, torch.Tensor], n_layers: int, C: int, H: int):
+    """Everything the residual stack needs from the conditioner, as ONE GEMM per batch (csrc/pipeline.cu,
+    cmtts_denoiser_cond_tc): weights (n_layers * C, H) and bias (n_layers * C,)  (fp64).  Row block 0 is layer 0's
+    conditioner projection Wc_0 (+ bc_0): the conditioner term of y_0; row block l > 0 is the conditioner block
+    Wc_l - r Wc_{l-1} of fused_recurrence_weights(l - 1) (its bias stays with the recurrence GEMM)."""
+    p0 = "net.residual_layers.0.conditioner_projection.conv."
+    ws = [sd[p0 + "weight"][:, :, 0].double()]
+    b = torch.zeros(n_layers * C, dtype=torch.float64)
+    b[:C] = sd[p0 + "bias"].double()
+    for l in range(n_layers - 1):
+        wf, _ = fused_recurrence_weights(sd, l, C, H)
+        ws.append(wf[:, 2 * C:])
+    return torch.cat(ws, dim=0), b
+
+
 def skip_stack_weights(sd: Dict[str, torch.Tensor], n_layers: int, C: int):
     """sum_l (Wo_l[C:] g_l + bo_l[C:]) (model/modules.py:629-634, blocks.py:683-686) as ONE GEMM over the stacked
     gate outputs: weights (n_layers * C, C) with row l*C + n = Wo_l[C + n], and the summed bias (C,)  (fp64)."""
@@ -323,9 +338,11 @@ class PackedAcoustic:
         # y-recurrence of the residual stack (csrc/pipeline.cu, cmtts_denoiser_forward_tc): per layer l < last the
         # (C, 2C + H) operand of fused_recurrence_weights, then the stacked skip projection of skip_stack_weights;
         # derived in fp64, then split into fp16 hi/lo like every other operand
+        # (the GEMM of the solver steps contracts over [g_l ; y_l] only: the conditioner block goes to the per-batch
+        # stack at the end of this table)
         for l in range(s.res_layers - 1):
             wf, bf = fused_recurrence_weights(sd, l, C, s.hidden)
-            hi, lo = split_f16(wf)
+            hi, lo = split_f16(wf[:, :2 * C].contiguous())
             dn16.add(hi); dn16.add(lo); dn16.add(bf.to(torch.float32))
         wsk, bsk = skip_stack_weights(sd, s.res_layers, C)
         hi, lo = split_f16(wsk)
@@ -341,6 +358,10 @@ class PackedAcoustic:
         for l in range(s.res_layers):
             hi8, lo8 = split_f8(conv_w_nk(sd[f"net.residual_layers.{l}.conv_layer.conv.weight"][perm]))
             dn16.add(hi8); dn16.add(lo8)
+        # conditioner projections of all layers as one per-batch GEMM (cond_stack_weights)
+        wcs, bcs = cond_stack_weights(sd, s.res_layers, C, s.hidden)
+        hi, lo = split_f16(wcs)
+        dn16.add(hi); dn16.add(lo); dn16.add(bcs.to(torch.float32))
         self.dn16 = dn16.finish()
 
         def add_pair(tab, w):

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CMTTS_ABI_VERSION 1
+#define CMTTS_ABI_VERSION 2
 
 int cmtts_abi_version(void);
 const char* cmtts_last_error(void);
@@ -207,17 +207,27 @@ int cmtts_f32_to_f16(const float* x, void* hi, void* lo, int64_t rows, int64_t C
 /* D1/D3 + S4 on tensor cores: same contract as cmtts_denoiser_forward; `w16` holds per layer
  * {cond_w hi, lo [C][H]; k3_w hi, lo [3*2C][C] (gate/filter interleaved per 64); out_w hi, lo [2C][C];
  *  out_b fp32 [2C]}, then {in_w hi, lo [C][128] (K zero-padded); skip_w hi, lo [C][C]}, then per layer
- * l < res_layers-1 the y-recurrence operands {y_w hi, lo [C][2C+H]; y_b fp32 [C]} with
- * y_w = [r Wo_l[:C] | r I | Wc_{l+1} - r Wc_l], r = 1/sqrt(2), then the stacked skip projection
+ * l < res_layers-1 the y-recurrence operands {y_w hi, lo [C][2C]; y_b fp32 [C]} with
+ * y_w = [r Wo_l[:C] | r I], r = 1/sqrt(2), then the stacked skip projection
  * {skip_stack_w hi, lo [res_layers*C][C] (row l*C+n = Wo_l[C+n]); summed bias fp32 [C]}, then the output
  * projection {out_w hi, lo [128][C] (rows >= n_mels zero); out_b fp32 [128]}, then per layer the k3 conv's weights
  * once more as an e4m3 pair {hi8 = e4m3(hi), lo8 = e4m3(lo * 2^11), bytes [3*2C][C]}: the operands of the gate conv's
  * cross terms A_hi W_lo + A_lo W_hi, which run as kind::f8f6f4 MMAs (csrc/umma_gate.cu; CMTTS_GATE_FP8=0 keeps them
- * in fp16) (cmtts_b200/weights.py);
- * cond_hi/cond_lo are the fp16 split of the conditioner (cmtts_f32_to_f16). */
+ * in fp16), then the conditioner stack {cond_stack_w hi, lo [res_layers*C][H]; bias fp32 [res_layers*C]}: row block 0
+ * = Wc_0 (+ bc_0), row block l > 0 = Wc_l - r Wc_{l-1} (cmtts_b200/weights.py).
+ *
+ * The conditioner (B,L,H) is the same for every solver step (karras_diffusion.py:560-566 re-derives it per step from
+ * the same inputs), so its projections for ALL layers are made once per batch by cmtts_denoiser_cond_tc:
+ * cond_proj = fp32 [res_layers][B*(L+1)][C] (cmtts_denoiser_cond_tc_bytes), row b*(L+1)+t, one unused guard row per
+ * utterance; cmtts_denoiser_forward_tc consumes it. */
+size_t cmtts_denoiser_cond_tc_bytes(const cmtts_dims* d, int64_t B, int64_t L);
+size_t cmtts_denoiser_cond_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t L);
+int cmtts_denoiser_cond_tc(const cmtts_dims* d, const void* const* w, const void* const* w16,
+                           const float* cond /* (B,L,H) */, int64_t B, int64_t L, float* cond_proj,
+                           void* ws, size_t ws_bytes, void* stream);
 size_t cmtts_denoiser_tc_workspace_bytes(const cmtts_dims* d, int64_t B, int64_t L);
 int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const* w, const void* const* w16,
-                              const float* x_t, const void* cond_hi, const void* cond_lo,
+                              const float* x_t, const float* cond_proj,
                               const float* ds_all, const float* dsp_all, float c_in, float c_out,
                               float c_skip, int64_t B, int64_t L, float* out, float* model_out,
                               void* ws, size_t ws_bytes, void* stream);

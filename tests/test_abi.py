@@ -19,7 +19,7 @@ def test_library_builds_and_exports_header_symbols():
     from cmtts_b200 import build, _lib
     build.build()
     lib = _lib.load()
-    assert lib.cmtts_abi_version() == 1
+    assert lib.cmtts_abi_version() == 2
     syms = _header_symbols()
     assert len(syms) >= 20
     for s in syms:
