@@ -884,6 +884,7 @@ extern "C" int cmtts_hifigan_forward_tc(const int32_t* cfg, const void* const* w
     float* pre32 = cv.take<float>((size_t)B * L * c.C0);
 
     int wi = 0;
+    int wpair = 0;      // first pair-packed entry of the 32-channel level (after the conv_pre hi/lo pair), set below
     // conv_pre (hifigan/models.py:150) -> fp16 lrelu(x).  The raw log-mel input spans +-11, too coarse for a single
     // fp16 pass, so it runs on the hi/lo kernel (fp32-class products; K = 7 taps x 80 mels zero-padded to 128):
     // w16[n_entries-2, n_entries-1] = {pre_w hi, lo [7][C0][128]} (weights.py), input split into the pre32 scratch.
@@ -891,6 +892,7 @@ extern "C" int cmtts_hifigan_forward_tc(const int32_t* cfg, const void* const* w
         int n_entries = 2;
         for (int i = 0; i < c.n_levels; ++i) n_entries += 2 + 4 * c.n_kernels * c.n_dil;
         n_entries += 2;                                   // conv_post
+        wpair = n_entries + 2;
         CMTTS_REQUIRE((size_t)c.C0 * 4 >= 2 * 128 * 2, "hifigan_tc: scratch too small for the mel hi/lo pair");
         __half* m_hi = reinterpret_cast<__half*>(pre32);
         __half* m_lo = m_hi + (size_t)B * L * 128;
@@ -944,6 +946,10 @@ extern "C" int cmtts_hifigan_forward_tc(const int32_t* cfg, const void* const* w
                     rb.a = cur; rb.w1 = (const __half*)w[wi]; rb.b1 = F(w, wi + 1); rb.t_slope = 0.1f;
                     rb.w2 = (const __half*)w[wi + 2]; rb.b2 = F(w, wi + 3); rb.alpha2 = 1.f;
                     rb.res_inv_slope = 10.f; rb.sum_h = sum; rb.out_h = fdst; rb.out_slope = oslope;
+                    if (ch == 32) {                       // pair-packed copies (weights.py: PackedHifiGan.table16 tail)
+                        rb.w1p = (const __half*)w[wpair + 2 * (j * c.n_dil + m)];
+                        rb.w2p = (const __half*)w[wpair + 2 * (j * c.n_dil + m) + 1];
+                    }
                     const int rc = launch_umma_resblock(rb, s);
                     if (rc == CMTTS_OK) { if (!last) cur = fdst; wi += 4; continue; }
                     if (rc != CMTTS_ERR_UNSUPPORTED) return rc;

@@ -226,6 +226,37 @@ __device__ __forceinline__ void store16_hilo(__half* hi, __half* lo, const float
     store16h(hi, h);
     store16h(lo, l);
 }
+// packed forms of the two helpers above/below (for epilogues that stage their output in shared memory for a TMA store)
+__device__ __forceinline__ void pack16_hilo(const float (&f)[16], uint4& h0, uint4& h1, uint4& l0, uint4& l1) {
+    __half2* ph0 = reinterpret_cast<__half2*>(&h0); __half2* ph1 = reinterpret_cast<__half2*>(&h1);
+    __half2* pl0 = reinterpret_cast<__half2*>(&l0); __half2* pl1 = reinterpret_cast<__half2*>(&l1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 a = __floats2half2_rn(f[2 * i], f[2 * i + 1]), b = __floats2half2_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
+        const float2 af = __half22float2(a), bf = __half22float2(b);
+        ph0[i] = a; ph1[i] = b;
+        pl0[i] = __floats2half2_rn(f[2 * i] - af.x, f[2 * i + 1] - af.y);
+        pl1[i] = __floats2half2_rn(f[8 + 2 * i] - bf.x, f[8 + 2 * i + 1] - bf.y);
+    }
+}
+__device__ __forceinline__ void pack16_f8pair(const float (&f)[16], uint4& h8, uint4& l8) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t hw = 0, lw = 0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float a = f[4 * i + 2 * j], b = f[4 * i + 2 * j + 1];
+            const float ah = __half2float(__float2half_rn(a)), bh = __half2float(__float2half_rn(b));
+            const uint32_t ph = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(ah, bh), __NV_SATFINITE, __NV_E4M3);
+            const uint32_t pl = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((a - ah) * 2048.f, (b - bh) * 2048.f), __NV_SATFINITE, __NV_E4M3);
+            hw |= ph << (16 * j); lw |= pl << (16 * j);
+        }
+        h[i] = hw; l[i] = lw;
+    }
+    h8 = make_uint4(h[0], h[1], h[2], h[3]);
+    l8 = make_uint4(l[0], l[1], l[2], l[3]);
+}
 // e4m3 pair of 16 values for the fp8 cross terms: hi8 = e4m3(fp16(v)), lo8 = e4m3((v - fp16(v)) * 2^11)   (16 bytes each)
 __device__ __forceinline__ void store16_f8pair(unsigned char* hi8, unsigned char* lo8, const float (&f)[16]) {
     uint32_t h[4], l[4];
@@ -300,6 +331,18 @@ static inline bool make_act_map8(CUtensorMap* m, const unsigned char* base, int 
     cuuint32_t es[3] = {1, 1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<unsigned char*>(base), dims, strides, box, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// byte tensors [B][L][C] as the TARGET of 64-byte-wide TMA stores: box {64 bytes, box_rows, 1}, 64B swizzle
+static inline bool make_store_map8(CUtensorMap* m, unsigned char* base, int C, int L, int B, int ld, long long bstride, int box_rows) {
+    auto enc = get_encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)bstride};
+    cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1u};
+    cuuint32_t es[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 static inline bool make_w_map8(CUtensorMap* m, const unsigned char* base, int Cin, int rows, int BN) {

@@ -90,6 +90,8 @@ __global__ void __launch_bounds__(384, 1)
 umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
+                 const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
+                 const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmO3,
                  const UmmaConvParams p) {
     constexpr int BM = 128;
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
@@ -103,8 +105,19 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     constexpr int ACC_COLS = SPLIT ? 2 * BN : BN;     // TMEM columns per accumulator buffer
     constexpr int TMEM_COLS = pow2_cols(2 * ACC_COLS);
 
+    // UEPI_DN_OUTY stages its output tile in shared memory and TMA-stores it: per epilogue warp (32 rows x 64 columns)
+    // {hi 4 KB | lo 4 KB | e4m3 hi 2 KB | e4m3 lo 2 KB} in the swizzled box layouts of tmO0..3.  With one STG.128 per
+    // thread and 16 columns, a warp-level store touched 32 rows = 32 L1 wavefronts for 512 bytes; 24 of them per thread
+    // and tile made the epilogue (~10 us per tile against 2.4 us of MMAs) the limiter of the layer GEMM (ncu launch
+    // lists: 37 us per launch whether the contraction ran over K = 640 or 384).
+    constexpr bool TMA_OUT = SPLIT && EPI == UEPI_DN_OUTY;
+    constexpr int OUT_SLAB = 12 * 1024;
+    constexpr int OUT_BYTES = TMA_OUT ? 8 * OUT_SLAB : 0;
+
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_out = smem_al;                               // [8 warps][OUT_SLAB] (TMA_OUT only)
+    uint8_t* smem = smem_al + OUT_BYTES;                       // operand ring
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
@@ -321,6 +334,66 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         store16_hilo(p.out_h + o, p.out_lo + o, v);
                     }
                 }
+            } else if constexpr (TMA_OUT) {
+                // y-recurrence: y = acc + bias + addvec[utterance] + P row -> hi/lo (+ e4m3 pair), staged in this warp's slab
+                // (rows outside the problem or guard rows: zeros — a guard row keeps the value the conv's padding needs)
+                uint8_t* slab = smem_out + (warp - 4) * OUT_SLAB;
+                if (lane == 0) tma_store_wait_read();            // the previous tile's stores have finished reading the slab
+                __syncwarp();
+                const int sw7 = lane & 7, sw3 = (lane >> 1) & 3;
+#pragma unroll
+                for (int c = 0; c < BNH / 16; ++c) {
+                    const int n = n0 + c * 16;
+                    float bia[16], av[16];
+                    load16f(p.bias + n, bia);
+                    if (valid) load16f(p.addvec + (long long)ub * p.addvec_bstride + n, av);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) av[j] = 0.f;
+                    }
+                    uint32_t r[16], r2[16];
+                    tmem_ld16(taddr + h * BNH + c * 16, r);
+                    tmem_ld16(taddr + BN + h * BNH + c * 16, r2);   // cross-term accumulator
+                    tmem_ld_wait();
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint4 u = have_pre ? pre[4 * c + i] : make_uint4(0u, 0u, 0u, 0u);
+                        const float xx[4] = {__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int j = 4 * i + k;
+                            const float a = fmaf(__uint_as_float(r[j]) + __uint_as_float(r2[j]), p.alpha, bia[j]) + av[j] + xx[k];
+                            v[j] = valid ? a : 0.f;
+                        }
+                    }
+                    uint4 h0, h1, l0, l1;
+                    pack16_hilo(v, h0, h1, l0, l1);
+                    uint8_t* rh = slab + lane * 128;
+                    *reinterpret_cast<uint4*>(rh + (((2 * c) ^ sw7) << 4)) = h0;
+                    *reinterpret_cast<uint4*>(rh + (((2 * c + 1) ^ sw7) << 4)) = h1;
+                    *reinterpret_cast<uint4*>(rh + 4096 + (((2 * c) ^ sw7) << 4)) = l0;
+                    *reinterpret_cast<uint4*>(rh + 4096 + (((2 * c + 1) ^ sw7) << 4)) = l1;
+                    if (p.out8_hi) {
+                        uint4 h8, l8;
+                        pack16_f8pair(v, h8, l8);
+                        uint8_t* r8 = slab + 8192 + lane * 64;
+                        *reinterpret_cast<uint4*>(r8 + ((c ^ sw3) << 4)) = h8;
+                        *reinterpret_cast<uint4*>(r8 + 2048 + ((c ^ sw3) << 4)) = l8;
+                    }
+                }
+                fence_proxy_async_smem();                        // generic-proxy writes of the slab -> visible to the TMA store
+                __syncwarp();
+                if (lane == 0 && !(p.dbg & 16)) {
+                    const int r0 = mt * BM + q * 32;
+                    tma_store_3d(&tmO0, slab, n0, r0, 0);
+                    tma_store_3d(&tmO1, slab + 4096, n0, r0, 0);
+                    if (p.out8_hi) {
+                        tma_store_3d(&tmO2, slab + 8192, n0, r0, 0);
+                        tma_store_3d(&tmO3, slab + 8192 + 2048, n0, r0, 0);
+                    }
+                    tma_store_commit();
+                }
             } else {
 #pragma unroll
                 for (int c = 0; c < BNH / 16; ++c) {
@@ -454,6 +527,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (lane == 0) mbar_arrive(&tempty[abuf]);
             abuf ^= 1; if (abuf == 0) aphase ^= 1;
         }
+        if (TMA_OUT && lane == 0) tma_store_wait_all();          // global writes complete before the CTA exits
     }
 
     tc_fence_before();
@@ -472,10 +546,13 @@ template <int BN, int BK, int SPLIT, int EPI = UEPI_VOC>
 int launch_cfg(const UmmaConvParams& p, cudaStream_t s) {
     constexpr int NOP = SPLIT ? 2 : 1;
     constexpr int STAGE_BYTES = NOP * (128 * BK * 2 + BN * BK * 2);
-    constexpr int BUDGET = 200 * 1024;
+    constexpr bool TMA_OUT = SPLIT && EPI == UEPI_DN_OUTY;                    // output tile staged for TMA stores (96 KB)
+    constexpr int OUT_BYTES = TMA_OUT ? 8 * 12 * 1024 : 0;
+    constexpr int BUDGET = (TMA_OUT ? 226 : 200) * 1024 - OUT_BYTES;
     constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
     static_assert(STAGES >= 2, "pipeline needs at least two stages");
-    constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
+    constexpr size_t SMEM = (size_t)OUT_BYTES + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
     auto kern = umma_conv_kernel<BN, BK, SPLIT, STAGES, EPI>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -506,6 +583,19 @@ int launch_cfg(const UmmaConvParams& p, cudaStream_t s) {
             return CMTTS_ERR_CUDA;
         }
     }
+    CUtensorMap o0 = a0, o1 = a0, o2 = a0, o3 = a0;
+    if (TMA_OUT) {
+        // y hi / lo [M][out_ld] fp16: boxes of 64 columns x 32 rows (128B swizzle); the e4m3 pair [M][out8_ld] bytes: 64 x 32 (64B swizzle)
+        bool ok = make_act_map(&o0, p.out_h, p.N, p.M, 1, p.out_ld, (long long)p.M * p.out_ld, 64, 32) &&
+                  make_act_map(&o1, p.out_lo, p.N, p.M, 1, p.out_ld, (long long)p.M * p.out_ld, 64, 32);
+        if (p.out8_hi)
+            ok = ok && make_store_map8(&o2, p.out8_hi, p.N, p.M, 1, p.out8_ld, (long long)p.M * p.out8_ld, 32) &&
+                 make_store_map8(&o3, p.out8_lo, p.N, p.M, 1, p.out8_ld, (long long)p.M * p.out8_ld, 32);
+        if (!ok) {
+            cmtts_set_error("umma_conv: cuTensorMapEncodeTiled failed (output maps)", __FILE__, __LINE__);
+            return CMTTS_ERR_CUDA;
+        }
+    }
     const int tiles = p.B * ((p.M + 127) / 128) * (p.N / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
     if (g_cmtts_prof_on) {
@@ -521,7 +611,7 @@ int launch_cfg(const UmmaConvParams& p, cudaStream_t s) {
                             (p.res_h ? rows * p.N * 2.0 : 0.0) + (p.sum_h ? rows * p.N * 2.0 : 0.0) + (p.x_f32 ? rows * n_out * 4.0 : 0.0) +
                             (double)p.taps * p.N * (p.Cin + (p.a2_hi ? p.Cin2 : 0)) * 2.0 * nop);
     }
-    launch_pdl(kern, grid, 384, SMEM, s, a0, a1, b0, b1, a2, a3, p);
+    launch_pdl(kern, grid, 384, SMEM, s, a0, a1, b0, b1, a2, a3, o0, o1, o2, o3, p);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }
@@ -550,8 +640,10 @@ int launch_umma_conv(const UmmaConvParams& p_in, cudaStream_t s) {
                           ((uintptr_t)p.a2_hi % 16 == 0) && ((uintptr_t)p.a2_lo % 16 == 0),
                           "umma_conv: second operand needs taps == 1, Cin2 % 64 == 0, n_k2 % 128 == 0, 16-byte alignment");
         }
-        CMTTS_REQUIRE(p.epi != UEPI_DN_OUTY || (p.a2_hi && p.out_h && p.out_lo && p.addvec),
-                      "umma_conv: UEPI_DN_OUTY needs the second operand, y hi/lo and addvec");
+        CMTTS_REQUIRE(p.epi != UEPI_DN_OUTY || (p.a2_hi && p.out_h && p.out_lo && p.addvec && p.bias && p.B == 1 && p.rows_per_utt > 0 &&
+                                                ((uintptr_t)p.out_h % 16) == 0 && ((uintptr_t)p.out_lo % 16) == 0 && p.out_ld % 8 == 0 &&
+                                                (!p.out8_hi || (p.out8_lo && ((uintptr_t)p.out8_hi % 16) == 0 && ((uintptr_t)p.out8_lo % 16) == 0 && p.out8_ld % 16 == 0))),
+                      "umma_conv: UEPI_DN_OUTY needs the second operand, bias, addvec, the flattened layout and 16-byte aligned y hi/lo (+ e4m3 pair)");
         CMTTS_REQUIRE(p.a2_diag == 0 || (p.a2_hi && p.a2_diag == p.N && p.n_k2 == p.N && p.a2_diag <= p.Cin2),
                       "umma_conv: a block-diagonal A2 segment must span exactly the N output columns");
         CMTTS_REQUIRE(p.rows_per_utt == 0 || (p.B == 1 && p.rows_per_utt >= 2), "umma_conv: flattened layout needs B == 1");
@@ -746,12 +838,23 @@ conv_post_f16x4_kernel(const __half* __restrict__ x, const float* __restrict__ w
     constexpr int pad = (K - 1) / 2;
     for (int i = threadIdx.x; i < K * C; i += POST4_THREADS) s_w[i] = w[i];
     const __half* xb = x + (long long)b * L * C;
-    for (int i = threadIdx.x; i < ROWS * CPR; i += POST4_THREADS) {
+    // all of a thread's loads are issued before the first shared-memory store: with a load -> store loop each thread
+    // had one 16-byte request in flight and the kernel sat on DRAM latency (1.9 TB/s whatever the inner loop cost)
+    constexpr int NLD = (ROWS * CPR + POST4_THREADS - 1) / POST4_THREADS;
+    uint4 stg[NLD];
+#pragma unroll
+    for (int it = 0; it < NLD; ++it) {
+        const int i = threadIdx.x + it * POST4_THREADS;
         const int r = i / CPR, ch = i - r * CPR;
         const int src = n0 - pad + r;
-        uint4 u = make_uint4(0u, 0u, 0u, 0u);
-        if (src >= 0 && src < L) u = reinterpret_cast<const uint4*>(xb + (long long)src * C)[ch];
-        *reinterpret_cast<uint4*>(s_x + ((r & 3) * QP + (r >> 2)) * PITCH + ch * 16) = u;
+        stg[it] = make_uint4(0u, 0u, 0u, 0u);
+        if (i < ROWS * CPR && src >= 0 && src < L) stg[it] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)src * C) + ch);
+    }
+#pragma unroll
+    for (int it = 0; it < NLD; ++it) {
+        const int i = threadIdx.x + it * POST4_THREADS;
+        const int r = i / CPR, ch = i - r * CPR;
+        if (i < ROWS * CPR) *reinterpret_cast<uint4*>(s_x + ((r & 3) * QP + (r >> 2)) * PITCH + ch * 16) = stg[it];
     }
     __syncthreads();
     const int t = threadIdx.x;

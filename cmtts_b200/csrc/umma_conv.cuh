@@ -66,7 +66,7 @@ struct UmmaConvParams {
     const unsigned char* a8_hi; const unsigned char* a8_lo; const unsigned char* w8_hi; const unsigned char* w8_lo;
     // UEPI_DN_COND / UEPI_DN_OUTY / UEPI_F32 (with out_h + out_lo): also write that e4m3 pair of the output rows (row pitch out8_ld bytes, flattened rows)
     unsigned char* out8_hi; unsigned char* out8_lo; int out8_ld;
-    int dbg;              // experiment bits (CMTTS_UMMA_DBG): 1 = descriptor base_offset, 2 = disable the halo kernel, 128 = disable the gate kernel, 256 = fp16 (not fp8) cross terms in the gate kernel, 512 = no CTA-pair halo kernel
+    int dbg;              // experiment bits (CMTTS_UMMA_DBG): 1 = descriptor base_offset, 2 = disable the halo kernel, 128 = disable the gate kernel, 256 = fp16 (not fp8) cross terms in the gate kernel, 512 = no CTA-pair halo kernel, 1024 = no paired-row ResBlock kernel at C = 32
 };
 
 static inline UmmaConvParams umma_params_default() {
@@ -91,6 +91,9 @@ struct UmmaResblockParams {
     const __half* a;                       // lrelu(y)
     const __half* w1; const float* b1; float t_slope;
     const __half* w2; const float* b2; float alpha2;
+    // C == 32 only, optional: the same weights pair-packed for the two-time-steps-per-row kernel (weights.py:
+    // pair_pack_d1 / pair_pack_taps): w1p = pair_pack_d1(w1) if dil == 1 else pair_pack_taps(w1); w2p = pair_pack_d1(w2)
+    const __half* w1p; const __half* w2p;
     float res_inv_slope;
     const __half* sum_h;                   // optional raw partial sum added before the output activation
     __half* out_h; float out_slope;

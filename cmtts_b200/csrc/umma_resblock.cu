@@ -28,6 +28,20 @@
 // 11-18 epilogue 2 (an epilogue warp's TMEM lane quarter is warp % 4, its column half the warp's position in its
 // group of eight).
 // Both weight sets stay resident in shared memory for the whole persistent loop.
+//
+// PAIRED modes (MODE 1 / 2; C = 32 tensors, kernel instantiated with C = 64).  At C = 32 an M = 128, N = 32, K = 16 MMA
+// spends 32 cycles reading its A slab from shared memory for 16 cycles of math: the tensor pipe cannot exceed 50 % and
+// the plain kernel sat at that cap for k = 7 / 11 (ncu: 644 / 706 TFLOP/s).  Here the (L, 32) tensors are viewed as
+// (L / 2, 64): one 128-byte row holds the time steps 2 r and 2 r + 1, and one accumulator row holds both outputs
+// (N = 64: columns [0, 32) = step 2 r, [32, 64) = step 2 r + 1).  For a dilation-1 conv the two outputs of a row share
+// K - 1 of their K input positions: the conv becomes K + 1 "units" of K = 32 (one per input position e = -h .. h + 1,
+// a 64-byte half row), each with the N = 64 weight block [W[e + h] ; W[e + h - 1]] (zero where the tap does not
+// exist; weights.py: pair_pack_d1) — 2 (K + 1) MMAs per 256 time steps instead of 4 K.  conv2 always has dilation 1;
+// conv1 has it in the first iteration of a ResBlock (MODE 1).  For odd dilations > 1 (MODE 2) the two outputs share
+// no input position: conv1 runs its K taps as two N = 32 MMAs each (the same weight block W[k], input halves at
+// positions 1 + k d and 2 + k d, accumulator columns [0, 32) and [32, 64)) — the MMA time of the plain kernel, but on
+// 128-byte TMA rows and with half as many tiles, epilogue hand-offs and barrier round trips per time step.  Epilogues,
+// rings and the TMA store are those of the C = 64 instantiation on the paired view (bias duplicated).
 #include "umma_common.cuh"
 #include <stdlib.h>
 
@@ -41,6 +55,7 @@ constexpr int T_ROWS_ALLOC = 144;      // 128 + (k_max - 1) rounded to the swizz
 
 struct RbCfg {
     int a_stages, rows_alloc, box_rows, valid, m_tiles, nb, nb2;   // nb2: depth of the conv2-accumulator ring (2..4)
+    int p1d;   // conv1 half-span in rows of the halo tile
     int pf;    // L2 prefetch distance of the halo tiles, in tiles (0 = off; CMTTS_PF)
     int dbg;   // timing ablations (CMTTS_RB_DBG, results become wrong): 1 epilogue 2 does no work, 2 epilogue 1 does no
                // work, 4 no MMAs are issued, 8 no residual read, 16 no output store
@@ -51,7 +66,7 @@ __device__ __forceinline__ float lrelu_inv(float v, float inv_slope) { return fm
 
 constexpr int RB_THREADS = 608;          // 19 warps
 
-template <int C, int TAPS, bool HAS_SUM>
+template <int C, int TAPS, bool HAS_SUM, int MODE>
 __global__ void __launch_bounds__(RB_THREADS, 1)
 umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                      const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmO,
@@ -66,7 +81,12 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     constexpr int O_SLAB = 32 * OROW;
     constexpr bool TMA_STORE = C >= 64;            // C = 32: 32-byte half rows, direct stores
     constexpr int TMEM_COLS = pow2_cols(2 * RB_MAX_NB * C);
-    constexpr int P2 = (TAPS - 1) / 2;
+    static_assert(MODE == 0 || C == 64, "paired modes run on the (L/2, 64) view");
+    constexpr int NBLK = (TAPS + 1) / 2;           // paired modes: weight blocks of two K = 32 units each (128-byte rows)
+    constexpr int W1_BYTES = MODE == 1 ? NBLK * 64 * 128 : MODE == 2 ? NBLK * 32 * 128 : TAPS * W_BLK;
+    constexpr int W2_BYTES = MODE ? NBLK * 64 * 128 : TAPS * W_BLK;
+    // conv2 half-span in rows of the tile: plain (TAPS-1)/2; paired: input positions -h .. h+1 = pair rows -(h+1)/2 .. (h+1)/2
+    constexpr int P2 = MODE ? ((TAPS - 1) / 2 + 1) / 2 : (TAPS - 1) / 2;
     constexpr uint32_t DESC_HI = (uint32_t)((8 * ROW_BYTES) >> 4) | (1u << 14) | ((BK == 64 ? 2u : 4u) << 29);
 
     const int a_alloc = cfg.rows_alloc * ROW_BYTES;
@@ -77,8 +97,8 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint8_t* smT = smA + cfg.a_stages * a_alloc;
     uint8_t* smO = smT + cfg.nb * T_ALLOC;
     uint8_t* smW1 = smO + 8 * O_SLAB;
-    uint8_t* smW2 = smW1 + TAPS * W_BLK;
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(smW2 + TAPS * W_BLK);
+    uint8_t* smW2 = smW1 + W1_BYTES;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smW2 + W2_BYTES);
     uint64_t* a_empty = a_full + RB_MAX_STAGES;
     uint64_t* w_full = a_empty + RB_MAX_STAGES;    // [1]
     uint64_t* acc1_full = w_full + 1;              // [RB_MAX_NB]
@@ -93,7 +113,8 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: warp index provably uniform for ptxas
     const int tiles = p.B * cfg.m_tiles;
-    const int p1d = ((TAPS - 1) / 2) * p.dil;      // conv1 half-span in rows
+    const int p1d = cfg.p1d;                       // conv1 half-span in rows of the tile (plain: (TAPS-1)/2 * dil)
+    const int Lr = MODE ? (p.L >> 1) : p.L;        // rows of the tensors as this kernel sees them
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < RB_MAX_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
@@ -109,7 +130,10 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (threadIdx.x >= 96 && threadIdx.x < 96 + C) { s_b1[threadIdx.x - 96] = p.b1[threadIdx.x - 96]; s_b2[threadIdx.x - 96] = p.b2[threadIdx.x - 96]; }
+    if (threadIdx.x >= 96 && threadIdx.x < 96 + C) {
+        const int ci = MODE ? ((threadIdx.x - 96) & 31) : (threadIdx.x - 96);      // paired: [b | b]
+        s_b1[threadIdx.x - 96] = p.b1[ci]; s_b2[threadIdx.x - 96] = p.b2[ci];
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -123,10 +147,18 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // ======================= producer: resident weights, then one halo tile per output tile =======
         {
             prefetch_tmap(&tmA); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2);
-            mbar_expect_tx_elect(&w_full[0], (uint32_t)(2 * TAPS * W_BLK));
-            for (int tap = 0; tap < TAPS; ++tap) {
-                tma_load_2d_elect(smW1 + tap * W_BLK, &tmW1, &w_full[0], 0, tap * C);
-                tma_load_2d_elect(smW2 + tap * W_BLK, &tmW2, &w_full[0], 0, tap * C);
+            mbar_expect_tx_elect(&w_full[0], (uint32_t)(W1_BYTES + W2_BYTES));
+            if constexpr (MODE == 0) {
+                for (int tap = 0; tap < TAPS; ++tap) {
+                    tma_load_2d_elect(smW1 + tap * W_BLK, &tmW1, &w_full[0], 0, tap * C);
+                    tma_load_2d_elect(smW2 + tap * W_BLK, &tmW2, &w_full[0], 0, tap * C);
+                }
+            } else {
+                constexpr int R1 = MODE == 1 ? 64 : 32;       // rows of one conv1 weight block
+                for (int blk = 0; blk < NBLK; ++blk) {
+                    tma_load_2d_elect(smW1 + blk * R1 * 128, &tmW1, &w_full[0], 0, blk * R1);
+                    tma_load_2d_elect(smW2 + blk * 64 * 128, &tmW2, &w_full[0], 0, blk * 64);
+                }
             }
             pdl_wait();
             int stage = 0; uint32_t phase = 0;
@@ -161,7 +193,8 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             // Issue form: `if (elect_one())` blocks, operands derived from warp-uniform values only (umma_common.cuh)
             const uint32_t tmem_u = make_uniform(tmem_base);
             const uint32_t idesc = make_idesc(BM, C);
-            const uint32_t tap_step1 = make_uniform((uint32_t)((p.dil * ROW_BYTES) >> 4));
+            // rows (plain) or 64-byte positions (paired) between conv1 taps, in 16-byte descriptor units
+            const uint32_t tap_step1 = make_uniform(MODE ? (uint32_t)(p.dil * 4) : (uint32_t)((p.dil * ROW_BYTES) >> 4));
             const uint32_t w1_lo = make_uniform(((smem_u32(smW1) >> 4) & 0x3FFF) | (1u << 16));
             const uint32_t a_base = make_uniform(((smem_u32(smA) >> 4) & 0x3FFF) | (1u << 16));
             const uint32_t a_alloc16 = make_uniform((uint32_t)(a_alloc >> 4));
@@ -176,7 +209,8 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const uint32_t d_tmem = make_uniform(tmem_u + (uint32_t)(b1 * C));
                 const uint32_t a_lo = make_uniform(a_base + (uint32_t)stage * a_alloc16);
                 if (elect_one()) {
-                    if (!(cfg.dbg & 4))
+                    if (!(cfg.dbg & 4)) {
+                    if constexpr (MODE == 0) {
 #pragma unroll
                     for (int tap = 0; tap < TAPS; ++tap) {
 #pragma unroll
@@ -184,6 +218,31 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                             umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | (a_lo + tap * tap_step1 + 2 * k),
                                      ((uint64_t)DESC_HI << 32) | (w1_lo + (uint32_t)((tap * W_BLK) >> 4) + 2 * k), idesc,
                                      (tap | k) ? 1u : 0u);
+                    }
+                    } else if constexpr (MODE == 1) {
+                        // dilation 1, paired: unit u = input position u - h = byte offset (u + 1) * 64 of the halo tile
+#pragma unroll
+                        for (int u = 0; u <= TAPS; ++u) {
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | (a_lo + (uint32_t)((u + 1) * 4 + 2 * k)),
+                                         ((uint64_t)DESC_HI << 32) | (w1_lo + (uint32_t)((u >> 1) * 512 + (u & 1) * 4 + 2 * k)), idesc,
+                                         (u | k) ? 1u : 0u);
+                        }
+                    } else {
+                        // odd dilation > 1, paired: tap j reads positions 1 + j d (even output) and 2 + j d (odd output)
+                        const uint32_t idesc32 = make_idesc(BM, 32);
+#pragma unroll
+                        for (int tap = 0; tap < TAPS; ++tap) {
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                const uint32_t a_e = a_lo + 4u + (uint32_t)tap * tap_step1 + (uint32_t)(2 * k);
+                                const uint64_t bd = ((uint64_t)DESC_HI << 32) | (w1_lo + (uint32_t)((tap >> 1) * 256 + (tap & 1) * 4 + 2 * k));
+                                umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | a_e, bd, idesc32, (tap | k) ? 1u : 0u);
+                                umma_f16(d_tmem + 32u, ((uint64_t)DESC_HI << 32) | (a_e + 4u), bd, idesc32, (tap | k) ? 1u : 0u);
+                            }
+                        }
+                    }
                     }
                     umma_commit(&a_empty[stage]);      // input stage free once conv1 has read it
                     umma_commit(&acc1_full[b1]);
@@ -212,7 +271,8 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const uint32_t d_tmem = make_uniform(tmem_u + (uint32_t)(RB_MAX_NB * C + ab * C));
                 const uint32_t t_lo = make_uniform(t_base + (uint32_t)b2 * (uint32_t)(T_ALLOC >> 4));
                 if (elect_one()) {
-                    if (!(cfg.dbg & 4))
+                    if (!(cfg.dbg & 4)) {
+                    if constexpr (MODE == 0) {
 #pragma unroll
                     for (int tap = 0; tap < TAPS; ++tap) {
 #pragma unroll
@@ -220,6 +280,17 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                             umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | (t_lo + tap * tap_step2 + 2 * k),
                                      ((uint64_t)DESC_HI << 32) | (w2_lo + (uint32_t)((tap * W_BLK) >> 4) + 2 * k), idesc,
                                      (tap | k) ? 1u : 0u);
+                    }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u <= TAPS; ++u) {
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | (t_lo + (uint32_t)((u + 1) * 4 + 2 * k)),
+                                         ((uint64_t)DESC_HI << 32) | (w2_lo + (uint32_t)((u >> 1) * 512 + (u & 1) * 4 + 2 * k)), idesc,
+                                         (u | k) ? 1u : 0u);
+                        }
+                    }
                     }
                     umma_commit(&t_empty[b2]);
                     umma_commit(&acc2_full[ab]);
@@ -249,7 +320,7 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 mbar_wait(&t_empty[bb], ph ^ 1);
                 tc_fence_after();
                 const int trow = mt * cfg.valid - P2 + row;                 // global row of this t row
-                const bool inside = trow >= 0 && trow < p.L;
+                const bool inside = trow >= 0 && trow < Lr;
                 const uint32_t taddr = tmem_base + (uint32_t)(bb * C + n_base) + lane_addr;
                 uint8_t* trow_ptr = smT + bb * T_ALLOC + row * ROW_BYTES;
                 if (!(cfg.dbg & 2))
@@ -299,8 +370,8 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             auto prefetch = [&](int tile_) {
                 const int mt_ = tile_ % cfg.m_tiles, b_ = tile_ / cfg.m_tiles;
                 const int o_ = mt_ * cfg.valid + row;
-                const bool ok = tile_ < tiles && row < cfg.valid && o_ < p.L && !(cfg.dbg & 8);
-                const long long g_ = ((long long)b_ * p.L + o_) * C + n_base;
+                const bool ok = tile_ < tiles && row < cfg.valid && o_ < Lr && !(cfg.dbg & 8);
+                const long long g_ = ((long long)b_ * Lr + o_) * C + n_base;
 #pragma unroll
                 for (int i = 0; i < CH / 8; ++i) {
                     rnext[i] = ok ? reinterpret_cast<const uint4*>(p.a + g_)[i] : make_uint4(0u, 0u, 0u, 0u);
@@ -312,8 +383,8 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
                 const int mt = tile % cfg.m_tiles, b = tile / cfg.m_tiles;
                 const int o = mt * cfg.valid + row;                         // output row of this thread
-                const bool valid = row < cfg.valid && o < p.L;
-                const long long goff = ((long long)b * p.L + o) * C + n_base;
+                const bool valid = row < cfg.valid && o < Lr;
+                const long long goff = ((long long)b * Lr + o) * C + n_base;
                 uint4 rres[CH / 8], rsum[HAS_SUM ? CH / 8 : 1];
 #pragma unroll
                 for (int i = 0; i < CH / 8; ++i) {
@@ -406,12 +477,14 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
 }
 
-template <int C, int TAPS, bool HAS_SUM>
+template <int C, int TAPS, bool HAS_SUM, int MODE>
 int launch_rb_cfg(const UmmaResblockParams& p, cudaStream_t s) {
     constexpr int BK = C;
     constexpr int ROW_BYTES = BK * 2;
     constexpr int ROW_ALIGN = 1024 / ROW_BYTES;
-    constexpr size_t W_BYTES = (size_t)2 * TAPS * C * ROW_BYTES;
+    constexpr int NBLK = (TAPS + 1) / 2;
+    constexpr int R1 = MODE == 1 ? 64 : 32;                // rows of one paired conv1 weight block
+    constexpr size_t W_BYTES = MODE ? (size_t)NBLK * (R1 + 64) * 128 : (size_t)2 * TAPS * C * ROW_BYTES;
     constexpr size_t T_ALLOC = (size_t)T_ROWS_ALLOC * ROW_BYTES;
     constexpr size_t O_BYTES = (size_t)8 * 32 * C;         // 8 epilogue-2 warps x 32 rows x C/2 fp16
     constexpr size_t FIXED = (2 * RB_MAX_STAGES + 1 + 6 * RB_MAX_NB) * 8 + 32 + 2 * C * 4 + 1024;
@@ -419,11 +492,20 @@ int launch_rb_cfg(const UmmaResblockParams& p, cudaStream_t s) {
     static_assert((T_ROWS_ALLOC * ROW_BYTES) % 1024 == 0, "t tile must keep the swizzle alignment");
 
     RbCfg cfg{};
-    cfg.valid = 128 - (TAPS - 1);
-    cfg.box_rows = 128 + (TAPS - 1) * p.dil;
+    constexpr int H = (TAPS - 1) / 2;
+    const int Lr = MODE ? p.L / 2 : p.L;                   // rows as the kernel sees them (paired: two time steps per row)
+    if (MODE) {
+        constexpr int HQ = (H + 1) / 2;                    // pair rows either side of a dilation-1 conv
+        cfg.valid = 128 - 2 * HQ;
+        cfg.p1d = (H * p.dil + 1) / 2;                     // positions -H d .. H d + 1
+    } else {
+        cfg.valid = 128 - (TAPS - 1);
+        cfg.p1d = H * p.dil;
+    }
+    cfg.box_rows = 128 + 2 * cfg.p1d;
     if (cfg.box_rows > 256) return CMTTS_ERR_UNSUPPORTED;
     cfg.rows_alloc = (cfg.box_rows + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
-    cfg.m_tiles = (p.L + cfg.valid - 1) / cfg.valid;
+    cfg.m_tiles = (Lr + cfg.valid - 1) / cfg.valid;
     const size_t a_alloc = (size_t)cfg.rows_alloc * ROW_BYTES;
     // deepest conv1 -> conv2 lag that still leaves room for >= 3 input stages (CMTTS_RB_NB overrides, 2..4)
     static int nb_env = -1;
@@ -450,7 +532,7 @@ int launch_rb_cfg(const UmmaResblockParams& p, cudaStream_t s) {
     cfg.a_stages = (int)(st > RB_MAX_STAGES ? RB_MAX_STAGES : st);
     const size_t smem = rest + (size_t)cfg.a_stages * a_alloc;
 
-    auto kern = umma_resblock_kernel<C, TAPS, HAS_SUM>;
+    auto kern = umma_resblock_kernel<C, TAPS, HAS_SUM, MODE>;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIMIT) != cudaSuccess) {
@@ -460,11 +542,13 @@ int launch_rb_cfg(const UmmaResblockParams& p, cudaStream_t s) {
         attr_done = true;
     }
     CUtensorMap a_map, w1_map, w2_map, o_map, ot_map;
-    const long long bs = (long long)p.L * C;
-    if (!make_act_map(&a_map, p.a, C, p.L, p.B, C, bs, BK, (cfg.dbg & 32) ? 16 : cfg.box_rows) ||
-        !make_w_map(&w1_map, p.w1, C, TAPS * C, BK, C) || !make_w_map(&w2_map, p.w2, C, TAPS * C, BK, C) ||
-        !make_act_map(&o_map, p.out_h, C, p.L, p.B, C, bs, 32, 32) ||              // per-warp box: C/2 (<= 32) channels
-        !make_act_map(&ot_map, p.out_h, C, p.L, p.B, C, bs, 32, cfg.valid - 96)) {
+    const long long bs = (long long)Lr * C;
+    bool ok = make_act_map(&a_map, p.a, C, Lr, p.B, C, bs, BK, (cfg.dbg & 32) ? 16 : cfg.box_rows) &&
+              make_act_map(&o_map, p.out_h, C, Lr, p.B, C, bs, 32, 32) &&              // per-warp box: C/2 (<= 32) channels
+              make_act_map(&ot_map, p.out_h, C, Lr, p.B, C, bs, 32, cfg.valid - 96);
+    if (MODE) ok = ok && make_w_map(&w1_map, p.w1p, 64, NBLK * R1, 64, R1) && make_w_map(&w2_map, p.w2p, 64, NBLK * 64, 64, 64);
+    else ok = ok && make_w_map(&w1_map, p.w1, C, TAPS * C, BK, C) && make_w_map(&w2_map, p.w2, C, TAPS * C, BK, C);
+    if (!ok) {
         cmtts_set_error("umma_resblock: cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
         return CMTTS_ERR_CUDA;
     }
@@ -473,9 +557,9 @@ int launch_rb_cfg(const UmmaResblockParams& p, cudaStream_t s) {
     if (g_cmtts_prof_on) {
         const double rows = (double)p.B * p.L;
         char lbl[96];
-        snprintf(lbl, sizeof(lbl), "umma_resblock<%d> k%d d%d%s (conv1+conv2)", C, p.taps, p.dil, p.sum_h ? " +sum" : "");
-        cmtts_prof_note(lbl, 2.0 * 2.0 * rows * C * C * p.taps,
-                        rows * C * 2.0 * 2.0 + (p.sum_h ? rows * C * 2.0 : 0.0) + 2.0 * p.taps * C * C * 2.0);
+        snprintf(lbl, sizeof(lbl), "umma_resblock<%d%s> k%d d%d%s (conv1+conv2)", p.C, MODE ? ", paired rows" : "", p.taps, p.dil, p.sum_h ? " +sum" : "");
+        cmtts_prof_note(lbl, 2.0 * 2.0 * rows * p.C * p.C * p.taps,
+                        rows * p.C * 2.0 * 2.0 + (p.sum_h ? rows * p.C * 2.0 : 0.0) + 2.0 * p.taps * p.C * p.C * 2.0);
     }
     launch_pdl(kern, grid, RB_THREADS, smem, s, a_map, w1_map, w2_map, o_map, ot_map, p, cfg);
     CMTTS_CHECK_LAUNCH();
@@ -492,15 +576,25 @@ int launch_umma_resblock(const UmmaResblockParams& p, cudaStream_t s) {
     // max / min form of leaky-ReLU: forward slopes in (0, 1], inverse slope >= 1
     if (!(p.t_slope > 0.f && p.t_slope <= 1.f && p.out_slope > 0.f && p.out_slope <= 1.f && p.res_inv_slope >= 1.f))
         return CMTTS_ERR_UNSUPPORTED;
-#define RB_DISPATCH(C_)                                                   \
+#define RB_DISPATCH(C_, MODE_)                                            \
     switch (p.taps) {                                                     \
-        case 3: return p.sum_h ? launch_rb_cfg<C_, 3, true>(p, s) : launch_rb_cfg<C_, 3, false>(p, s);      \
-        case 7: return p.sum_h ? launch_rb_cfg<C_, 7, true>(p, s) : launch_rb_cfg<C_, 7, false>(p, s);      \
-        case 11: return p.sum_h ? launch_rb_cfg<C_, 11, true>(p, s) : launch_rb_cfg<C_, 11, false>(p, s);   \
+        case 3: return p.sum_h ? launch_rb_cfg<C_, 3, true, MODE_>(p, s) : launch_rb_cfg<C_, 3, false, MODE_>(p, s);      \
+        case 7: return p.sum_h ? launch_rb_cfg<C_, 7, true, MODE_>(p, s) : launch_rb_cfg<C_, 7, false, MODE_>(p, s);      \
+        case 11: return p.sum_h ? launch_rb_cfg<C_, 11, true, MODE_>(p, s) : launch_rb_cfg<C_, 11, false, MODE_>(p, s);   \
         default: return CMTTS_ERR_UNSUPPORTED;                            \
     }
-    if (p.C == 32) { RB_DISPATCH(32) }
-    if (p.C == 64) { RB_DISPATCH(64) }
+    if (p.C == 32) {
+        // paired rows (two time steps per 128-byte row): needs the pair-packed weights, an even length, an odd dilation
+        static int pair_env = -1;                              // CMTTS_RB_PAIR=0 or CMTTS_UMMA_DBG bit 1024: the plain C = 32 kernel (A/B)
+        if (pair_env < 0) { const char* e = getenv("CMTTS_RB_PAIR"); pair_env = e ? atoi(e) : 1; }
+        if (g_cmtts_umma_dbg < 0) { const char* e = getenv("CMTTS_UMMA_DBG"); g_cmtts_umma_dbg = e ? atoi(e) : 0; }
+        if (pair_env && !(g_cmtts_umma_dbg & 1024) && p.w1p && p.w2p && (p.L % 2) == 0 && (p.dil % 2) == 1 && ((uintptr_t)p.w1p % 16) == 0 && ((uintptr_t)p.w2p % 16) == 0) {
+            if (p.dil == 1) { RB_DISPATCH(64, 1) }
+            RB_DISPATCH(64, 2)
+        }
+        RB_DISPATCH(32, 0)
+    }
+    if (p.C == 64) { RB_DISPATCH(64, 0) }
 #undef RB_DISPATCH
     return CMTTS_ERR_UNSUPPORTED;
 }

@@ -86,6 +86,36 @@ def conv_w_nk(w: torch.Tensor) -> torch.Tensor:
     return w.permute(2, 0, 1).contiguous()
 
 
+def pair_pack_d1(w_nk: torch.Tensor) -> torch.Tensor:
+    """Dilation-1 conv weights [k][32][32] (conv_w_nk) for the paired-row ResBlock kernel (csrc/umma_resblock.cu, MODE 1
+    and every conv2): a row of the (L/2, 64) view holds the time steps 2r, 2r+1 and yields both outputs.  Unit u = input
+    position u - h (h = (k-1)/2) meets the N = 64 block [W[u] ; W[u-1]] (rows [0,32) -> output 2r, rows [32,64) -> output
+    2r+1; zero where the tap does not exist).  Two units share one 128-byte-row block: -> [(k+1)/2][64][64]."""
+    k, co, ci = w_nk.shape
+    if co != 32 or ci != 32 or k % 2 == 0:
+        raise ValueError("pair_pack_d1: expects [k odd][32][32]")
+    out = torch.zeros((k + 1) // 2, 64, 64, dtype=w_nk.dtype)
+    for u in range(k + 1):
+        c0 = (u & 1) * 32
+        if u < k:
+            out[u >> 1, :32, c0:c0 + 32] = w_nk[u]
+        if u >= 1:
+            out[u >> 1, 32:, c0:c0 + 32] = w_nk[u - 1]
+    return out.contiguous()
+
+
+def pair_pack_taps(w_nk: torch.Tensor) -> torch.Tensor:
+    """Conv weights [k][32][32] for conv1 of the paired-row kernel at odd dilations > 1 (MODE 2): the plain per-tap blocks,
+    two taps per 128-byte-row block -> [(k+1)/2][32][64] (tap j at block j >> 1, columns (j & 1) * 32 ...)."""
+    k, co, ci = w_nk.shape
+    if co != 32 or ci != 32:
+        raise ValueError("pair_pack_taps: expects [k][32][32]")
+    out = torch.zeros((k + 1) // 2, 32, 64, dtype=w_nk.dtype)
+    for j in range(k):
+        out[j >> 1, :, (j & 1) * 32:(j & 1) * 32 + 32] = w_nk[j]
+    return out.contiguous()
+
+
 #: power-of-two pre-scale of hi/lo weight pairs: keeps the `lo` halves (|lo| ~ 2^-11 |w|) out of the fp16
 #: subnormal range, where their absolute spacing (6e-8) would cap the pair at ~18 bits for |w| ~ 0.01.
 #: The kernels multiply the accumulator by 1 / TC_W_SCALE (csrc/pipeline.cu: TC_W_SCALE).
@@ -442,6 +472,23 @@ class PackedHifiGan:
         w_pre[:, :, :hspec.n_mels] = conv_w_nk(sd["conv_pre.weight"])
         hi, lo = split_f16(w_pre)
         t16.add(hi); t16.add(lo)
+        # the 32-channel level once more, pair-packed for the two-time-steps-per-row ResBlock kernel: per (resblock,
+        # iteration) in consumption order {w1p, w2p} (csrc/pipeline.cu: cmtts_hifigan_forward_tc)
+        ch = C0
+        for i in range(len(hspec.upsample_rates)):
+            ch //= 2
+            if ch != 32:
+                continue
+            for j in range(nk):
+                r = i * nk + j
+                for m in range(nd):
+                    w1 = conv_w_nk(sd[f"resblocks.{r}.convs1.{m}.weight"]).to(torch.float16)
+                    w2 = conv_w_nk(sd[f"resblocks.{r}.convs2.{m}.weight"]).to(torch.float16)
+                    k, d = w1.shape[0], hspec.resblock_dilation_sizes[j][m]
+                    if k % 2 == 1 and d % 2 == 1:
+                        t16.add(pair_pack_d1(w1) if d == 1 else pair_pack_taps(w1)); t16.add(pair_pack_d1(w2))
+                    else:
+                        t16.add(None); t16.add(None)
         self.table16 = t16.finish()
         dil = [d for ds in hspec.resblock_dilation_sizes for d in ds]
         # per level: may a tile skip its all-zero tap?  True when the packed transposed conv has 3 taps of which the

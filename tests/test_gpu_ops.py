@@ -176,3 +176,36 @@ def test_vocoder_is_deterministic_and_batch_invariant(B, L):
     assert torch.equal(full[0][:h], lo[0]) and torch.equal(full[1][:h], lo[1])
     hi = voc.run(mel[h:].contiguous(), want_float=True, want_int16=True)
     assert torch.equal(full[0][h:], hi[0]) and torch.equal(full[1][h:], hi[1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,L", [(3, 40), (4, 801)])
+def test_paired_row_resblock_kernel_against_the_plain_one(B, L):
+    """The 32-channel level runs on the two-time-steps-per-row ResBlock kernel (csrc/umma_resblock.cu, MODE 1 / 2); bit
+    1024 of the debug word sends it back to the plain C = 32 kernel.  Same fp16 operands, fp32 accumulation in another
+    order: the two wavs agree to fp16-storage noise, and each is within the vocoder bound of the fp32 FFMA path."""
+    from cmtts_b200 import _lib, synthetic
+    from cmtts_b200.config import HifiGanSpec
+    from cmtts_b200.vocoder import Generator
+    lib = _lib.load()
+    ck = synthetic.make_hifigan_checkpoint(HifiGanSpec(), seed=7)
+    voc = Generator(hspec=HifiGanSpec(), precision="tc").load_state_dict(ck["generator"]).to(DEV)
+    ref = Generator(hspec=HifiGanSpec(), precision="fp32").load_state_dict(ck["generator"]).to(DEV)
+    mel = synthetic.make_mels(B, 80, L, seed=3).transpose(1, 2).contiguous().to(DEV)
+    n0 = lib.cmtts_launch_count()
+    paired = voc.run(mel, want_float=True, want_int16=False)[0].clone()
+    n_paired = lib.cmtts_launch_count() - n0
+    try:
+        lib.cmtts_debug_set(1024, -1)
+        plain = voc.run(mel, want_float=True, want_int16=False)[0].clone()
+    finally:
+        lib.cmtts_debug_set(-1, -1)
+    exact = ref.run(mel, want_float=True, want_int16=False)[0]
+    torch.cuda.synchronize()
+    d_pp = float((paired - plain).abs().max())
+    d_p = float((paired - exact).abs().max())
+    d_q = float((plain - exact).abs().max())
+    print(f"paired-row ResBlock kernel B={B} L={L}: paired vs plain {d_pp:.2e}, paired vs fp32 {d_p:.2e}, plain vs fp32 {d_q:.2e} "
+          f"({n_paired} launches)")
+    assert torch.isfinite(paired).all()
+    assert d_pp <= 2e-3 and d_p <= 4e-3 and d_p <= 2.0 * d_q + 1e-4

@@ -4,14 +4,15 @@ set -u
 TAG=${1:-quick}
 OUT=gpurun_out; mkdir -p $OUT
 nvidia-smi -L
-timeout 1200 python -m pytest tests -m gpu -q -s -x > $OUT/gpu_tests_$TAG.log 2>&1
-tail -6 $OUT/gpu_tests_$TAG.log
+timeout 1200 python -m pytest tests -m gpu -q -s > $OUT/gpu_tests_$TAG.log 2>&1
+grep -E 'paired-row|FAILED|Error|error' $OUT/gpu_tests_$TAG.log | head -20; tail -6 $OUT/gpu_tests_$TAG.log
 timeout 120 python __graft_entry__.py --smoke 2>&1 | tail -1
 run() { name=$1; shift; timeout 300 python bench.py --no-cpu-baseline --steps 20 --warmup 5 "$@" > $OUT/bench_${TAG}_$name.json 2> $OUT/bench_${TAG}_$name.err || tail -c 600 $OUT/bench_${TAG}_$name.err; }
 run C2_T4 --config C2
 run C2_T1 --config C2 --T 1
 run C3 --config C3
 run C5_B32 --config C5 --batch 32
+CMTTS_RB_PAIR=0 run C5_B32_nopair --config C5 --batch 32
 python - <<PY
 import json, glob
 for f in sorted(glob.glob("$OUT/bench_${TAG}_*.json")):
