@@ -660,7 +660,7 @@ extern "C" size_t cmtts_denoiser_tc_workspace_bytes(const cmtts_dims* d, int64_t
 // step and every layer only sees it through a 1x1 projection (blocks.py:675), so everything that depends on it is
 // ONE GEMM over the stacked projection weights (weights.py: cond_stack_weights), run once per batch:
 //     P[0]   = Wc_0 cond + bc_0                       (the conditioner term of y_0)
-//     P[l>0] = (Wc_l - r Wc_{l-1}) cond               (the conditioner term of the y-recurrence below)
+//     P[l>0] = (Wc_l - r Wc_{l-1}) cond + const_l     (the conditioner term and constant bias of the y-recurrence below)
 // as fp32 [layer][flattened row][C].  The per-layer GEMMs of the solver steps then contract over the gate output and y
 // only (K = 384 instead of 640) and add their P row in the epilogue.
 extern "C" size_t cmtts_denoiser_cond_tc_bytes(const cmtts_dims* d, int64_t B, int64_t L) {
@@ -691,6 +691,7 @@ extern "C" int cmtts_denoiser_cond_tc(const cmtts_dims* d, const void* const* w,
     const void* const* wcs = w16 + NLY * 7 + 4 + 3 * (NLY - 1) + 3 + 3 + 2 * NLY;   // {cond stack w hi, lo [NLY*C][H]; bias [NLY*C]}
     UmmaConvParams u = tc_same(HL{c_hi, c_lo}, 1, R, H, wcs[0], wcs[1], (const float*)wcs[2], NLY * C, 1, 1);
     u.rows_per_utt = Lp;
+    u.epi = UEPI_F32_PLANES;                                   // fp32 planes through shared memory + TMA stores
     u.out_f32 = cond_proj; u.out32_bstride = 0; u.out32_ld = C;
     u.out32_ncols = C; u.out32_plane = (long long)R * C;
     CMTTS_TRY(launch_umma_conv(u, s));
@@ -806,7 +807,7 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
             u.a2_hi = y_hi; u.a2_lo = y_lo; u.a2_bstride = (long long)R * C; u.a2_ld = C;
             u.Cin2 = C; u.n_k2 = C; u.a2_diag = C;
             u.w_hi = (const __half*)wf[3 * l]; u.w_lo = (const __half*)wf[3 * l + 1];
-            u.bias = (const float*)wf[3 * l + 2];
+            u.bias = nullptr;                                  // the GEMM's constant bias (wf[3 l + 2]) is part of P_{l+1}
             u.addvec = yc + (long long)l * C; u.addvec_bstride = (long long)(NLY - 1) * C;
             u.x_f32 = const_cast<float*>(cond_proj) + (long long)(l + 1) * PL; u.x_bstride = 0; u.x_ld = C;
             u.out_h = y_hi; u.out_lo = y_lo; u.out_bstride = (long long)R * C; u.out_ld = C;

@@ -333,6 +333,18 @@ static inline bool make_act_map8(CUtensorMap* m, const unsigned char* base, int 
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+// fp32 planes [P][L][C] as the TARGET of TMA stores: box {32 floats (128 bytes), box_rows, 1}, 128B swizzle
+static inline bool make_store_map_f32(CUtensorMap* m, float* base, int C, int L, int P, int ld, long long pstride, int box_rows) {
+    auto enc = get_encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)P};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)pstride * 4};
+    cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, 1u};
+    cuuint32_t es[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 // byte tensors [B][L][C] as the TARGET of 64-byte-wide TMA stores: box {64 bytes, box_rows, 1}, 64B swizzle
 static inline bool make_store_map8(CUtensorMap* m, unsigned char* base, int C, int L, int B, int ld, long long bstride, int box_rows) {
     auto enc = get_encode_fn();

@@ -111,8 +111,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // and tile made the epilogue (~10 us per tile against 2.4 us of MMAs) the limiter of the layer GEMM (ncu launch
     // lists: 37 us per launch whether the contraction ran over K = 640 or 384).
     constexpr bool TMA_OUT = SPLIT && EPI == UEPI_DN_OUTY;
-    constexpr int OUT_SLAB = 12 * 1024;
-    constexpr int OUT_BYTES = TMA_OUT ? 8 * OUT_SLAB : 0;
+    constexpr bool TMA_F32 = SPLIT && EPI == UEPI_F32_PLANES;   // fp32 planes: per warp two boxes of 32 columns x 32 rows (8 KB)
+    constexpr int OUT_SLAB = TMA_F32 ? 8 * 1024 : 12 * 1024;
+    constexpr int OUT_BYTES = (TMA_OUT || TMA_F32) ? 8 * OUT_SLAB : 0;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -334,26 +335,72 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         store16_hilo(p.out_h + o, p.out_lo + o, v);
                     }
                 }
+            } else if constexpr (TMA_F32) {
+                uint8_t* slab = smem_out + (warp - 4) * OUT_SLAB;
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+                const int sw7 = lane & 7;
+                float bia[16], bian[16];
+                load16f(p.bias + n0, bia);
+#pragma unroll
+                for (int c = 0; c < BNH / 16; ++c) {
+                    uint32_t r[16], r2[16];
+                    tmem_ld16(taddr + h * BNH + c * 16, r);
+                    tmem_ld16(taddr + BN + h * BNH + c * 16, r2);
+                    if (c + 1 < BNH / 16) load16f(p.bias + n0 + (c + 1) * 16, bian);
+                    tmem_ld_wait();
+                    uint8_t* rp = slab + (c >> 1) * 4096 + lane * 128;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 u;
+                        u.x = __float_as_uint(fmaf(__uint_as_float(r[4 * i]) + __uint_as_float(r2[4 * i]), p.alpha, bia[4 * i]));
+                        u.y = __float_as_uint(fmaf(__uint_as_float(r[4 * i + 1]) + __uint_as_float(r2[4 * i + 1]), p.alpha, bia[4 * i + 1]));
+                        u.z = __float_as_uint(fmaf(__uint_as_float(r[4 * i + 2]) + __uint_as_float(r2[4 * i + 2]), p.alpha, bia[4 * i + 2]));
+                        u.w = __float_as_uint(fmaf(__uint_as_float(r[4 * i + 3]) + __uint_as_float(r2[4 * i + 3]), p.alpha, bia[4 * i + 3]));
+                        *reinterpret_cast<uint4*>(rp + ((((c & 1) * 4 + i) ^ sw7) << 4)) = u;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) bia[j] = bian[j];
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && !(p.dbg & 16)) {
+                    const int r0 = mt * BM + q * 32;
+                    const int pl = n0 / p.out32_ncols, col = n0 - pl * p.out32_ncols;
+                    tma_store_3d(&tmO0, slab, col, r0, pl);
+                    tma_store_3d(&tmO0, slab + 4096, col + 32, r0, pl);
+                    tma_store_commit();
+                }
             } else if constexpr (TMA_OUT) {
-                // y-recurrence: y = acc + bias + addvec[utterance] + P row -> hi/lo (+ e4m3 pair), staged in this warp's slab
-                // (rows outside the problem or guard rows: zeros — a guard row keeps the value the conv's padding needs)
+                // y-recurrence: y = acc + addvec[utterance] + P row -> hi/lo (+ e4m3 pair), staged in this warp's slab
+                // (rows outside the problem or guard rows: zeros — a guard row keeps the value the conv's padding needs).
+                // The P row streams from DRAM (each layer has its own plane): the rows of this CTA's NEXT tile are pulled
+                // into L2 now, one tile ahead of the register loads above (ncu: with the loads issued only when the tile
+                // begins, their DRAM latency sat in front of every tile's epilogue, which bounded the kernel).
+                {
+                    TileSched tn = ts;
+                    int nt2, mt2, b2; bool heavy2;
+                    if (tn.next(nt2, mt2, b2, heavy2)) {
+                        const int t2 = mt2 * BM + row;
+                        if (t2 < p.M && p.x_f32 != nullptr) {
+                            const float* pn = p.x_f32 + (long long)t2 * p.x_ld + nt2 * BN + h * BNH;
+                            prefetch_l2(pn); prefetch_l2(pn + 32);
+                        }
+                    }
+                }
                 uint8_t* slab = smem_out + (warp - 4) * OUT_SLAB;
                 if (lane == 0) tma_store_wait_read();            // the previous tile's stores have finished reading the slab
                 __syncwarp();
                 const int sw7 = lane & 7, sw3 = (lane >> 1) & 3;
+                const float* avp = p.addvec + (long long)ub * p.addvec_bstride + n0;
+                float av[16], avn[16];
+                if (valid) load16f(avp, av);
 #pragma unroll
                 for (int c = 0; c < BNH / 16; ++c) {
-                    const int n = n0 + c * 16;
-                    float bia[16], av[16];
-                    load16f(p.bias + n, bia);
-                    if (valid) load16f(p.addvec + (long long)ub * p.addvec_bstride + n, av);
-                    else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) av[j] = 0.f;
-                    }
                     uint32_t r[16], r2[16];
                     tmem_ld16(taddr + h * BNH + c * 16, r);
                     tmem_ld16(taddr + BN + h * BNH + c * 16, r2);   // cross-term accumulator
+                    if (valid && c + 1 < BNH / 16) load16f(avp + (c + 1) * 16, avn);   // next chunk's vector, behind the TMEM loads
                     tmem_ld_wait();
                     float v[16];
 #pragma unroll
@@ -363,10 +410,12 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const int j = 4 * i + k;
-                            const float a = fmaf(__uint_as_float(r[j]) + __uint_as_float(r2[j]), p.alpha, bia[j]) + av[j] + xx[k];
+                            const float a = fmaf(__uint_as_float(r[j]) + __uint_as_float(r2[j]), p.alpha, av[j]) + xx[k];
                             v[j] = valid ? a : 0.f;
                         }
                     }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) av[j] = avn[j];
                     uint4 h0, h1, l0, l1;
                     pack16_hilo(v, h0, h1, l0, l1);
                     uint8_t* rh = slab + lane * 128;
@@ -527,7 +576,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (lane == 0) mbar_arrive(&tempty[abuf]);
             abuf ^= 1; if (abuf == 0) aphase ^= 1;
         }
-        if (TMA_OUT && lane == 0) tma_store_wait_all();          // global writes complete before the CTA exits
+        if ((TMA_OUT || TMA_F32) && lane == 0) tma_store_wait_all();   // global writes complete before the CTA exits
     }
 
     tc_fence_before();
@@ -547,8 +596,9 @@ int launch_cfg(const UmmaConvParams& p, cudaStream_t s) {
     constexpr int NOP = SPLIT ? 2 : 1;
     constexpr int STAGE_BYTES = NOP * (128 * BK * 2 + BN * BK * 2);
     constexpr bool TMA_OUT = SPLIT && EPI == UEPI_DN_OUTY;                    // output tile staged for TMA stores (96 KB)
-    constexpr int OUT_BYTES = TMA_OUT ? 8 * 12 * 1024 : 0;
-    constexpr int BUDGET = (TMA_OUT ? 226 : 200) * 1024 - OUT_BYTES;
+    constexpr bool TMA_F32 = SPLIT && EPI == UEPI_F32_PLANES;                 // fp32 planes staged for TMA stores (64 KB)
+    constexpr int OUT_BYTES = TMA_OUT ? 8 * 12 * 1024 : TMA_F32 ? 8 * 8 * 1024 : 0;
+    constexpr int BUDGET = ((TMA_OUT || TMA_F32) ? 226 : 200) * 1024 - OUT_BYTES;
     constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
     static_assert(STAGES >= 2, "pipeline needs at least two stages");
     constexpr size_t SMEM = (size_t)OUT_BYTES + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
@@ -596,6 +646,10 @@ int launch_cfg(const UmmaConvParams& p, cudaStream_t s) {
             return CMTTS_ERR_CUDA;
         }
     }
+    if (TMA_F32 && !make_store_map_f32(&o0, p.out_f32, p.out32_ncols, p.M, p.N / p.out32_ncols, p.out32_ld, p.out32_plane, 32)) {
+        cmtts_set_error("umma_conv: cuTensorMapEncodeTiled failed (fp32 plane map)", __FILE__, __LINE__);
+        return CMTTS_ERR_CUDA;
+    }
     const int tiles = p.B * ((p.M + 127) / 128) * (p.N / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
     if (g_cmtts_prof_on) {
@@ -640,18 +694,22 @@ int launch_umma_conv(const UmmaConvParams& p_in, cudaStream_t s) {
                           ((uintptr_t)p.a2_hi % 16 == 0) && ((uintptr_t)p.a2_lo % 16 == 0),
                           "umma_conv: second operand needs taps == 1, Cin2 % 64 == 0, n_k2 % 128 == 0, 16-byte alignment");
         }
-        CMTTS_REQUIRE(p.epi != UEPI_DN_OUTY || (p.a2_hi && p.out_h && p.out_lo && p.addvec && p.bias && p.B == 1 && p.rows_per_utt > 0 &&
+        CMTTS_REQUIRE(p.epi != UEPI_DN_OUTY || (p.a2_hi && p.out_h && p.out_lo && p.addvec && !p.bias && p.B == 1 && p.rows_per_utt > 0 &&
                                                 ((uintptr_t)p.out_h % 16) == 0 && ((uintptr_t)p.out_lo % 16) == 0 && p.out_ld % 8 == 0 &&
                                                 (!p.out8_hi || (p.out8_lo && ((uintptr_t)p.out8_hi % 16) == 0 && ((uintptr_t)p.out8_lo % 16) == 0 && p.out8_ld % 16 == 0))),
-                      "umma_conv: UEPI_DN_OUTY needs the second operand, bias, addvec, the flattened layout and 16-byte aligned y hi/lo (+ e4m3 pair)");
+                      "umma_conv: UEPI_DN_OUTY needs the second operand, addvec, no bias (it belongs to the P plane), the flattened layout and 16-byte aligned y hi/lo (+ e4m3 pair)");
         CMTTS_REQUIRE(p.a2_diag == 0 || (p.a2_hi && p.a2_diag == p.N && p.n_k2 == p.N && p.a2_diag <= p.Cin2),
                       "umma_conv: a block-diagonal A2 segment must span exactly the N output columns");
         CMTTS_REQUIRE(p.rows_per_utt == 0 || (p.B == 1 && p.rows_per_utt >= 2), "umma_conv: flattened layout needs B == 1");
         CMTTS_REQUIRE(!p.a_tap_dim || (p.B == 1 && !p.a2_hi), "umma_conv: a_tap_dim needs B == 1 and no second operand");
         CMTTS_REQUIRE(!p.io_unguard || (p.rows_per_utt > 0 && p.epi == UEPI_F32 && p.n_valid % 16 == 0),
                       "umma_conv: io_unguard needs the flattened layout, the generic epilogue and n_valid % 16 == 0");
-        CMTTS_REQUIRE(p.out32_ncols == 0 || (p.epi == UEPI_F32 && p.out32_ncols % 16 == 0 && p.out_f32 != nullptr),
+        CMTTS_REQUIRE(p.out32_ncols == 0 || ((p.epi == UEPI_F32 || p.epi == UEPI_F32_PLANES) && p.out32_ncols % 16 == 0 && p.out_f32 != nullptr),
                       "umma_conv: out32_ncols needs the generic epilogue, an fp32 output and a multiple of 16");
+        CMTTS_REQUIRE(p.epi != UEPI_F32_PLANES || (p.B == 1 && p.bias && p.out_f32 && ((uintptr_t)p.out_f32 % 16) == 0 && p.out32_ncols > 0 &&
+                                                   p.out32_ncols % 64 == 0 && p.N % p.out32_ncols == 0 && p.out32_ld % 4 == 0 && p.out32_plane % 4 == 0 &&
+                                                   !p.a2_hi && !p.out_h && !p.addvec && !p.x_f32 && !p.lens && p.act == ACT_NONE && p.beta == 1.f),
+                      "umma_conv: UEPI_F32_PLANES is acc * alpha + bias into fp32 column planes of a flattened problem, nothing else");
         CMTTS_REQUIRE(p.out8_hi == nullptr || (p.out8_lo && p.out_h && p.out_lo && p.rows_per_utt > 0),
                       "umma_conv: the e4m3 output pair needs the hi/lo output and the flattened layout");
         CMTTS_REQUIRE(p.x_f32 == nullptr || ((uintptr_t)p.x_f32 % 16 == 0 && p.x_ld % 4 == 0 && p.x_bstride % 4 == 0),
@@ -669,6 +727,7 @@ int launch_umma_conv(const UmmaConvParams& p_in, cudaStream_t s) {
             case UEPI_DN_OUT: return launch_cfg<128, 64, 1, UEPI_DN_OUT>(p, s);
             case UEPI_DN_OUTY: return launch_cfg<128, 64, 1, UEPI_DN_OUTY>(p, s);
             case UEPI_F32: return launch_cfg<128, 64, 1, UEPI_F32>(p, s);
+            case UEPI_F32_PLANES: return launch_cfg<128, 64, 1, UEPI_F32_PLANES>(p, s);
             default: CMTTS_REQUIRE(false, "umma_conv: unknown split-mode epilogue");
         }
     }

@@ -12,6 +12,8 @@ enum UmmaEpi {
     UEPI_DN_OUTY = 5,  // y-recurrence of the residual stack (see pipeline.cu): y = acc + bias + addvec[utterance]
                        // + x_f32[row] (the layer's precomputed conditioner projection, fp32, read ahead of the
                        // accumulator wait) -> fp16 hi/lo, written in place over the y operand (out_h/out_lo)
+    UEPI_F32_PLANES = 6,  // v = acc*alpha + bias as fp32 into a stack of column planes (out_f32, out32_ncols, out32_plane),
+                       // staged in shared memory and TMA-stored; nothing else (the per-batch conditioner GEMM)
     UEPI_F32 = 4,      // generic: v = act((acc*alpha + bias) * beta) + addvec[b] + res*res_scale ; v *= out_scale ;
                        // rows >= lens[b] -> 0 ; written as fp32 (out_f32) and/or fp16 hi/lo ; cols >= n_valid dropped
 };

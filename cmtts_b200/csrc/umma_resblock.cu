@@ -10,9 +10,12 @@
 //     rows outside the utterance are written as zeros (conv2 zero-pads t, not c1(padding));
 //   * conv2 (dilation 1) reads that tile, again by row offsets; each tile yields 128 - (k-1) valid
 //     output rows (92-98 % of the MMA rows);
-//   * the residual y is re-read from global memory (L2-hot: the TMA just fetched the same rows) into
-//     registers BEFORE the accumulator wait (stored as lrelu(y), inverted exactly in the epilogue); the
-//     output is staged in the TMA box layout and TMA-stored.
+//   * the residual y comes from the input halo tile itself (its rows P2 + p1d .. are the output rows; stored as
+//     lrelu(y), inverted exactly in the epilogue): an input stage stays allocated until epilogue 2 of its tile
+//     has read them.  (It used to be re-read from global memory one tile ahead, "L2-hot" — ncu showed 60 % of
+//     those reads going to DRAM, 660 MB read per launch for 416 MB of input, and the epilogue-2 warps waiting on
+//     them 40 % of their time: ~10 tiles x 148 CTAs x 64 KB of traffic pass between the TMA load of a tile and its
+//     epilogue 2, about the size of the L2.)  The output is staged in the TMA box layout and TMA-stored.
 // HBM traffic per iteration: read y once (+halo), write y' once.
 //
 // Pipelining: conv2 of a tile can only start after conv1 -> commit -> epilogue 1 -> t tile, a chain of
@@ -22,7 +25,7 @@
 // quarter x column half): a lone warp per SM sub-partition issues its dependent ALU chain at ~4 cycles per
 // instruction, which made the epilogues (not HBM, not the tensor pipe) the limiter (ncu: MMA warp stalled on
 // acc2_empty, epilogue-2 warps > 80 % busy).  Biases sit in shared memory; leaky-ReLU is max / min(v, s v).
-// The input stage is released by the conv1 commit.
+// An input stage is released by the conv1 commit AND the eight epilogue-2 warps (9 arrivals).
 //
 // Roles (608 threads): warp 0 TMEM allocator + TMA producer, 1 conv1 issuer, 2 conv2 issuer, 3-10 epilogue 1,
 // 11-18 epilogue 2 (an epilogue warp's TMEM lane quarter is warp % 4, its column half the warp's position in its
@@ -117,7 +120,7 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int Lr = MODE ? (p.L >> 1) : p.L;        // rows of the tensors as this kernel sees them
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < RB_MAX_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < RB_MAX_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 9); }   // conv1 commit + 8 epilogue-2 warps
         mbar_init(&w_full[0], 1);
         for (int i = 0; i < RB_MAX_NB; ++i) {
             mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], 8);
@@ -362,23 +365,25 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             // ---- epilogue 2: y' = lrelu_out(c2 + b2 + inv_lrelu(a) [+ sum]) -> staged + TMA store (direct for C = 32)
             const int swo = (OROW == 64) ? ((lane >> 1) & 3) : (lane & 1);
             uint8_t* slab = smO + ew * O_SLAB + lane * OROW;
-            // residual lrelu(y) [+ MRF partial sum] of this thread's output row: global reads (L2-hot: the rows were
-            // fetched by the tile's TMA a moment ago), software-pipelined ONE TILE AHEAD so that their latency never
-            // sits between the accumulator wait and the stores
-            constexpr bool PIPE_SUM = HAS_SUM && C == 32;     // C = 64: not enough registers to pipeline the sum too
-            uint4 rnext[CH / 8], snext[PIPE_SUM ? CH / 8 : 1];
+            // MRF partial sum of this thread's output row: global reads, software-pipelined ONE TILE AHEAD so that their
+            // latency never sits between the accumulator wait and the stores.  The residual lrelu(y) is read from the
+            // input stage in shared memory (rows P2 + p1d + row of the halo tile, swizzled like the TMA wrote them).
+            uint4 snext[HAS_SUM ? CH / 8 : 1];
             auto prefetch = [&](int tile_) {
-                const int mt_ = tile_ % cfg.m_tiles, b_ = tile_ / cfg.m_tiles;
-                const int o_ = mt_ * cfg.valid + row;
-                const bool ok = tile_ < tiles && row < cfg.valid && o_ < Lr && !(cfg.dbg & 8);
-                const long long g_ = ((long long)b_ * Lr + o_) * C + n_base;
+                if constexpr (HAS_SUM) {
+                    const int mt_ = tile_ % cfg.m_tiles, b_ = tile_ / cfg.m_tiles;
+                    const int o_ = mt_ * cfg.valid + row;
+                    const bool ok = tile_ < tiles && row < cfg.valid && o_ < Lr;
+                    const long long g_ = ((long long)b_ * Lr + o_) * C + n_base;
 #pragma unroll
-                for (int i = 0; i < CH / 8; ++i) {
-                    rnext[i] = ok ? reinterpret_cast<const uint4*>(p.a + g_)[i] : make_uint4(0u, 0u, 0u, 0u);
-                    if constexpr (PIPE_SUM) snext[i] = ok ? reinterpret_cast<const uint4*>(p.sum_h + g_)[i] : make_uint4(0u, 0u, 0u, 0u);
+                    for (int i = 0; i < CH / 8; ++i)
+                        snext[i] = ok ? reinterpret_cast<const uint4*>(p.sum_h + g_)[i] : make_uint4(0u, 0u, 0u, 0u);
                 }
             };
             prefetch((int)blockIdx.x);
+            const int arow = row + P2 + p1d;                                // this thread's row of the input halo tile
+            const int asw = (BK == 64) ? (arow & 7) : ((arow >> 1) & 3);
+            int st = 0; uint32_t sph = 0;                                   // input-stage ring position of the tile
             int bb = 0; uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
                 const int mt = tile % cfg.m_tiles, b = tile / cfg.m_tiles;
@@ -386,11 +391,17 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const bool valid = row < cfg.valid && o < Lr;
                 const long long goff = ((long long)b * Lr + o) * C + n_base;
                 uint4 rres[CH / 8], rsum[HAS_SUM ? CH / 8 : 1];
+                mbar_wait(&a_full[st], sph);                                // (long complete: conv1 of this tile has run)
+                {
+                    const uint8_t* ap = smA + st * a_alloc + arow * ROW_BYTES;
+#pragma unroll
+                    for (int i = 0; i < CH / 8; ++i)
+                        rres[i] = (cfg.dbg & 8) ? make_uint4(0u, 0u, 0u, 0u)
+                                                : *reinterpret_cast<const uint4*>(ap + (((n_base / 8 + i) ^ asw) << 4));
+                }
 #pragma unroll
                 for (int i = 0; i < CH / 8; ++i) {
-                    rres[i] = rnext[i];
-                    if constexpr (PIPE_SUM) rsum[i] = snext[i];
-                    else if constexpr (HAS_SUM) rsum[i] = valid ? reinterpret_cast<const uint4*>(p.sum_h + goff)[i] : make_uint4(0u, 0u, 0u, 0u);
+                    if constexpr (HAS_SUM) rsum[i] = snext[i];
                 }
                 prefetch(tile + (int)gridDim.x);
                 mbar_wait(&acc2_full[bb], ph);
@@ -455,6 +466,7 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(&acc2_empty[bb]);
+                    mbar_arrive(&a_empty[st]);      // residual rows consumed (their values went through the adds above)
                     if (TMA_STORE && !(cfg.dbg & 17)) {
                         // rows [q*32, q*32+32) of the tile; the last lane quarter only owns `valid - 96` rows
                         const int r0 = mt * cfg.valid + q * 32;
@@ -464,6 +476,7 @@ umma_resblock_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     }
                 }
                 if (++bb == cfg.nb2) { bb = 0; ph ^= 1; }
+                if (++st == cfg.a_stages) { st = 0; sph ^= 1; }
             }
             if (TMA_STORE && lane == 0) tma_store_wait_all();
         }
@@ -507,7 +520,9 @@ int launch_rb_cfg(const UmmaResblockParams& p, cudaStream_t s) {
     cfg.rows_alloc = (cfg.box_rows + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
     cfg.m_tiles = (Lr + cfg.valid - 1) / cfg.valid;
     const size_t a_alloc = (size_t)cfg.rows_alloc * ROW_BYTES;
-    // deepest conv1 -> conv2 lag that still leaves room for >= 3 input stages (CMTTS_RB_NB overrides, 2..4)
+    // An input stage lives from its TMA load to the end of epilogue 2 of its tile (the residual is read from it), i.e.
+    // across the whole conv1 -> epilogue 1 -> conv2 -> epilogue 2 chain: the deepest conv1 -> conv2 lag nb that still
+    // leaves nb + 2 input stages, else nb = 2 with at least 2 (CMTTS_RB_NB overrides, 2..4)
     static int nb_env = -1;
     if (nb_env < 0) { const char* e = getenv("CMTTS_RB_NB"); nb_env = e ? atoi(e) : 0; }
     cfg.nb = 0;
@@ -515,7 +530,7 @@ int launch_rb_cfg(const UmmaResblockParams& p, cudaStream_t s) {
     for (int nb = RB_MAX_NB; nb >= 2; --nb) {
         if (nb_env >= 2 && nb_env <= RB_MAX_NB && nb != nb_env) continue;
         rest = W_BYTES + (size_t)nb * T_ALLOC + O_BYTES + FIXED;
-        const size_t min_stages = (nb == 2 || nb == nb_env) ? 2 : 3;
+        const size_t min_stages = (nb == 2 || nb == nb_env) ? 2 : (size_t)nb + 2;
         if (rest + min_stages * a_alloc <= LIMIT) { cfg.nb = nb; break; }
     }
     if (cfg.nb == 0) return CMTTS_ERR_UNSUPPORTED;

@@ -177,14 +177,16 @@ def cond_stack_weights(sd: Dict[str, torch.Tensor], n_layers: int, C: int, H: in
     """Everything the residual stack needs from the conditioner, as ONE GEMM per batch (csrc/pipeline.cu,
     cmtts_denoiser_cond_tc): weights (n_layers * C, H) and bias (n_layers * C,)  (fp64).  Row block 0 is layer 0's
     conditioner projection Wc_0 (+ bc_0): the conditioner term of y_0; row block l > 0 is the conditioner block
-    Wc_l - r Wc_{l-1} of fused_recurrence_weights(l - 1) (its bias stays with the recurrence GEMM)."""
+    Wc_l - r Wc_{l-1} of fused_recurrence_weights(l - 1) together with that GEMM's constant bias (the layer GEMMs of
+    the solver steps then add one fp32 plane and the per-utterance step vector, nothing else)."""
     p0 = "net.residual_layers.0.conditioner_projection.conv."
     ws = [sd[p0 + "weight"][:, :, 0].double()]
     b = torch.zeros(n_layers * C, dtype=torch.float64)
     b[:C] = sd[p0 + "bias"].double()
     for l in range(n_layers - 1):
-        wf, _ = fused_recurrence_weights(sd, l, C, H)
+        wf, bf = fused_recurrence_weights(sd, l, C, H)
         ws.append(wf[:, 2 * C:])
+        b[(l + 1) * C:(l + 2) * C] = bf
     return torch.cat(ws, dim=0), b
 
 
