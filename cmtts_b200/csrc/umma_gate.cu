@@ -638,7 +638,12 @@ __device__ __forceinline__ void gx2_arrive_leader(uint64_t* bar) {
 // that frees goes into DEEPER weight rings: the one-CTA kernel's 3 / 2 stages cover only ~0.5 us of tensor-pipe work, less
 // than one L2 round trip, which (not the operand bytes) is what holds it at ~57 us per launch.
 constexpr int GX2_WB = G_B_BYTES / 2;                 // one half block: 64 rows x 128 bytes
-constexpr int GX2_W16_STAGES = 6, GX2_W8_STAGES = 3;
+// (W16 ring: 4 stages, was 6 — the 16 KB go to the epilogue's output staging; the profile that asked for deeper rings was
+// taken while the epilogue warps, spilling their bias arrays, hid everything else)
+constexpr int GX2_W16_STAGES = 4, GX2_W8_STAGES = 3;
+constexpr int GX2_OUT_SLAB = 4096;                    // per epilogue warp: g hi | g lo boxes of 32 columns x 32 rows
+constexpr int GX2_OUT_BYTES = 8 * GX2_OUT_SLAB;
+constexpr int GX2_MAX_N = 512;                        // bias staged in shared memory
 constexpr int GX2_W8_STAGE = 2 * GX2_WB;
 
 template <int TAPS>
@@ -646,6 +651,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1)
 umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant__ CUtensorMap tmA8h,
                   const __grid_constant__ CUtensorMap tmA8l, const __grid_constant__ CUtensorMap tmW16,
                   const __grid_constant__ CUtensorMap tmW8h, const __grid_constant__ CUtensorMap tmW8l,
+                  const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
                   const UmmaConvParams p, const int rows_alloc, const int box_rows) {
     constexpr int BM = G_BM, BN = G_BN;
     constexpr int CB = 4, CB8 = 2;                    // 256 channels: four 64-channel fp16 blocks / two 128-channel e4m3 blocks
@@ -659,7 +665,8 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* smA16 = smem;
+    uint8_t* smOut = smem;                            // [8 warps][GX2_OUT_SLAB], 1024-byte aligned slabs
+    uint8_t* smA16 = smOut + GX2_OUT_BYTES;
     uint8_t* smW16 = smA16 + G8_A16_STAGES * a_half;
     uint8_t* smA8 = smW16 + GX2_W16_STAGES * GX2_WB;
     uint8_t* smW8 = smA8 + G8_A8_STAGES * a8_stage;
@@ -674,9 +681,14 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
     uint64_t* tfull = w8_empty + GX2_W8_STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // [p.N]
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int rank = (int)gx2_ctarank();              // 0 = leader of the CTA pair
+    // bias (constant weights: no dependency on the previous kernel) -> shared memory.  Held in registers (64 per
+    // thread) it pushed the epilogue over the 128-register cap: spills (LDL in the element loops), the 8 epilogue
+    // warps 93 % busy and the MMA issuers waiting for accumulators (ncu).
+    for (int i = threadIdx.x; i < p.N; i += G8_THREADS) s_bias[i] = p.bias[i];
     const int m_tiles = (p.M + BM - 1) / BM;
     const int m_pairs = (m_tiles + 1) / 2;            // a pair covers 256 rows: row tile 2 * mp + rank per CTA
     const int n_tiles = p.N / BN;
@@ -863,34 +875,33 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
             }
         }
     } else if (warp >= 4 && warp < 12) {
-        // ================= epilogue (UEPI_DN_GATE), as umma_gate_kernel's, cross accumulator scaled by 2^-11 =================
+        // ================= epilogue (UEPI_DN_GATE): cross accumulator scaled by 2^-11, gate math, g as fp16 hi/lo =================
+        // staged per warp as two boxes of 32 columns x 32 rows (64-byte rows, 64B swizzle) and TMA-stored: a direct
+        // STG.128 per thread touches 32 rows = 32 L1 wavefronts per warp instruction (see umma_conv.cu, UEPI_DN_OUTY).
+        // Rows outside the problem and guard rows are written as zeros (nothing consumes them).
         constexpr int GH = BN / 4;
         const int q = warp & 3;
         const int h = (warp - 4) >> 2;
         const int row = q * 32 + lane;
+        uint8_t* slab = smOut + (warp - 4) * GX2_OUT_SLAB;
+        uint8_t* srow = slab + lane * 64;
+        const int sw3 = (lane >> 1) & 3;
         int abuf = 0; uint32_t tphase = 0;
         for (int tile = first; tile < tiles; tile += stride) {
             const int nt = tile % n_tiles, rest = tile / n_tiles;
-            const int mt = 2 * (rest % m_pairs) + rank, b = rest / m_pairs;
+            const int mt = 2 * (rest % m_pairs) + rank;
             const int t = mt * BM + row;
             bool valid = t < p.M;
             if (p.rows_per_utt > 0) {
                 const int ub = t / p.rows_per_utt;
                 valid = valid && (t - ub * p.rows_per_utt) < p.rows_per_utt - 1;
             }
-            float bg[GH], bf[GH];
-            {
-                const float4* pg = reinterpret_cast<const float4*>(p.bias + nt * BN + h * GH);
-                const float4* pf = reinterpret_cast<const float4*>(p.bias + nt * BN + BN / 2 + h * GH);
-#pragma unroll
-                for (int i = 0; i < GH / 4; ++i) {
-                    const float4 x = __ldg(pg + i), y = __ldg(pf + i);
-                    bg[4 * i] = x.x; bg[4 * i + 1] = x.y; bg[4 * i + 2] = x.z; bg[4 * i + 3] = x.w;
-                    bf[4 * i] = y.x; bf[4 * i + 1] = y.y; bf[4 * i + 2] = y.z; bf[4 * i + 3] = y.w;
-                }
-            }
+            const float* sbg = s_bias + nt * BN + h * GH;
+            const float* sbf = sbg + BN / 2;
             mbar_wait(&tfull[abuf], tphase);
             tc_fence_after();
+            if (lane == 0) tma_store_wait_read();         // the previous tile's stores have finished reading the slab
+            __syncwarp();
             const uint32_t taddr = tmem_base + (uint32_t)(abuf * ACC_COLS) + ((uint32_t)(q * 32) << 16);
 #pragma unroll
             for (int c = 0; c < GH / 16; ++c) {
@@ -901,24 +912,40 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
                 tmem_ld16(taddr + BN + g0, rg2);
                 tmem_ld16(taddr + BN + BN / 2 + g0, rf2);
                 tmem_ld_wait();
-                if (valid) {
-                    const int ch = nt * (BN / 2) + g0;
-                    float v[16];
+                float v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float g = fmaf(fmaf(__uint_as_float(rg2[j]), G8_LO_SCALE_INV, __uint_as_float(rg[j])), p.alpha, bg[c * 16 + j]);
-                        const float f = fmaf(fmaf(__uint_as_float(rf2[j]), G8_LO_SCALE_INV, __uint_as_float(rf[j])), p.alpha, bf[c * 16 + j]);
-                        v[j] = gate_fast(g, f);
+                for (int i = 0; i < 4; ++i) {
+                    const float4 b4g = *reinterpret_cast<const float4*>(sbg + c * 16 + 4 * i);
+                    const float4 b4f = *reinterpret_cast<const float4*>(sbf + c * 16 + 4 * i);
+                    const float bgv[4] = {b4g.x, b4g.y, b4g.z, b4g.w}, bfv[4] = {b4f.x, b4f.y, b4f.z, b4f.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int j = 4 * i + k;
+                        const float g = fmaf(fmaf(__uint_as_float(rg2[j]), G8_LO_SCALE_INV, __uint_as_float(rg[j])), p.alpha, bgv[k]);
+                        const float f = fmaf(fmaf(__uint_as_float(rf2[j]), G8_LO_SCALE_INV, __uint_as_float(rf[j])), p.alpha, bfv[k]);
+                        v[j] = valid ? gate_fast(g, f) : 0.f;
                     }
-                    const long long o = (long long)b * p.out_bstride + (long long)t * p.out_ld + ch;
-                    store16_hilo(p.out_h + o, p.out_lo + o, v);
                 }
+                uint4 h0, h1, l0, l1;
+                pack16_hilo(v, h0, h1, l0, l1);
+                *reinterpret_cast<uint4*>(srow + (((2 * c) ^ sw3) << 4)) = h0;
+                *reinterpret_cast<uint4*>(srow + (((2 * c + 1) ^ sw3) << 4)) = h1;
+                *reinterpret_cast<uint4*>(srow + 2048 + (((2 * c) ^ sw3) << 4)) = l0;
+                *reinterpret_cast<uint4*>(srow + 2048 + (((2 * c + 1) ^ sw3) << 4)) = l1;
             }
             tc_fence_before();
+            fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) gx2_arrive_leader(&tempty[abuf]);
+            if (lane == 0) {
+                gx2_arrive_leader(&tempty[abuf]);
+                const int c0 = nt * (BN / 2) + h * GH, r0 = mt * BM + q * 32;
+                tma_store_3d(&tmOh, slab, c0, r0, 0);
+                tma_store_3d(&tmOl, slab + 2048, c0, r0, 0);
+                tma_store_commit();
+            }
             abuf ^= 1; if (abuf == 0) tphase ^= 1;
         }
+        if (lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -937,10 +964,12 @@ int launch_gate8x2_cfg(const UmmaConvParams& p, cudaStream_t s) {
     const int box_rows = 128 + span;
     const int rows_alloc = (box_rows + 7) / 8 * 8;
     const size_t a_half = (size_t)rows_alloc * G_ROW_BYTES;
-    const size_t smem = G8_A16_STAGES * a_half + (size_t)GX2_W16_STAGES * GX2_WB + G8_A8_STAGES * 2 * a_half +
+    const size_t smem = GX2_OUT_BYTES + G8_A16_STAGES * a_half + (size_t)GX2_W16_STAGES * GX2_WB + G8_A8_STAGES * 2 * a_half +
                         (size_t)GX2_W8_STAGES * GX2_W8_STAGE +
-                        (2 * (G8_A16_STAGES + GX2_W16_STAGES + G8_A8_STAGES + GX2_W8_STAGES) + 4) * 8 + 16 + 1024;
-    if (smem > 227 * 1024 || box_rows > 256) return CMTTS_ERR_UNSUPPORTED;
+                        (2 * (G8_A16_STAGES + GX2_W16_STAGES + G8_A8_STAGES + GX2_W8_STAGES) + 4) * 8 + 32 + GX2_MAX_N * 4 + 1024;
+    if (smem > 227 * 1024 || box_rows > 256 || p.N > GX2_MAX_N || p.B != 1 || p.rows_per_utt <= 0 || p.out_ld % 8 != 0 ||
+        ((uintptr_t)p.out_h % 16) != 0 || ((uintptr_t)p.out_lo % 16) != 0)
+        return CMTTS_ERR_UNSUPPORTED;
     auto kern = umma_gate8x2_kernel<TAPS>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -950,7 +979,13 @@ int launch_gate8x2_cfg(const UmmaConvParams& p, cudaStream_t s) {
         }
         attr_done = true;
     }
-    CUtensorMap a16, a8h, a8l, w16, w8h, w8l;
+    CUtensorMap a16, a8h, a8l, w16, w8h, w8l, oh, ol;
+    // g hi / lo [M][out_ld] fp16: per-warp boxes of 32 columns x 32 rows (64B swizzle)
+    if (!make_act_map(&oh, p.out_h, p.N / 2, p.M, 1, p.out_ld, (long long)p.M * p.out_ld, 32, 32) ||
+        !make_act_map(&ol, p.out_lo, p.N / 2, p.M, 1, p.out_ld, (long long)p.M * p.out_ld, 32, 32)) {
+        cmtts_set_error("umma_gate8x2: cuTensorMapEncodeTiled failed (output maps)", __FILE__, __LINE__);
+        return CMTTS_ERR_CUDA;
+    }
     // weight boxes: HALF an N tile (64 output channels) per CTA
     if (!make_act_map(&a16, p.a_hi, p.Cin, p.Lin, p.B, p.a_ld, p.a_bstride, G_BK, box_rows) ||
         !make_act_map8(&a8h, p.a8_hi, p.Cin, p.Lin, p.B, p.Cin, (long long)p.Lin * p.Cin, box_rows) ||
@@ -972,7 +1007,7 @@ int launch_gate8x2_cfg(const UmmaConvParams& p, cudaStream_t s) {
         cmtts_prof_note(lbl, 2.0 * rows * p.N * p.taps * p.Cin,
                         rows * p.Cin * 4.0 + rows * (p.N / 2) * 4.0 + (double)p.taps * p.N * p.Cin * 4.0);
     }
-    launch_pdl(kern, grid, G8_THREADS, smem, s, a16, a8h, a8l, w16, w8h, w8l, p, rows_alloc, box_rows);
+    launch_pdl(kern, grid, G8_THREADS, smem, s, a16, a8h, a8l, w16, w8h, w8l, oh, ol, p, rows_alloc, box_rows);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }
