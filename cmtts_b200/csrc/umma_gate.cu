@@ -896,6 +896,7 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
                 const int ub = t / p.rows_per_utt;
                 valid = valid && (t - ub * p.rows_per_utt) < p.rows_per_utt - 1;
             }
+            const float vmask = valid ? 1.f : 0.f;        // gate_fast clamps its arguments: finite for any accumulator
             const float* sbg = s_bias + nt * BN + h * GH;
             const float* sbf = sbg + BN / 2;
             mbar_wait(&tfull[abuf], tphase);
@@ -923,7 +924,8 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
                         const int j = 4 * i + k;
                         const float g = fmaf(fmaf(__uint_as_float(rg2[j]), G8_LO_SCALE_INV, __uint_as_float(rg[j])), p.alpha, bgv[k]);
                         const float f = fmaf(fmaf(__uint_as_float(rf2[j]), G8_LO_SCALE_INV, __uint_as_float(rf[j])), p.alpha, bfv[k]);
-                        v[j] = valid ? gate_fast(g, f) : 0.f;
+                        v[j] = __fmul_rn(gate_fast(g, f), vmask);      // a mask, not a select: `valid ? gate(...) : 0` compiles to a branch per element
+                                                                       // (serial MUFU chains, no overlap between the 16 outputs)
                     }
                 }
                 uint4 h0, h1, l0, l1;
