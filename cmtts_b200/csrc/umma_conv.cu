@@ -90,9 +90,7 @@ __global__ void __launch_bounds__(384, 1)
 umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
-                 const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
-                 const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmO3,
-                 const UmmaConvParams p) {
+                 const __grid_constant__ CUtensorMap tmO0, const UmmaConvParams p) {
     constexpr int BM = 128;
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     constexpr int NOP = SPLIT ? 2 : 1;
@@ -105,8 +103,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     constexpr int ACC_COLS = SPLIT ? 2 * BN : BN;     // TMEM columns per accumulator buffer
     constexpr int TMEM_COLS = pow2_cols(2 * ACC_COLS);
 
-    // UEPI_DN_OUTY stages its output tile in shared memory and TMA-stores it: per epilogue warp (32 rows x 64 columns)
-    // {hi 4 KB | lo 4 KB | e4m3 hi 2 KB | e4m3 lo 2 KB} in the swizzled box layouts of tmO0..3.  With one STG.128 per
+    // UEPI_DN_OUTY stages its output tile in shared memory and writes it out with coalesced stores: per epilogue warp (32 rows
+    // x 64 columns) {hi 4 KB | lo 4 KB | e4m3 hi 2 KB | e4m3 lo 2 KB}, rows swizzled against bank conflicts.  With one STG.128 per
     // thread and 16 columns, a warp-level store touched 32 rows = 32 L1 wavefronts for 512 bytes; 24 of them per thread
     // and tile made the epilogue (~10 us per tile against 2.4 us of MMAs) the limiter of the layer GEMM (ncu launch
     // lists: 37 us per launch whether the contraction ran over K = 640 or 384).
@@ -389,8 +387,6 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     }
                 }
                 uint8_t* slab = smem_out + (warp - 4) * OUT_SLAB;
-                if (lane == 0) tma_store_wait_read();            // the previous tile's stores have finished reading the slab
-                __syncwarp();
                 const int sw7 = lane & 7, sw3 = (lane >> 1) & 3;
                 const float* avp = p.addvec + (long long)ub * p.addvec_bstride + n0;
                 float av[16], avn[16];
@@ -431,18 +427,38 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         *reinterpret_cast<uint4*>(r8 + 2048 + ((c ^ sw3) << 4)) = l8;
                     }
                 }
-                fence_proxy_async_smem();                        // generic-proxy writes of the slab -> visible to the TMA store
+                // slab -> global with COALESCED stores: 8 lanes cover one 128-byte row segment, a warp-level STG.128 touches
+                // 4 rows (4 L1 wavefronts, not 32).  (A TMA store of the slab was tried first: the warp then waited ~2 us
+                // per tile on fence.proxy.async and on the store's shared-memory reads before it could reuse the slab — ncu.)
                 __syncwarp();
-                if (lane == 0 && !(p.dbg & 16)) {
+                if (!(p.dbg & 16)) {
                     const int r0 = mt * BM + q * 32;
-                    tma_store_3d(&tmO0, slab, n0, r0, 0);
-                    tma_store_3d(&tmO1, slab + 4096, n0, r0, 0);
-                    if (p.out8_hi) {
-                        tma_store_3d(&tmO2, slab + 8192, n0, r0, 0);
-                        tma_store_3d(&tmO3, slab + 8192 + 2048, n0, r0, 0);
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int pc = it * 32 + lane, rr = pc >> 3, un = pc & 7;
+                        if (r0 + rr < p.M) {
+                            const uint4 vh = *reinterpret_cast<const uint4*>(slab + rr * 128 + ((un ^ (rr & 7)) << 4));
+                            const uint4 vl = *reinterpret_cast<const uint4*>(slab + 4096 + rr * 128 + ((un ^ (rr & 7)) << 4));
+                            const long long o = (long long)(r0 + rr) * p.out_ld + n0 + un * 8;
+                            *reinterpret_cast<uint4*>(p.out_h + o) = vh;
+                            *reinterpret_cast<uint4*>(p.out_lo + o) = vl;
+                        }
                     }
-                    tma_store_commit();
+                    if (p.out8_hi) {
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            const int pc = it * 32 + lane, rr = pc >> 2, un = pc & 3;
+                            if (r0 + rr < p.M) {
+                                const uint4 vh = *reinterpret_cast<const uint4*>(slab + 8192 + rr * 64 + ((un ^ ((rr >> 1) & 3)) << 4));
+                                const uint4 vl = *reinterpret_cast<const uint4*>(slab + 8192 + 2048 + rr * 64 + ((un ^ ((rr >> 1) & 3)) << 4));
+                                const long long o = (long long)(r0 + rr) * p.out8_ld + n0 + un * 16;
+                                *reinterpret_cast<uint4*>(p.out8_hi + o) = vh;
+                                *reinterpret_cast<uint4*>(p.out8_lo + o) = vl;
+                            }
+                        }
+                    }
                 }
+                __syncwarp();                                    // slab free for the next tile
             } else {
 #pragma unroll
                 for (int c = 0; c < BNH / 16; ++c) {
@@ -576,7 +592,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (lane == 0) mbar_arrive(&tempty[abuf]);
             abuf ^= 1; if (abuf == 0) aphase ^= 1;
         }
-        if ((TMA_OUT || TMA_F32) && lane == 0) tma_store_wait_all();   // global writes complete before the CTA exits
+        if (TMA_F32 && lane == 0) tma_store_wait_all();          // global writes complete before the CTA exits
     }
 
     tc_fence_before();
@@ -633,19 +649,7 @@ int launch_cfg(const UmmaConvParams& p, cudaStream_t s) {
             return CMTTS_ERR_CUDA;
         }
     }
-    CUtensorMap o0 = a0, o1 = a0, o2 = a0, o3 = a0;
-    if (TMA_OUT) {
-        // y hi / lo [M][out_ld] fp16: boxes of 64 columns x 32 rows (128B swizzle); the e4m3 pair [M][out8_ld] bytes: 64 x 32 (64B swizzle)
-        bool ok = make_act_map(&o0, p.out_h, p.N, p.M, 1, p.out_ld, (long long)p.M * p.out_ld, 64, 32) &&
-                  make_act_map(&o1, p.out_lo, p.N, p.M, 1, p.out_ld, (long long)p.M * p.out_ld, 64, 32);
-        if (p.out8_hi)
-            ok = ok && make_store_map8(&o2, p.out8_hi, p.N, p.M, 1, p.out8_ld, (long long)p.M * p.out8_ld, 32) &&
-                 make_store_map8(&o3, p.out8_lo, p.N, p.M, 1, p.out8_ld, (long long)p.M * p.out8_ld, 32);
-        if (!ok) {
-            cmtts_set_error("umma_conv: cuTensorMapEncodeTiled failed (output maps)", __FILE__, __LINE__);
-            return CMTTS_ERR_CUDA;
-        }
-    }
+    CUtensorMap o0 = a0;                                      // fp32 plane map of UEPI_F32_PLANES
     if (TMA_F32 && !make_store_map_f32(&o0, p.out_f32, p.out32_ncols, p.M, p.N / p.out32_ncols, p.out32_ld, p.out32_plane, 32)) {
         cmtts_set_error("umma_conv: cuTensorMapEncodeTiled failed (fp32 plane map)", __FILE__, __LINE__);
         return CMTTS_ERR_CUDA;
@@ -665,7 +669,7 @@ int launch_cfg(const UmmaConvParams& p, cudaStream_t s) {
                             (p.res_h ? rows * p.N * 2.0 : 0.0) + (p.sum_h ? rows * p.N * 2.0 : 0.0) + (p.x_f32 ? rows * n_out * 4.0 : 0.0) +
                             (double)p.taps * p.N * (p.Cin + (p.a2_hi ? p.Cin2 : 0)) * 2.0 * nop);
     }
-    launch_pdl(kern, grid, 384, SMEM, s, a0, a1, b0, b1, a2, a3, o0, o1, o2, o3, p);
+    launch_pdl(kern, grid, 384, SMEM, s, a0, a1, b0, b1, a2, a3, o0, p);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }

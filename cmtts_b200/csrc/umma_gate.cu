@@ -651,7 +651,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G8_THREADS, 1)
 umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_constant__ CUtensorMap tmA8h,
                   const __grid_constant__ CUtensorMap tmA8l, const __grid_constant__ CUtensorMap tmW16,
                   const __grid_constant__ CUtensorMap tmW8h, const __grid_constant__ CUtensorMap tmW8l,
-                  const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
                   const UmmaConvParams p, const int rows_alloc, const int box_rows) {
     constexpr int BM = G_BM, BN = G_BN;
     constexpr int CB = 4, CB8 = 2;                    // 256 channels: four 64-channel fp16 blocks / two 128-channel e4m3 blocks
@@ -876,9 +875,9 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
         }
     } else if (warp >= 4 && warp < 12) {
         // ================= epilogue (UEPI_DN_GATE): cross accumulator scaled by 2^-11, gate math, g as fp16 hi/lo =================
-        // staged per warp as two boxes of 32 columns x 32 rows (64-byte rows, 64B swizzle) and TMA-stored: a direct
-        // STG.128 per thread touches 32 rows = 32 L1 wavefronts per warp instruction (see umma_conv.cu, UEPI_DN_OUTY).
-        // Rows outside the problem and guard rows are written as zeros (nothing consumes them).
+        // staged per warp as two tiles of 32 rows x 32 columns (64-byte rows, swizzled against bank conflicts) and written
+        // out with coalesced stores (4 lanes per row segment: a warp-level STG.128 touches 8 rows, not 32 — see
+        // umma_conv.cu, UEPI_DN_OUTY).  Guard rows are written as zeros (nothing consumes them).
         constexpr int GH = BN / 4;
         const int q = warp & 3;
         const int h = (warp - 4) >> 2;
@@ -901,8 +900,6 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
             const float* sbf = sbg + BN / 2;
             mbar_wait(&tfull[abuf], tphase);
             tc_fence_after();
-            if (lane == 0) tma_store_wait_read();         // the previous tile's stores have finished reading the slab
-            __syncwarp();
             const uint32_t taddr = tmem_base + (uint32_t)(abuf * ACC_COLS) + ((uint32_t)(q * 32) << 16);
 #pragma unroll
             for (int c = 0; c < GH / 16; ++c) {
@@ -936,18 +933,25 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
                 *reinterpret_cast<uint4*>(srow + 2048 + (((2 * c + 1) ^ sw3) << 4)) = l1;
             }
             tc_fence_before();
-            fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
-                gx2_arrive_leader(&tempty[abuf]);
+            if (lane == 0) gx2_arrive_leader(&tempty[abuf]);
+            {
                 const int c0 = nt * (BN / 2) + h * GH, r0 = mt * BM + q * 32;
-                tma_store_3d(&tmOh, slab, c0, r0, 0);
-                tma_store_3d(&tmOl, slab + 2048, c0, r0, 0);
-                tma_store_commit();
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int pc = it * 32 + lane, rr = pc >> 2, un = pc & 3;
+                    if (r0 + rr < p.M) {
+                        const uint4 vh = *reinterpret_cast<const uint4*>(slab + rr * 64 + ((un ^ ((rr >> 1) & 3)) << 4));
+                        const uint4 vl = *reinterpret_cast<const uint4*>(slab + 2048 + rr * 64 + ((un ^ ((rr >> 1) & 3)) << 4));
+                        const long long o = (long long)(r0 + rr) * p.out_ld + c0 + un * 8;
+                        *reinterpret_cast<uint4*>(p.out_h + o) = vh;
+                        *reinterpret_cast<uint4*>(p.out_lo + o) = vl;
+                    }
+                }
             }
+            __syncwarp();                                 // slab free for the next tile
             abuf ^= 1; if (abuf == 0) tphase ^= 1;
         }
-        if (lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -981,13 +985,7 @@ int launch_gate8x2_cfg(const UmmaConvParams& p, cudaStream_t s) {
         }
         attr_done = true;
     }
-    CUtensorMap a16, a8h, a8l, w16, w8h, w8l, oh, ol;
-    // g hi / lo [M][out_ld] fp16: per-warp boxes of 32 columns x 32 rows (64B swizzle)
-    if (!make_act_map(&oh, p.out_h, p.N / 2, p.M, 1, p.out_ld, (long long)p.M * p.out_ld, 32, 32) ||
-        !make_act_map(&ol, p.out_lo, p.N / 2, p.M, 1, p.out_ld, (long long)p.M * p.out_ld, 32, 32)) {
-        cmtts_set_error("umma_gate8x2: cuTensorMapEncodeTiled failed (output maps)", __FILE__, __LINE__);
-        return CMTTS_ERR_CUDA;
-    }
+    CUtensorMap a16, a8h, a8l, w16, w8h, w8l;
     // weight boxes: HALF an N tile (64 output channels) per CTA
     if (!make_act_map(&a16, p.a_hi, p.Cin, p.Lin, p.B, p.a_ld, p.a_bstride, G_BK, box_rows) ||
         !make_act_map8(&a8h, p.a8_hi, p.Cin, p.Lin, p.B, p.Cin, (long long)p.Lin * p.Cin, box_rows) ||
@@ -1009,7 +1007,7 @@ int launch_gate8x2_cfg(const UmmaConvParams& p, cudaStream_t s) {
         cmtts_prof_note(lbl, 2.0 * rows * p.N * p.taps * p.Cin,
                         rows * p.Cin * 4.0 + rows * (p.N / 2) * 4.0 + (double)p.taps * p.N * p.Cin * 4.0);
     }
-    launch_pdl(kern, grid, G8_THREADS, smem, s, a16, a8h, a8l, w16, w8h, w8l, oh, ol, p, rows_alloc, box_rows);
+    launch_pdl(kern, grid, G8_THREADS, smem, s, a16, a8h, a8l, w16, w8h, w8l, p, rows_alloc, box_rows);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }
