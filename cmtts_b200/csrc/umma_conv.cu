@@ -121,7 +121,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* pbar = tempty + 2;                               // [8] TMA_OUT: one per epilogue warp (its P rows have landed)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pbar + 8);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: warp index provably uniform for ptxas
     const int cblocks = p.Cin / BK;
@@ -134,6 +135,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // SPLIT: two issuing warps (main products / cross terms) each commit to `empty` and `tfull`
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], SPLIT ? 2 : 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], SPLIT ? 2 : 1); mbar_init(&tempty[i], 8); }
+        for (int i = 0; i < 8; ++i) mbar_init(&pbar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -258,6 +260,22 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         int abuf = 0; uint32_t aphase = 0;
         TileSched ts(p, BN, BK);
         int nt, mt, b; bool heavy;
+        // TMA_OUT: the tile's rows of the conditioner plane P (32 rows x 64 fp32 columns per warp = two 128-byte-row boxes)
+        // are TMA-loaded into the warp's staging slab, which is idle between tiles: issued when the previous tile's epilogue
+        // ends (the first one here), so their DRAM latency runs behind that tile's MMAs instead of in front of the epilogue
+        // (as register loads they could only be issued once the tile began: ~2 us of exposed latency per tile — ncu).
+        uint32_t pphase = 0;
+        auto issue_p = [&](int nt_, int mt_) {
+            uint8_t* sl = smem_out + (warp - 4) * OUT_SLAB;
+            mbar_expect_tx(&pbar[warp - 4], 8192u);
+            tma_load_3d(sl, &tmO0, &pbar[warp - 4], nt_ * BN + h * BNH, mt_ * BM + q * 32, 0);
+            tma_load_3d(sl + 4096, &tmO0, &pbar[warp - 4], nt_ * BN + h * BNH + 32, mt_ * BM + q * 32, 0);
+        };
+        if constexpr (TMA_OUT) {
+            TileSched t0 = ts;
+            int nt0, mt0, b0; bool hv0;
+            if (lane == 0 && t0.next(nt0, mt0, b0, hv0)) issue_p(nt0, mt0);
+        }
         while (ts.next(nt, mt, b, heavy)) {
             const int t = mt * BM + row;
             bool valid = t < p.M;
@@ -272,8 +290,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if constexpr (SPLIT) {
                 const float* src = nullptr;
                 const long long t_io = p.io_unguard ? (long long)(t - ub) : (long long)t;   // row in un-guarded fp32 tensors
-                if (EPI == UEPI_DN_COND || (EPI == UEPI_DN_OUTY && p.x_f32 != nullptr) ||
-                    (EPI == UEPI_F32 && p.x_f32 != nullptr && n0 < p.n_valid))
+                if (EPI == UEPI_DN_COND || (EPI == UEPI_F32 && p.x_f32 != nullptr && n0 < p.n_valid))
                     src = p.x_f32 + (long long)b * p.x_bstride + t_io * p.x_ld + n0;
                 else if (EPI == UEPI_DN_OUT) {
                     const int half_n = p.N >> 1;
@@ -372,22 +389,15 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             } else if constexpr (TMA_OUT) {
                 // y-recurrence: y = acc + addvec[utterance] + P row -> hi/lo (+ e4m3 pair), staged in this warp's slab
                 // (rows outside the problem or guard rows: zeros — a guard row keeps the value the conv's padding needs).
-                // The P row streams from DRAM (each layer has its own plane): the rows of this CTA's NEXT tile are pulled
-                // into L2 now, one tile ahead of the register loads above (ncu: with the loads issued only when the tile
-                // begins, their DRAM latency sat in front of every tile's epilogue, which bounded the kernel).
-                {
-                    TileSched tn = ts;
-                    int nt2, mt2, b2; bool heavy2;
-                    if (tn.next(nt2, mt2, b2, heavy2)) {
-                        const int t2 = mt2 * BM + row;
-                        if (t2 < p.M && p.x_f32 != nullptr) {
-                            const float* pn = p.x_f32 + (long long)t2 * p.x_ld + nt2 * BN + h * BNH;
-                            prefetch_l2(pn); prefetch_l2(pn + 32);
-                        }
-                    }
-                }
+                // The P rows were TMA-loaded into the slab while the previous tile was in flight (issue_p above).
                 uint8_t* slab = smem_out + (warp - 4) * OUT_SLAB;
                 const int sw7 = lane & 7, sw3 = (lane >> 1) & 3;
+                uint4 pp[16];                                    // this thread's 64 P values
+                mbar_wait(&pbar[warp - 4], pphase); pphase ^= 1u;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    pp[i] = *reinterpret_cast<const uint4*>(slab + (i >> 3) * 4096 + lane * 128 + (((i & 7) ^ sw7) << 4));
+                __syncwarp();                                    // every lane holds its P row: the slab may be overwritten
                 const float* avp = p.addvec + (long long)ub * p.addvec_bstride + n0;
                 float av[16], avn[16];
                 if (valid) load16f(avp, av);
@@ -401,7 +411,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     float v[16];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const uint4 u = have_pre ? pre[4 * c + i] : make_uint4(0u, 0u, 0u, 0u);
+                        const uint4 u = pp[4 * c + i];
                         const float xx[4] = {__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)};
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
@@ -458,7 +468,15 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         }
                     }
                 }
-                __syncwarp();                                    // slab free for the next tile
+                __syncwarp();                                    // slab free: the next tile's P rows may land in it
+                {
+                    TileSched tn = ts;
+                    int nt2, mt2, b2; bool heavy2;
+                    if (lane == 0 && tn.next(nt2, mt2, b2, heavy2)) {
+                        fence_proxy_async_smem();                // this tile's generic-proxy accesses of the slab before the TMA write
+                        issue_p(nt2, mt2);
+                    }
+                }
             } else {
 #pragma unroll
                 for (int c = 0; c < BNH / 16; ++c) {
@@ -617,7 +635,7 @@ int launch_cfg(const UmmaConvParams& p, cudaStream_t s) {
     constexpr int BUDGET = ((TMA_OUT || TMA_F32) ? 226 : 200) * 1024 - OUT_BYTES;
     constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
     static_assert(STAGES >= 2, "pipeline needs at least two stages");
-    constexpr size_t SMEM = (size_t)OUT_BYTES + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
+    constexpr size_t SMEM = (size_t)OUT_BYTES + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 12) * 8 + 16 + 1024;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
     auto kern = umma_conv_kernel<BN, BK, SPLIT, STAGES, EPI>;
     static bool attr_done = false;
@@ -650,6 +668,10 @@ int launch_cfg(const UmmaConvParams& p, cudaStream_t s) {
         }
     }
     CUtensorMap o0 = a0;                                      // fp32 plane map of UEPI_F32_PLANES
+    if (TMA_OUT && !make_store_map_f32(&o0, p.x_f32, p.N, p.M, 1, p.x_ld, (long long)p.M * p.x_ld, 32)) {   // P plane: loads of 32 x 32 boxes
+        cmtts_set_error("umma_conv: cuTensorMapEncodeTiled failed (conditioner plane map)", __FILE__, __LINE__);
+        return CMTTS_ERR_CUDA;
+    }
     if (TMA_F32 && !make_store_map_f32(&o0, p.out_f32, p.out32_ncols, p.M, p.N / p.out32_ncols, p.out32_ld, p.out32_plane, 32)) {
         cmtts_set_error("umma_conv: cuTensorMapEncodeTiled failed (fp32 plane map)", __FILE__, __LINE__);
         return CMTTS_ERR_CUDA;
@@ -698,10 +720,10 @@ int launch_umma_conv(const UmmaConvParams& p_in, cudaStream_t s) {
                           ((uintptr_t)p.a2_hi % 16 == 0) && ((uintptr_t)p.a2_lo % 16 == 0),
                           "umma_conv: second operand needs taps == 1, Cin2 % 64 == 0, n_k2 % 128 == 0, 16-byte alignment");
         }
-        CMTTS_REQUIRE(p.epi != UEPI_DN_OUTY || (p.a2_hi && p.out_h && p.out_lo && p.addvec && !p.bias && p.B == 1 && p.rows_per_utt > 0 &&
+        CMTTS_REQUIRE(p.epi != UEPI_DN_OUTY || (p.a2_hi && p.out_h && p.out_lo && p.addvec && !p.bias && p.x_f32 && p.B == 1 && p.rows_per_utt > 0 &&
                                                 ((uintptr_t)p.out_h % 16) == 0 && ((uintptr_t)p.out_lo % 16) == 0 && p.out_ld % 8 == 0 &&
                                                 (!p.out8_hi || (p.out8_lo && ((uintptr_t)p.out8_hi % 16) == 0 && ((uintptr_t)p.out8_lo % 16) == 0 && p.out8_ld % 16 == 0))),
-                      "umma_conv: UEPI_DN_OUTY needs the second operand, addvec, no bias (it belongs to the P plane), the flattened layout and 16-byte aligned y hi/lo (+ e4m3 pair)");
+                      "umma_conv: UEPI_DN_OUTY needs the second operand, addvec, the P plane (x_f32; it carries the bias), the flattened layout and 16-byte aligned y hi/lo (+ e4m3 pair)");
         CMTTS_REQUIRE(p.a2_diag == 0 || (p.a2_hi && p.a2_diag == p.N && p.n_k2 == p.N && p.a2_diag <= p.Cin2),
                       "umma_conv: a block-diagonal A2 segment must span exactly the N output columns");
         CMTTS_REQUIRE(p.rows_per_utt == 0 || (p.B == 1 && p.rows_per_utt >= 2), "umma_conv: flattened layout needs B == 1");
