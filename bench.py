@@ -587,7 +587,7 @@ def main():
         line["roofline"] = top
         line["roofline_other"] = others
         line["kernels"] = [{"kernel": r["kernel"], "launches": r["launches"], "ms": r["us"] / 1e3, "share": r["share"]}
-                           for r in rows_[:12]]
+                           for r in rows_[:40]]
     else:
         line["roofline"] = {"kernel": synth.dominant_kernel(), "bound": "tensor", "achieved": total_flops / sec / 1e12,
                             "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",

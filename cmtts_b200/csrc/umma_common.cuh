@@ -14,6 +14,11 @@ namespace umma {
 // PTX wrappers
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// 1024-byte alignment of the dynamic shared-memory base as POINTER ARITHMETIC on the __shared__ array: rounding the address up
+// through uintptr_t turned every pointer derived from it into a generic one (LD.E / ST.E: generic address translation in front
+// of each staging-slab, bias and t-tile access, and no reordering against global stores); an offset keeps the address space,
+// so the same accesses compile to LDS / STS.
+__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* base) { return base + ((1024u - (smem_u32(base) & 1023u)) & 1023u); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -114,7 +114,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     constexpr int OUT_BYTES = (TMA_OUT || TMA_F32) ? 8 * OUT_SLAB : 0;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_al = smem_align1024(smem_raw);
     uint8_t* smem_out = smem_al;                               // [8 warps][OUT_SLAB] (TMA_OUT only)
     uint8_t* smem = smem_al + OUT_BYTES;                       // operand ring
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -319,6 +319,11 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
             if (p.dbg & 64) {
                 // timing ablation: the epilogue does nothing
+                if constexpr (TMA_OUT) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[abuf]);
+                }
             } else if (SPLIT && EPI == UEPI_DN_GATE) {
                 // tile columns [0, BN/2) are gates, [BN/2, BN) the matching filters (weights.py gate_permutation)
                 constexpr int GH = BN / 4;                        // gate columns per column-half
@@ -437,10 +442,14 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         *reinterpret_cast<uint4*>(r8 + 2048 + ((c ^ sw3) << 4)) = l8;
                     }
                 }
+                // the accumulator buffer is free as soon as every lane has read it: release it BEFORE the copy-out, so the
+                // MMAs of the tile after next do not wait for this tile's global stores
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[abuf]);
                 // slab -> global with COALESCED stores: 8 lanes cover one 128-byte row segment, a warp-level STG.128 touches
                 // 4 rows (4 L1 wavefronts, not 32).  (A TMA store of the slab was tried first: the warp then waited ~2 us
                 // per tile on fence.proxy.async and on the store's shared-memory reads before it could reuse the slab — ncu.)
-                __syncwarp();
                 if (!(p.dbg & 16)) {
                     const int r0 = mt * BM + q * 32;
 #pragma unroll
@@ -605,9 +614,11 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[abuf]);
+            if constexpr (!TMA_OUT) {                            // (TMA_OUT released its accumulator before the copy-out)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[abuf]);
+            }
             abuf ^= 1; if (abuf == 0) aphase ^= 1;
         }
         if (TMA_F32 && lane == 0) tma_store_wait_all();          // global writes complete before the CTA exits
@@ -751,7 +762,8 @@ int launch_umma_conv(const UmmaConvParams& p_in, cudaStream_t s) {
             case UEPI_DN_COND: return launch_cfg<128, 64, 1, UEPI_DN_COND>(p, s);
             case UEPI_DN_GATE: return launch_cfg<128, 64, 1, UEPI_DN_GATE>(p, s);
             case UEPI_DN_OUT: return launch_cfg<128, 64, 1, UEPI_DN_OUT>(p, s);
-            case UEPI_DN_OUTY: return launch_cfg<128, 64, 1, UEPI_DN_OUTY>(p, s);
+            case UEPI_DN_OUTY: return (p.dbg & 2048) ? launch_cfg<128, 32, 1, UEPI_DN_OUTY>(p, s)      // experiment: 4 stages of 32 KB
+                                                       : launch_cfg<128, 64, 1, UEPI_DN_OUTY>(p, s);
             case UEPI_F32: return launch_cfg<128, 64, 1, UEPI_F32>(p, s);
             case UEPI_F32_PLANES: return launch_cfg<128, 64, 1, UEPI_F32_PLANES>(p, s);
             default: CMTTS_REQUIRE(false, "umma_conv: unknown split-mode epilogue");

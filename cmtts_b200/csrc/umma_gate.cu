@@ -130,7 +130,7 @@ umma_gate_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int a_stage = 2 * a_half;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_align1024(smem_raw);
     uint8_t* smA = smem;
     uint8_t* smB = smA + G_A_STAGES * a_stage;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smB + G_B_STAGES * G_B_STAGE);
@@ -314,7 +314,7 @@ umma_gate8_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_consta
     const int a8_stage = 2 * a_half;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_align1024(smem_raw);
     uint8_t* smA16 = smem;
     uint8_t* smW16 = smA16 + G8_A16_STAGES * a_half;
     uint8_t* smA8 = smW16 + G8_W16_STAGES * G_B_BYTES;
@@ -663,7 +663,7 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
     const int a8_stage = 2 * a_half;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_align1024(smem_raw);
     uint8_t* smOut = smem;                            // [8 warps][GX2_OUT_SLAB], 1024-byte aligned slabs
     uint8_t* smA16 = smOut + GX2_OUT_BYTES;
     uint8_t* smW16 = smA16 + G8_A16_STAGES * a_half;

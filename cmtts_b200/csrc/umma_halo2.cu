@@ -99,7 +99,7 @@ umma_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool has_res = p.res_h != nullptr;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_align1024(smem_raw);
     uint8_t* smA = smem;
     uint8_t* smO = smA + cfg.a_stages * a_alloc;
     uint8_t* smW = smO + O_BYTES;
