@@ -68,7 +68,7 @@ struct UmmaConvParams {
     const unsigned char* a8_hi; const unsigned char* a8_lo; const unsigned char* w8_hi; const unsigned char* w8_lo;
     // UEPI_DN_COND / UEPI_DN_OUTY / UEPI_F32 (with out_h + out_lo): also write that e4m3 pair of the output rows (row pitch out8_ld bytes, flattened rows)
     unsigned char* out8_hi; unsigned char* out8_lo; int out8_ld;
-    int dbg;              // experiment bits (CMTTS_UMMA_DBG): 1 = descriptor base_offset, 2 = disable the halo kernel, 128 = disable the gate kernel, 256 = fp16 (not fp8) cross terms in the gate kernel, 512 = no CTA-pair halo kernel, 1024 = no paired-row ResBlock kernel at C = 32
+    int dbg;              // experiment bits (CMTTS_UMMA_DBG): timing ablations 8 = no epilogue pre-loads, 16 = no copy-out / stores, 32 = no MMAs, 64 = epilogue does nothing (results wrong; tools/ablate.py); 1 = descriptor base_offset, 2 = disable the halo kernel, 128 = disable the gate kernel, 256 = fp16 (not fp8) cross terms in the gate kernel, 512 = no CTA-pair halo kernel, 1024 = no paired-row ResBlock kernel at C = 32
 };
 
 static inline UmmaConvParams umma_params_default() {

@@ -818,9 +818,11 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
                     const uint32_t ah = a0 + (uint32_t)tap * tap_step;
                     const uint32_t wh = b_base + (uint32_t)((bs * GX2_WB) >> 4);
                     if (elect_one()) {
+                        if (!(p.dbg & 32)) {                       // dbg 32 = timing ablation: no MMAs
 #pragma unroll
-                        for (int k = 0; k < G_BK / 16; ++k)
-                            gx2_mma_f16(d_tmem, HI | (ah + 2 * k), HI | (wh + 2 * k), idesc, (cb | tap | k) ? 1u : 0u);
+                            for (int k = 0; k < G_BK / 16; ++k)
+                                gx2_mma_f16(d_tmem, HI | (ah + 2 * k), HI | (wh + 2 * k), idesc, (cb | tap | k) ? 1u : 0u);
+                        }
                         gx2_commit_both(&w16_empty[bs]);
                         if (tap == TAPS - 1) gx2_commit_both(&a16_empty[as]);
                         if (tap == TAPS - 1 && cb == CB - 1) gx2_commit_both(&tfull[abuf]);
@@ -859,12 +861,14 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
                     const uint32_t ah = a0 + (uint32_t)tap * tap_step, al = ah + a_half16;
                     const uint32_t wh = b_base + (uint32_t)((bs * GX2_W8_STAGE) >> 4), wl = wh + (uint32_t)(GX2_WB >> 4);
                     if (elect_one()) {
+                        if (!(p.dbg & 32)) {
 #pragma unroll
-                        for (int k = 0; k < 128 / 32; ++k)                                   // A_hi8 W_lo8
-                            gx2_mma_f8(d_tmem, HI | (ah + 2 * k), HI | (wl + 2 * k), idesc, (cb | tap | k) ? 1u : 0u);
+                            for (int k = 0; k < 128 / 32; ++k)                                   // A_hi8 W_lo8
+                                gx2_mma_f8(d_tmem, HI | (ah + 2 * k), HI | (wl + 2 * k), idesc, (cb | tap | k) ? 1u : 0u);
 #pragma unroll
-                        for (int k = 0; k < 128 / 32; ++k)                                   // A_lo8 W_hi8
-                            gx2_mma_f8(d_tmem, HI | (al + 2 * k), HI | (wh + 2 * k), idesc, 1u);
+                            for (int k = 0; k < 128 / 32; ++k)                                   // A_lo8 W_hi8
+                                gx2_mma_f8(d_tmem, HI | (al + 2 * k), HI | (wh + 2 * k), idesc, 1u);
+                        }
                         gx2_commit_both(&w8_empty[bs]);
                         if (tap == TAPS - 1) gx2_commit_both(&a8_empty[as]);
                         if (tap == TAPS - 1 && cb == CB8 - 1) gx2_commit_both(&tfull[abuf]);
@@ -903,6 +907,7 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
             const uint32_t taddr = tmem_base + (uint32_t)(abuf * ACC_COLS) + ((uint32_t)(q * 32) << 16);
 #pragma unroll
             for (int c = 0; c < GH / 16; ++c) {
+                if (p.dbg & 64) break;                    // dbg 64 = timing ablation: the epilogue does nothing
                 uint32_t rg[16], rf[16], rg2[16], rf2[16];
                 const int g0 = h * GH + c * 16;
                 tmem_ld16(taddr + g0, rg);
@@ -935,7 +940,7 @@ umma_gate8x2_kernel(const __grid_constant__ CUtensorMap tmA16, const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) gx2_arrive_leader(&tempty[abuf]);
-            {
+            if (!(p.dbg & (16 | 64))) {                   // dbg 16 = timing ablation: no copy-out
                 const int c0 = nt * (BN / 2) + h * GH, r0 = mt * BM + q * 32;
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {

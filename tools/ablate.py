@@ -70,8 +70,8 @@ def main():
         table("TMA row-rate experiment (fused ResBlock kernel, all roles but the producer switched off)", res)
     if which in ("all", "dn"):
         res = OrderedDict()
-        for tag, env in [("base", {}), ("noEpiLd", {"CMTTS_UMMA_DBG": "8"}), ("noMMA", {"CMTTS_UMMA_DBG": "32"}),
-                         ("noEpi", {"CMTTS_UMMA_DBG": "64"}), ("pfNext", {"CMTTS_UMMA_DBG": "128"})]:
+        for tag, env in [("base", {}), ("noStore", {"CMTTS_UMMA_DBG": "16"}), ("noMMA", {"CMTTS_UMMA_DBG": "32"}),
+                         ("noEpi", {"CMTTS_UMMA_DBG": "64"}), ("noMMAnoEpi", {"CMTTS_UMMA_DBG": "96"})]:
             res[tag] = run("denoiser_only.py", env, "dn_" + tag)
         table("denoiser", res)
 
