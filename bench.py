@@ -253,8 +253,8 @@ def roofline_blocks(rows, total_us, peaks, step_ms, total_flops, stage_ms, stage
         return b
 
     top = block(rows[0])
-    stamp_file = os.path.join(ROOT, "cmtts_b200", "lib", "libcmtts_b200.so.stamp")
-    top["traffic_same_build"] = bool(tr.get("_build_stamp")) and os.path.isfile(stamp_file) and open(stamp_file).read().strip() == tr.get("_build_stamp")
+    from cmtts_b200.build import kernel_stamp
+    top["traffic_same_build"] = bool(tr.get("_kernel_stamp")) and kernel_stamp() == tr.get("_kernel_stamp")   # same kernel sources as the capture
     top["peak_source"] = peaks["source"] + ", sustained (kernel timed inside the step)"
     top["step_frac"] = total_flops / (step_ms * 1e-3) / 1e12 / peaks["tflops_sustained"]
     top["stage_fracs"] = {k: (stage_flops[k] / (v * 1e-3) / 1e12 / peaks["tflops_sustained"]) for k, v in stage_ms.items()

@@ -105,6 +105,8 @@ PROTOTYPES = {
     "cmtts_variance_frame_tc": (C.c_int, [PD, PV, PV, vp, vp, vp, vp, f32, i64, i64, i64, vp, vp, vp, vp, vp, vp, szt, vp]),
     "cmtts_hifigan_tc_workspace_bytes": (szt, [PI32, i64, i64]),
     "cmtts_hifigan_forward_tc": (C.c_int, [PI32, PV, vp, i64, i64, vp, vp, f32, vp, szt, vp]),
+    "cmtts_rescnn_workspace_bytes": (szt, [PI32, i64, i64]),
+    "cmtts_rescnn_forward": (C.c_int, [PI32, PV, vp, i64, i64, vp, vp, szt, vp]),
 }
 
 _lib: Optional[C.CDLL] = None

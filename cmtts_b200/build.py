@@ -37,6 +37,19 @@ def _stamp():
     return h.hexdigest()
 
 
+def kernel_stamp() -> str:
+    """Digest of the sources of the hot path's kernels only (everything but the off-path speaker encoder): what a committed
+    ncu capture under profiles/ is tied to (profiles/roofline_traffic_r2.json, bench.py `traffic_same_build`)."""
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh"))):
+        if os.path.basename(f) == "rescnn.cu":
+            continue
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     stamp_file = LIB + ".stamp"

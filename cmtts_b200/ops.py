@@ -14,6 +14,7 @@ SURVEY.md §7.2).
     torch.ops.cmtts_b200.renoise(x0, noise, s1, s2)                           -> x
     torch.ops.cmtts_b200.hifigan_forward(handle, mel_blc, want_float, want_int16, max_wav) -> wav, wav_i16
     torch.ops.cmtts_b200.transpose_bcl_blc(x)                                 -> (B, L, C)
+    torch.ops.cmtts_b200.rescnn_forward(handle, fbank)                        -> (B, 512) speaker embeddings (zero-shot path)
 
 Each op is registered for the CUDA dispatch key only and is a thin shim: allocate the outputs with torch (device
 memory is PyTorch's job), hand raw pointers + the current stream to libcmtts_b200.so through ctypes, return.  There
@@ -72,6 +73,7 @@ _DEF.define("denoiser_forward(int handle, Tensor x, Tensor cond, Tensor? cond_pr
 _DEF.define("renoise(Tensor x0, Tensor noise, float s1, float s2) -> Tensor")
 _DEF.define("hifigan_forward(int handle, Tensor mel, bool want_float, bool want_int16, float max_wav_value) -> (Tensor, Tensor)")
 _DEF.define("transpose_bcl_blc(Tensor x) -> Tensor")
+_DEF.define("rescnn_forward(int handle, Tensor fbank) -> Tensor")
 
 
 # ---- CUDA implementations ------------------------------------------------------------------------------------------
@@ -274,12 +276,28 @@ def _transpose_bcl_blc(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _rescnn_forward(handle: int, fbank: torch.Tensor) -> torch.Tensor:
+    """DeepSpeaker ResCNN (speaker_encoder.DeepSpeakerModel): (B, T, 64) normalised filter-bank frames -> (B, 512)."""
+    o = _owner(handle)
+    lib, dev = o.lib, o.device
+    B, T, _ = fbank.shape
+    emb = torch.empty(B, 512, dtype=torch.float32, device=dev)
+    if B:
+        with torch.cuda.device(dev):
+            need = lib.cmtts_rescnn_workspace_bytes(o.packed.cfg, B, T)
+            if o._ws is None or o._ws.numel() < need:
+                o._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            _lib.check(lib.cmtts_rescnn_forward(o.packed.cfg, o.packed.ptrs, _lib.ptr(fbank), B, T, _lib.ptr(emb), _lib.ptr(o._ws),
+                                                o._ws.numel(), _lib.stream_ptr(dev)), "rescnn_forward")
+    return emb
+
+
 _IMPL = torch.library.Library("cmtts_b200", "IMPL", "CUDA")
 for _name, _fn in (("encoder_forward", _encoder_forward), ("variance_token", _variance_token), ("variance_frame", _variance_frame),
                    ("denoiser_prepare", _denoiser_prepare), ("split_f16", _split_f16), ("denoiser_cond", _denoiser_cond),
-                   ("denoiser_forward", _denoiser_forward),
+                   ("denoiser_forward", _denoiser_forward), ("rescnn_forward", _rescnn_forward),
                    ("renoise", _renoise), ("hifigan_forward", _hifigan_forward), ("transpose_bcl_blc", _transpose_bcl_blc)):
     _IMPL.impl(_name, _fn)
 
 OPS = ("encoder_forward", "variance_token", "variance_frame", "denoiser_prepare", "split_f16", "denoiser_cond", "denoiser_forward", "renoise",
-       "hifigan_forward", "transpose_bcl_blc")
+       "hifigan_forward", "transpose_bcl_blc", "rescnn_forward")

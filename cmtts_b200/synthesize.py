@@ -97,9 +97,18 @@ class CMTotalTTSSynthesize:
         model.eval()
         return model, diffusion
 
-    def synthesize(self, batch, T: Optional[int] = None, generator=None, trace=None):
+    def synthesize(self, batch, T: Optional[int] = None, generator=None, trace=None, ref_audio: Optional[str] = None,
+                   speaker_ckpt: Optional[str] = None):
+        """`ref_audio`: the zero-shot variant (synthesize_zeroshot_lj.py:89-102 / synthesize_zeroshot_vctk.py): the speaker
+        embedding of every utterance of the batch is the DeepSpeaker embedding of this recording (computed on the GPU by
+        cmtts_b200.speaker_encoder; `speaker_ckpt` = the Keras checkpoint, default the reference's relative path)
+        instead of the batch's precomputed one."""
         T = int(T if T is not None else getattr(self.args, "T", 1))
         kw = {"speakers": batch[2], "texts": batch[3], "src_lens": batch[4], "spker_embeds": batch[-1]}
+        if ref_audio is not None:
+            from .speaker_encoder import get_deep_speaker_emb
+            kw["spker_embeds"] = get_deep_speaker_emb(filepath=ref_audio, batch_size=batch[2].size(0), device=batch[2].device,
+                                                      ckpt_path=speaker_ckpt)
         ctl = {"p_control": self.p_control, "e_control": self.e_control, "d_control": self.d_control} \
             if self.forward_controls else {}
         out_dict = self.duration_pitch_energy_net(**kw, **ctl)

@@ -259,6 +259,18 @@ int cmtts_hifigan_forward_tc(const int32_t* cfg, const void* const* w16, const f
                              int64_t B, int64_t L, float* wav, int16_t* wav_i16, float max_wav_value,
                              void* ws, size_t ws_bytes, void* stream);
 
+/* N4 (zero-shot path): DeepSpeaker ResCNN speaker encoder — replaces `DeepSpeakerModel().m.predict(mfcc[None])` of
+ * deepspeaker/embedding.py:13-27 (model: deepspeaker/conv_models.py:44-138; caller: synthesize_zeroshot_lj.py:93-97).
+ * cfg = {n_fbanks (64), first_filters (64, doubling over the 4 stages), dense_out (512)}.
+ * x: (B, T, n_fbanks) fp32 per-frame-normalised filter-bank energies (one input channel; T = 160 in the reference).
+ * w: per conv {kernel HWIO fp32, scale [Cout], shift [Cout]} (BatchNormalization(eps 1e-3) and the conv bias folded:
+ *    scale = gamma / sqrt(var + eps), shift = beta + (bias - mean) * scale) for the 28 convs in network order — per stage
+ *    the strided 5x5 conv, then each identity block's 2a and 2b 3x3 convs — then {dense kernel [feat][dense_out], bias}.
+ * emb: (B, dense_out) fp32, L2-normalised (K.l2_normalize, eps 1e-12). */
+size_t cmtts_rescnn_workspace_bytes(const int32_t* cfg, int64_t B, int64_t T);
+int cmtts_rescnn_forward(const int32_t* cfg, const void* const* w, const float* x, int64_t B, int64_t T,
+                         float* emb, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,7 +27,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 STAGED_ROOT = os.path.join(_HERE, "_ref")
 #: sub-trees of the reference the hot path imports (+ its YAML configs): ~0.4 MB of Python + the HiFi-GAN weights
 STAGED_PARTS = ("model", "utils", "text", "config", "hifigan/__init__.py", "hifigan/models.py", "hifigan/config.json",
-                "hifigan/generator_universal.pth.tar")
+                "hifigan/generator_universal.pth.tar",
+                # DeepSpeaker ResCNN weights of the zero-shot path (97 MB Keras HDF5; read by cmtts_b200.h5lite)
+                "deepspeaker/pretrained_models/ResCNN_triplet_training_checkpoint_265.h5")
 
 
 def _pick_root() -> str:

@@ -68,7 +68,9 @@ def main():
     sp = os.path.join(ROOT, "cmtts_b200", "lib", "libcmtts_b200.so.stamp")
     if os.path.isfile(sp):
         stamp = open(sp).read().strip()
-    out = {"_build_stamp": stamp, "_note": "mean per launch over the captured launches of each kernel; ncu --set full --clock-control none"}
+    sys.path.insert(0, ROOT)
+    from cmtts_b200.build import kernel_stamp
+    out = {"_build_stamp": stamp, "_kernel_stamp": kernel_stamp(), "_note": "mean per launch over the captured launches of each kernel; ncu --set full --clock-control none"}
     for k, a in sorted(acc.items()):
         out[k] = {"dram_bytes_per_launch": a["bytes"] / a["n"], "launches_captured": a["n"], "us_per_launch_under_ncu": a["us"] / a["n"],
                   "tensor_pipe_pct": a["pipe"] / a["n"], "source": a["source"]}
