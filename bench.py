@@ -68,6 +68,10 @@ def parse():
     ap.add_argument("--src-hi", type=int, default=None)
     ap.add_argument("--cpu-sample", type=int, default=None, help="utterances in the CPU sample (default: 4 beside the GPU "
                     "arm, 8 = the reference's own DataLoader batch size in the reference arm)")
+    ap.add_argument("--zero-shot", default="auto", choices=["auto", "on", "off"],
+                    help="include the zero-shot path's speaker encoder in the step: the DeepSpeaker embedding of one reference "
+                         "recording per batch (synthesize_zeroshot_*.py) computed on the GPU and used for every utterance "
+                         "(auto: on for C4, BASELINE.json's zero-shot config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel launch profile / roofline pass")
     ap.add_argument("--graphs", default="auto", choices=["auto", "on", "off"],
@@ -389,6 +393,7 @@ def main():
 
     lib = _lib.load()
     use_graphs = args.graphs == "on" or (args.graphs == "auto" and args.config in ("C1", "C3"))
+    zero_shot = args.zero_shot == "on" or (args.zero_shot == "auto" and args.config == "C4")
     pipe = Pipeline(spec, sd, hifigan_sd, dev, precision=args.precision, tc_frontend=not args.ffma_frontend, graphs=use_graphs)
 
     def barrier():
@@ -445,20 +450,47 @@ def main():
         d_spk = None if h_spk is None else h_spk.to(dev)
         synth = ShardedSynthesizer(pipe, dist if world > 1 else None, padding=padding, counts=counts, dst=0)
 
+        # zero-shot (BASELINE.json configs[3]; synthesize_zeroshot_lj.py:93-102): every utterance of the batch is conditioned on
+        # the DeepSpeaker embedding of ONE reference recording, computed inside the step (cmtts_rescnn_forward).  The host side
+        # of it (WAV decode, filter-bank features: numpy, as in the reference) runs once, outside the timed region; its
+        # 160 x 64 window is resident (value) or uploaded from pinned memory every step (e2e).
+        zs_enc, zs_src = None, None
+        if zero_shot and h_spk is not None and len(rows):
+            from cmtts_b200 import speaker_encoder as SE
+            zs_enc = SE.DeepSpeakerModel(str(dev))
+            ck = os.path.join(ROOT, "oracle", "_ref", "deepspeaker", "pretrained_models", "ResCNN_triplet_training_checkpoint_265.h5")
+            if os.path.isfile(ck):
+                zs_enc.load_weights(ck)
+                zs_src = "reference checkpoint ResCNN_triplet_training_checkpoint_265.h5"
+            else:
+                zs_enc.set_keras_weights(synthetic.make_deepspeaker_weights(seed=0))
+                zs_src = "synthetic weights (checkpoint not staged)"
+            mfcc = SE.read_mfcc(synthetic.make_voice_like(2.5, SE.SAMPLE_RATE, seed=3), SE.SAMPLE_RATE, SE.WIN_LENGTH)
+            h_fb = torch.from_numpy(SE.sample_from_mfcc(mfcc, SE.NUM_FRAMES, offset=0)[None, ..., 0].copy()).pin_memory()
+            d_fb = h_fb.to(dev)
+            n_rows = int(h_spk.shape[0])
+
+        def zs_embed(fb):
+            return zs_enc.predict_tensor(fb).expand(n_rows, -1).contiguous()
+
         def step_resident():
-            return synth.run(d_texts, d_lens, d_spk, args.T, gather=(world > 1))
+            spk = zs_embed(d_fb) if zs_enc is not None else d_spk
+            return synth.run(d_texts, d_lens, spk, args.T, gather=(world > 1))
 
         def step_e2e():
             t = h_texts.to(dev, non_blocking=True)
             l = h_lens.to(dev, non_blocking=True)
-            s = None if h_spk is None else h_spk.to(dev, non_blocking=True)
+            if zs_enc is not None:
+                s = zs_embed(h_fb.to(dev, non_blocking=True))
+            else:
+                s = None if h_spk is None else h_spk.to(dev, non_blocking=True)
             out = synth.run(t, l, s, args.T, gather=(world > 1))
             w = to_pinned("wav", out["wav_i16"])
             ml = to_pinned("mel_lens", out["mel_lens"])
             torch.cuda.current_stream(dev).synchronize()          # the step's result is on the host
             return w, ml
 
-        h2d = h_texts.numel() * 8 + h_lens.numel() * 8 + (0 if h_spk is None else h_spk.numel() * 4)
+        h2d = h_texts.numel() * 8 + h_lens.numel() * 8 + (0 if h_spk is None else (h_fb.numel() if zs_enc is not None else h_spk.numel()) * 4)
 
     # ---- warm-up (the clock sampler is already running: nvidia-smi needs a moment before its first report) ----
     clocks = ClockSampler(local_rank)
@@ -518,6 +550,22 @@ def main():
         stage_ms = synth.stage_times(d_texts, d_lens, d_spk, args.T, reps=max(2, min(args.steps, 5))) if B else {}
         af = acoustic_flops(spec, B, Tsrc, L, args.T)
         stage_flops = {"dpen": af["encoder"] + af["variance"], "sampler": af["denoiser"], "vocoder": hf * B * L}
+        if zs_enc is not None and B:
+            z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            zs_embed(d_fb)
+            z0.record()
+            for _ in range(5):
+                zs_embed(d_fb)
+            z1.record()
+            torch.cuda.synchronize(dev)
+            stage_ms["speaker_encoder"] = z0.elapsed_time(z1) / 5
+            # 28 convs of the ResCNN on a 160 x 64 window (deepspeaker/conv_models.py:110-133) + Dense
+            zf, hh, ww, ci = 0.0, 160, 64, 1
+            for co in (64, 128, 256, 512):
+                hh, ww = (hh + 1) // 2, (ww + 1) // 2
+                zf += 2.0 * hh * ww * co * (25 * ci + 6 * 9 * co)
+                ci = co
+            stage_flops["speaker_encoder"] = zf + 2.0 * 2048 * 512
         total_flops = sum(stage_flops.values())
         # RTF as p_rtf_cm.py defines it (informational; every rank computes its own, rank 0 reports)
         from cmtts_b200.synthesize import rtf_like_reference
@@ -525,7 +573,7 @@ def main():
         def prof_step():                 # the profiler times launches: one EAGER step (graph replays launch nothing through the library)
             was, pipe.graphs = pipe.graphs, False
             try:
-                pipe(d_texts, d_lens, d_spk, T=args.T)
+                pipe(d_texts, d_lens, zs_embed(d_fb) if zs_enc is not None else d_spk, T=args.T)
             finally:
                 pipe.graphs = was
     prof = None
@@ -565,6 +613,7 @@ def main():
                                     "local": "per-shard L_max (length-bucketed shards; each shard = the reference run on its rows)",
                                     "n/a": "fixed-length mels"}[padding] if world > 1 else "single batch",
                    "cuda_graphs": bool(use_graphs), "graph_replays": int(pipe.graph_replays),
+                   "zero_shot_speaker_encoder": (zs_src if args.config != "C5" and zs_enc is not None else None),
                    "collation": "async gather of int16 wavs + mel_lens to rank 0, inside the timed region" if world > 1 else "none",
                    "l2_policy": "working set (GBs of activations per step) is far larger than the 126 MB L2; no flush needed"
                    if B * L >= 8000 else "small batch: activations of consecutive launches stay L2-resident by design "

@@ -64,6 +64,11 @@ class ModelSpec:
     res_channels: int = 256
     multi_speaker: bool = False
     ext_speaker_dim: int = 512
+    # `speaker_embedder: none` (cmtts.py:27-37): an nn.Embedding(n_speaker, hidden) table indexed by the batch's speaker ids
+    # instead of a Linear over external 512-d embeddings.  0 = external embeddings.  On the device the table is the
+    # Linear's weight over one-hot rows (exact: one product with 1.0, the rest with 0.0), ext_speaker_dim = n_speakers
+    # rounded up to a multiple of 16.
+    n_speakers: int = 0
     # consistency model (train.yaml cm block; karras_diffusion.py / script_util.py:66-73)
     sigma_min: float = 0.002
     sigma_max: float = 80.0
@@ -120,8 +125,10 @@ class ModelSpec:
             raise NotImplementedError("only linear energy quantization (all shipped configs)")
         if tr["ffn_padding"] != "SAME":
             raise NotImplementedError("only ffn_padding SAME (all shipped configs)")
+        n_speakers = 0
         if model_config["multi_speaker"] and pp.get("speaker_embedder", "none") == "none":
-            raise NotImplementedError("speaker-id embedding table path (speaker_embedder 'none')")
+            with open(os.path.join(preprocess_config["path"]["preprocessed_path"], "speakers.json")) as f:   # cmtts.py:28-34
+                n_speakers = len(json.load(f))
         if stats is None:
             p = os.path.join(preprocess_config["path"]["preprocessed_path"], "stats.json")
             with open(p) as f:
@@ -141,7 +148,8 @@ class ModelSpec:
             energy_min=float(e_min), energy_max=float(e_max),
             n_mels=pp["mel"]["n_mel_channels"], res_layers=dn["residual_layers"],
             res_channels=dn["residual_channels"], multi_speaker=bool(model_config["multi_speaker"]),
-            ext_speaker_dim=int(model_config.get("external_speaker_dim", 512)),
+            ext_speaker_dim=((n_speakers + 15) // 16 * 16) if n_speakers else int(model_config.get("external_speaker_dim", 512)),
+            n_speakers=n_speakers,
             sigma_min=float(cm.get("sigma_min", 0.002)), sigma_max=float(cm.get("sigma_max", 80.0)),
             sampling_rate=pp["audio"]["sampling_rate"], hop_length=pp["stft"]["hop_length"],
             max_wav_value=float(pp["audio"]["max_wav_value"]), max_seq_len=model_config["max_seq_len"],

@@ -16,11 +16,11 @@
 
 namespace {
 
-constexpr int PIX = 8;          // output positions per thread (along W)
 constexpr int CI_CHUNK = 32;    // input channels staged per pass
 
-// grid: (ceil(Wout / PIX) * Hout, ceil(Cout / blockDim.x), B); block: min(Cout, 128) threads
-template <int K>
+// grid: (ceil(Wout / PIX) * Hout, ceil(Cout / blockDim.x), B); block: 64 or 128 threads (<= Cout)
+// PIX = output positions per thread along W (8; 4 for the last stage, whose rows are 4 wide)
+template <int K, int PIX>
 __global__ void __launch_bounds__(128)
 rescnn_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
                    const float* __restrict__ shift, const float* __restrict__ res, float* __restrict__ out,
@@ -135,21 +135,34 @@ inline int same_pad_before(int in, int k, int stride) {
     return total / 2;                                       // TensorFlow puts the odd element after
 }
 
+template <int K, int PIX>
+void launch_conv_t(const float* x, const float* w, const float* sc, const float* sh, const float* res, float* out, int B, int H,
+                   int W, int Cin, int Cout, int stride, cudaStream_t s) {
+    const int Hout = same_out(H, stride), Wout = same_out(W, stride);
+    const int wtiles = (Wout + PIX - 1) / PIX;
+    // 128 threads (4 warps of 32 output channels) unless that leaves most SMs without a block (the late, small stages)
+    int threads = Cout < 128 ? ((Cout + 31) / 32) * 32 : 128;
+    if (threads == 128 && (long long)wtiles * Hout * (Cout / 128) * B < 148) threads = 64;
+    dim3 grid(wtiles * Hout, (Cout + threads - 1) / threads, B);
+    const size_t smem = (size_t)K * ((PIX - 1) * stride + K) * CI_CHUNK * sizeof(float);
+    rescnn_conv_kernel<K, PIX><<<grid, threads, smem, s>>>(x, w, sc, sh, res, out, H, W, Cin, Hout, Wout, Cout, stride,
+                                                            same_pad_before(H, K, stride), same_pad_before(W, K, stride));
+}
+
 int launch_conv(const float* x, const float* w, const float* sc, const float* sh, const float* res, float* out, int B,
                 int H, int W, int Cin, int Cout, int K, int stride, cudaStream_t s) {
     const int Hout = same_out(H, stride), Wout = same_out(W, stride);
-    const int threads = Cout < 128 ? ((Cout + 31) / 32) * 32 : 128;
-    dim3 grid(((Wout + PIX - 1) / PIX) * Hout, (Cout + threads - 1) / threads, B);
-    const size_t smem = (size_t)K * ((PIX - 1) * stride + K) * CI_CHUNK * sizeof(float);
-    const int ph = same_pad_before(H, K, stride), pw = same_pad_before(W, K, stride);
     if (g_cmtts_prof_on) {
         char lbl[64];
         snprintf(lbl, sizeof(lbl), "rescnn_conv k%d s%d %d->%d", K, stride, Cin, Cout);
         cmtts_prof_note(lbl, 2.0 * B * Hout * Wout * (double)Cout * K * K * Cin,
                         4.0 * ((double)B * H * W * Cin + (double)B * Hout * Wout * Cout * (res ? 2 : 1) + (double)K * K * Cin * Cout));
     }
-    if (K == 5) rescnn_conv_kernel<5><<<grid, threads, smem, s>>>(x, w, sc, sh, res, out, H, W, Cin, Hout, Wout, Cout, stride, ph, pw);
-    else if (K == 3) rescnn_conv_kernel<3><<<grid, threads, smem, s>>>(x, w, sc, sh, res, out, H, W, Cin, Hout, Wout, Cout, stride, ph, pw);
+    const bool narrow = Wout <= 4;
+    if (K == 5 && !narrow) launch_conv_t<5, 8>(x, w, sc, sh, res, out, B, H, W, Cin, Cout, stride, s);
+    else if (K == 5) launch_conv_t<5, 4>(x, w, sc, sh, res, out, B, H, W, Cin, Cout, stride, s);
+    else if (K == 3 && !narrow) launch_conv_t<3, 8>(x, w, sc, sh, res, out, B, H, W, Cin, Cout, stride, s);
+    else if (K == 3) launch_conv_t<3, 4>(x, w, sc, sh, res, out, B, H, W, Cin, Cout, stride, s);
     else { cmtts_set_error("rescnn: kernel size must be 3 or 5", __FILE__, __LINE__); return CMTTS_ERR_ARG; }
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;

@@ -54,6 +54,7 @@ class DurationPitchSpeakerNet:
         if p_targets is not None or e_targets is not None or d_targets is not None:
             raise NotImplementedError("teacher-forced targets are a training path (out of scope)")
         max_mel_len = None if mels is None else int(mels.shape[2])  # cmtts.py:60-63
+        spker_embeds = self.owner.speaker_input(speakers, spker_embeds)
         return self.owner.dpen(texts, src_lens, spker_embeds, max_mel_len, float(p_control),
                                float(e_control), float(d_control))
 
@@ -202,6 +203,22 @@ class CMTotalTTS:
             raise IndexError(f"token id outside [0, {self.spec.vocab}) (wrong symbol table?)")
         return int(m), []
 
+    def speaker_input(self, speakers, spker_embeds):
+        """What `dpen` takes as its speaker argument: the external embeddings (cmtts.py:79-81), or — `speaker_embedder: none`,
+        cmtts.py:76-78 `self.speaker_emb(speakers)` — one-hot rows of the speaker ids, which the packed table turns into
+        the embedding rows exactly.  An id outside the table raises IndexError as nn.Embedding does."""
+        n = self.spec.n_speakers
+        if not n:
+            return spker_embeds
+        if speakers is None:
+            raise AssertionError("speaker ids are needed (speaker_embedder: none)")
+        ids = torch.as_tensor(speakers).to(torch.int64).reshape(-1)
+        if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= n):
+            raise IndexError(f"speaker id outside [0, {n})")
+        onehot = torch.zeros(ids.numel(), self.spec.ext_speaker_dim, dtype=torch.float32, device=ids.device)
+        onehot[torch.arange(ids.numel(), device=ids.device), ids] = 1.0
+        return onehot
+
     def prepare_inputs(self, texts, src_lens, spker_embeds):
         """Host-side checks the reference makes, then contiguous device tensors."""
         s, dev = self.spec, self.device
@@ -292,7 +309,7 @@ class CMTotalTTS:
         then the denoiser on x (already scaled by c_in by the caller).  -> (B,1,L,80)."""
         if pitch is not None:
             raise NotImplementedError("training targets are out of scope")
-        out = self.dpen(texts, src_lens, spker_embeds, int(x.shape[2]), p_control, e_control, d_control)
+        out = self.dpen(texts, src_lens, self.speaker_input(speakers, spker_embeds), int(x.shape[2]), p_control, e_control, d_control)
         steps = self.prepare_steps(timesteps, out["speaker_emb"])
         return self.denoise_step(x, out["cond"], steps)
 

@@ -96,7 +96,7 @@ class _FusedDistiller:
     def conditioner(self, L: int) -> dict:
         if self.cond is None or self.cond["cond"].shape[1] != L:
             kw = self.kw
-            self.cond = self.model.dpen(kw["texts"], kw["src_lens"], kw.get("spker_embeds"), L,
+            self.cond = self.model.dpen(kw["texts"], kw["src_lens"], self.model.speaker_input(kw.get("speakers"), kw.get("spker_embeds")), L,
                                         kw.get("p_control", 1.0), kw.get("e_control", 1.0), kw.get("d_control", 1.0))
         return self.cond
 

@@ -111,8 +111,11 @@ def make_acoustic_state_dict(spec: ModelSpec, seed: int = 0) -> "OrderedDict[str
     ee[0] = 0.0
     sd[va + "energy_embedding.weight"] = ee
     if spec.multi_speaker:
-        sd["duration_pitch_energy_net.speaker_emb.weight"] = d.normal((H, spec.ext_speaker_dim), 0.1)
-        sd["duration_pitch_energy_net.speaker_emb.bias"] = d.normal((H,), 0.02)
+        if getattr(spec, "n_speakers", 0):            # nn.Embedding table (speaker_embedder: none)
+            sd["duration_pitch_energy_net.speaker_emb.weight"] = d.normal((spec.n_speakers, H), 1.0)
+        else:
+            sd["duration_pitch_energy_net.speaker_emb.weight"] = d.normal((H, spec.ext_speaker_dim), 0.1)
+            sd["duration_pitch_energy_net.speaker_emb.bias"] = d.normal((H,), 0.02)
 
     C = spec.res_channels
     M = spec.n_mels
@@ -234,3 +237,46 @@ def write_acoustic_checkpoint(root: str, spec: ModelSpec, seed: int = 0, step: i
     f = os.path.join(p, "model{:06d}.pt".format(step))
     torch.save(make_acoustic_state_dict(spec, seed), f)
     return f
+
+
+def make_deepspeaker_weights(seed: int = 0, scale: float = 1.0):
+    """Random DeepSpeaker ResCNN weights in the naming / shapes of the reference's Keras checkpoint
+    ({'<layer>/kernel:0', '<layer>_bn/gamma:0', ..., 'affine/kernel:0'}; deepspeaker/conv_models.py:83-131) — for tests and
+    bench runs on boxes where the 97 MB checkpoint is not staged."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    w = {}
+    cin = 1
+
+    def conv(name, k, ci, co):
+        w[f"{name}/kernel:0"] = (rng.standard_normal((k, k, ci, co)) * scale / np.sqrt(k * k * ci)).astype(np.float32)
+        w[f"{name}/bias:0"] = (rng.standard_normal(co) * 0.05).astype(np.float32)
+        w[f"{name}_bn/gamma:0"] = (1.0 + 0.2 * rng.standard_normal(co)).astype(np.float32)
+        w[f"{name}_bn/beta:0"] = (0.3 * rng.standard_normal(co)).astype(np.float32)
+        w[f"{name}_bn/moving_mean:0"] = (0.1 * rng.standard_normal(co)).astype(np.float32)
+        w[f"{name}_bn/moving_variance:0"] = (0.5 + rng.random(co)).astype(np.float32)
+
+    for stage, f in enumerate((64, 128, 256, 512), start=1):
+        conv(f"conv{f}-s", 5, cin, f)
+        for blk in range(3):
+            conv(f"res{stage}_{blk}_branch_2a", 3, f, f)
+            conv(f"res{stage}_{blk}_branch_2b", 3, f, f)
+        cin = f
+    w["affine/kernel:0"] = (rng.standard_normal((2048, 512)) / np.sqrt(2048)).astype(np.float32)
+    w["affine/bias:0"] = (rng.standard_normal(512) * 0.05).astype(np.float32)
+    return w
+
+
+def make_voice_like(seconds: float = 2.5, sr: int = 22050, seed: int = 0):
+    """Harmonic signal with a moving pitch, amplitude modulation, a little noise and a quiet head / tail (a stand-in for a
+    reference recording of the zero-shot path) -> float32 in [-1, 1]."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    t = np.arange(int(seconds * sr)) / sr
+    f0 = 120 + 40 * np.sin(2 * np.pi * 0.7 * t)
+    ph = 2 * np.pi * np.cumsum(f0) / sr
+    x = sum(np.sin(k * ph) / k for k in range(1, 12)) * (0.5 + 0.5 * np.sin(2 * np.pi * 3 * t) ** 2)
+    x = 0.2 * x / np.abs(x).max() + 0.002 * rng.standard_normal(t.size)
+    x[: sr // 5] *= 0.01
+    x[-sr // 5:] *= 0.01
+    return x.astype(np.float32)

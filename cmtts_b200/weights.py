@@ -250,7 +250,7 @@ class PackedAcoustic:
             "net.output_projection.conv.weight": (s.n_mels, s.res_channels, 1),
         }
         if s.multi_speaker:
-            need[SPK + "weight"] = (s.hidden, s.ext_speaker_dim)
+            need[SPK + "weight"] = (s.n_speakers, s.hidden) if s.n_speakers else (s.hidden, s.ext_speaker_dim)
             need["net.residual_layers.0.speaker_projection.linear.weight"] = (s.res_channels, s.hidden)
         for k, shp in need.items():
             if k not in sd:
@@ -294,7 +294,12 @@ class PackedAcoustic:
 
         va = _Table(dev)
         if s.multi_speaker:
-            va.add(lin_w(sd[SPK + "weight"])); va.add(sd[SPK + "bias"])
+            if s.n_speakers:        # nn.Embedding table (n_speaker, H) == the [in][out] weight of a Linear over one-hot rows
+                tab = torch.zeros(s.ext_speaker_dim, s.hidden, dtype=torch.float32)
+                tab[: s.n_speakers] = sd[SPK + "weight"].detach().to(torch.float32).cpu()
+                va.add(tab); va.add(torch.zeros(s.hidden, dtype=torch.float32))
+            else:
+                va.add(lin_w(sd[SPK + "weight"])); va.add(sd[SPK + "bias"])
         else:
             va.add(None); va.add(None)
 

@@ -94,24 +94,5 @@ def rescnn_forward(x: np.ndarray, w: Dict[str, np.ndarray], return_stages: bool 
 
 def synthetic_keras_weights(seed: int = 0, scale: float = 1.0) -> Dict[str, np.ndarray]:
     """Random weights in the checkpoint's naming / shapes (for tests on boxes without the 97 MB file)."""
-    rng = np.random.default_rng(seed)
-    w: Dict[str, np.ndarray] = {}
-    cin = 1
-
-    def conv(name, k, ci, co):
-        w[f"{name}/kernel:0"] = (rng.standard_normal((k, k, ci, co)) * scale / np.sqrt(k * k * ci)).astype(np.float32)
-        w[f"{name}/bias:0"] = (rng.standard_normal(co) * 0.05).astype(np.float32)
-        w[f"{name}_bn/gamma:0"] = (1.0 + 0.2 * rng.standard_normal(co)).astype(np.float32)
-        w[f"{name}_bn/beta:0"] = (0.3 * rng.standard_normal(co)).astype(np.float32)
-        w[f"{name}_bn/moving_mean:0"] = (0.1 * rng.standard_normal(co)).astype(np.float32)
-        w[f"{name}_bn/moving_variance:0"] = (0.5 + rng.random(co)).astype(np.float32)
-
-    for stage, f in enumerate(STAGE_FILTERS, start=1):
-        conv(f"conv{f}-s", 5, cin, f)
-        for blk in range(3):
-            conv(f"res{stage}_{blk}_branch_2a", 3, f, f)
-            conv(f"res{stage}_{blk}_branch_2b", 3, f, f)
-        cin = f
-    w["affine/kernel:0"] = (rng.standard_normal((2048, 512)) / np.sqrt(2048)).astype(np.float32)
-    w["affine/bias:0"] = (rng.standard_normal(512) * 0.05).astype(np.float32)
-    return w
+    from cmtts_b200.synthetic import make_deepspeaker_weights
+    return make_deepspeaker_weights(seed, scale)

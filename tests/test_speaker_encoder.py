@@ -32,16 +32,8 @@ needs_ckpt = pytest.mark.skipif(ckpt_path() is None, reason="reference DeepSpeak
 
 
 def voice_like(seconds=2.5, sr=SE.SAMPLE_RATE, seed=0):
-    """harmonic signal with a moving pitch + noise, silent head and tail"""
-    rng = np.random.default_rng(seed)
-    t = np.arange(int(seconds * sr)) / sr
-    f0 = 120 + 40 * np.sin(2 * np.pi * 0.7 * t)
-    ph = 2 * np.pi * np.cumsum(f0) / sr
-    x = sum(np.sin(k * ph) / k for k in range(1, 12)) * (0.5 + 0.5 * np.sin(2 * np.pi * 3 * t) ** 2)
-    x = 0.2 * x / np.abs(x).max() + 0.002 * rng.standard_normal(t.size)
-    x[: sr // 5] *= 0.01
-    x[-sr // 5:] *= 0.01
-    return x.astype(np.float32)
+    from cmtts_b200.synthetic import make_voice_like
+    return make_voice_like(seconds, sr, seed)
 
 
 # ---------------------------------------------------------------------------------------------------- CPU
