@@ -7,80 +7,91 @@
 // GPU kernels), not tensor-core throughput:
 //   * direct NHWC convolution, TensorFlow "SAME" padding (the extra row / column goes AFTER: stride-2 5x5 convs pad 1 | 2);
 //   * a thread owns one output channel and PIX consecutive output positions of a row, a warp 32 consecutive channels: the
-//     HWIO weight read is one coalesced 128-byte line per (kh, kw, ci), the input patch of the block sits in shared
-//     memory and is read as broadcast float4s (4 input channels per LDS.128);
+//     HWIO weight read is one coalesced 128-byte line per (kh, kw, ci), the warp's input patch sits in shared memory and
+//     is read as broadcast float4s (4 input channels per LDS.128); the reduction over input channels is split over the
+//     warps of a block (the late stages have 40 - 160 output positions: without the split most SMs had nothing to do);
 //   * epilogue: BN scale / shift, clipped ReLU min(max(v, 0), 20), optionally + residual and the clip again — the order
 //     of identity_block (conv_models.py:83-108: the ReLU comes BEFORE the add);
-//   * tail kernel: Reshape((-1, 2048)) + mean over time + Dense(512) + l2_normalize (conv_models.py:52-66).
+//   * tail: Reshape((-1, 2048)) + mean over time + Dense(512), then l2_normalize (conv_models.py:52-66).
 #include "common.cuh"
 
 namespace {
 
-constexpr int CI_CHUNK = 32;    // input channels staged per pass
+constexpr int CI_CHUNK = 32;    // input channels per pass of a warp
+constexpr int MAX_WARPS = 4;
 
-// grid: (ceil(Wout / PIX) * Hout, ceil(Cout / blockDim.x), B); block: 64 or 128 threads (<= Cout)
-// PIX = output positions per thread along W (8; 4 for the last stage, whose rows are 4 wide)
+// One block = PIX consecutive output positions of one output row x 32 output channels.  The reduction over K x K x Cin is
+// SPLIT OVER THE BLOCK'S WARPS by 32-channel chunk (warp w takes chunks w, w + nwarps, ...); partial sums meet in shared
+// memory.  Per (chunk, tap) a thread first issues all 32 weight loads (one coalesced 128-byte line per input channel across
+// the warp) and only then runs the 32 x PIX FMAs: the first version loaded 4 weights, used them, loaded the next 4 — one L2
+// round trip per 16 FMAs, 873 us for a 512 -> 512 layer on a 10 x 4 map (ncu launch list, profiles/launches_r4e_rescnn_summary.txt).
+// grid: (ceil(Wout / PIX) * Hout, Cout / 32, B); block: 32 * min(4, Cin / 32 rounded up) threads
 template <int K, int PIX>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * MAX_WARPS)
 rescnn_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
                    const float* __restrict__ shift, const float* __restrict__ res, float* __restrict__ out,
                    int H, int W, int Cin, int Hout, int Wout, int Cout, int stride, int pad_h, int pad_w) {
-    // input patch of this block: K rows x ((PIX - 1) * stride + K) columns x CI_CHUNK channels
-    extern __shared__ __align__(16) float patch[];
+    extern __shared__ __align__(16) float smem[];          // [nwarps][K][pw][CI_CHUNK] input patches, reused for the reduction
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int wtiles = (Wout + PIX - 1) / PIX;
     const int oh = blockIdx.x / wtiles, ow0 = (blockIdx.x % wtiles) * PIX;
-    const int co = blockIdx.y * blockDim.x + threadIdx.x;
+    const int co = blockIdx.y * 32 + lane;
     const int b = blockIdx.z;
     const int pw = (PIX - 1) * stride + K;                 // patch width in input columns
     const int ih0 = oh * stride - pad_h, iw0 = ow0 * stride - pad_w;
     const float* xb = x + (long long)b * H * W * Cin;
+    float* patch = smem + warp * (K * pw * CI_CHUNK);
+    const bool co_ok = co < Cout;
 
     float acc[PIX];
 #pragma unroll
     for (int p = 0; p < PIX; ++p) acc[p] = 0.f;
 
-    for (int c0 = 0; c0 < Cin; c0 += CI_CHUNK) {
-        const int cn = min(CI_CHUNK, Cin - c0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < K * pw * CI_CHUNK; i += blockDim.x) {
-            const int ci = i % CI_CHUNK, col = (i / CI_CHUNK) % pw, row = i / (CI_CHUNK * pw);
+    const int nchunks = (Cin + CI_CHUNK - 1) / CI_CHUNK;
+    for (int c = warp; c < nchunks; c += nwarps) {
+        const int c0 = c * CI_CHUNK, cn = min(CI_CHUNK, Cin - c0);
+        __syncwarp();
+        for (int i = lane; i < K * pw * CI_CHUNK; i += 32) {            // lane = input channel: one 128-byte line per position
+            const int col = (i / CI_CHUNK) % pw, row = i / (CI_CHUNK * pw);
             const int ih = ih0 + row, iw = iw0 + col;
             float v = 0.f;
-            if (ci < cn && ih >= 0 && ih < H && iw >= 0 && iw < W) v = xb[((long long)ih * W + iw) * Cin + c0 + ci];
+            if (lane < cn && ih >= 0 && ih < H && iw >= 0 && iw < W) v = xb[((long long)ih * W + iw) * Cin + c0 + lane];
             patch[i] = v;
         }
-        __syncthreads();
-        if (co < Cout) {
-            for (int kh = 0; kh < K; ++kh) {
-                for (int kw = 0; kw < K; ++kw) {
-                    const float* wp = w + ((long long)(kh * K + kw) * Cin + c0) * Cout + co;
-                    const float* pp = patch + (kh * pw + kw) * CI_CHUNK;
-                    if (cn == CI_CHUNK) {
-#pragma unroll 2
-                        for (int ci = 0; ci < CI_CHUNK; ci += 4) {
-                            const float w0 = wp[(long long)ci * Cout], w1 = wp[(long long)(ci + 1) * Cout];
-                            const float w2 = wp[(long long)(ci + 2) * Cout], w3 = wp[(long long)(ci + 3) * Cout];
+        __syncwarp();
+        for (int kh = 0; kh < K; ++kh) {
+            for (int kw = 0; kw < K; ++kw) {
+                const float* wp = w + ((long long)(kh * K + kw) * Cin + c0) * Cout + co;
+                float wv[CI_CHUNK];
 #pragma unroll
-                            for (int p = 0; p < PIX; ++p) {
-                                const float4 xv = *reinterpret_cast<const float4*>(pp + p * stride * CI_CHUNK + ci);
-                                acc[p] = fmaf(xv.x, w0, acc[p]);
-                                acc[p] = fmaf(xv.y, w1, acc[p]);
-                                acc[p] = fmaf(xv.z, w2, acc[p]);
-                                acc[p] = fmaf(xv.w, w3, acc[p]);
-                            }
-                        }
-                    } else {
-                        for (int ci = 0; ci < cn; ++ci) {
-                            const float wv = wp[(long long)ci * Cout];
+                for (int ci = 0; ci < CI_CHUNK; ++ci) wv[ci] = (co_ok && ci < cn) ? wp[(long long)ci * Cout] : 0.f;
+                const float* pp = patch + (kh * pw + kw) * CI_CHUNK;
 #pragma unroll
-                            for (int p = 0; p < PIX; ++p) acc[p] = fmaf(pp[p * stride * CI_CHUNK + ci], wv, acc[p]);
-                        }
+                for (int ci = 0; ci < CI_CHUNK; ci += 4) {
+#pragma unroll
+                    for (int p = 0; p < PIX; ++p) {
+                        const float4 xv = *reinterpret_cast<const float4*>(pp + p * stride * CI_CHUNK + ci);
+                        acc[p] = fmaf(xv.x, wv[ci], acc[p]);
+                        acc[p] = fmaf(xv.y, wv[ci + 1], acc[p]);
+                        acc[p] = fmaf(xv.z, wv[ci + 2], acc[p]);
+                        acc[p] = fmaf(xv.w, wv[ci + 3], acc[p]);
                     }
                 }
             }
         }
     }
-    if (co >= Cout) return;
+    // partial sums of the warps -> warp 0 (fixed order: the result does not depend on scheduling)
+    __syncthreads();
+    if (warp > 0) {
+#pragma unroll
+        for (int p = 0; p < PIX; ++p) smem[((warp - 1) * PIX + p) * 32 + lane] = acc[p];
+    }
+    __syncthreads();
+    if (warp > 0 || !co_ok) return;
+    for (int wq = 1; wq < nwarps; ++wq) {
+#pragma unroll
+        for (int p = 0; p < PIX; ++p) acc[p] += smem[((wq - 1) * PIX + p) * 32 + lane];
+    }
     const float sc = scale[co], sh = shift[co];
 #pragma unroll
     for (int p = 0; p < PIX; ++p) {
@@ -93,10 +104,13 @@ rescnn_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, con
     }
 }
 
-// Reshape((-1, W*C)) + mean over time + Dense + l2_normalize; one block per utterance, blockDim.x == n_out
-__global__ void rescnn_tail_kernel(const float* __restrict__ x, const float* __restrict__ wd, const float* __restrict__ bd,
-                                   float* __restrict__ emb, int H, int feat, int n_out) {
-    extern __shared__ float m[];                            // [feat] means, then [32] partial sums
+// Reshape((-1, W*C)) + mean over time + Dense: grid (B, n_out / 32), 8 warps per block; warp w reduces the k range
+// [w, w + 1) * feat / 8 for the block's 32 outputs (coalesced 128-byte weight lines), partial sums meet in shared memory.
+// (One block per utterance spent 223 us streaming the 4 MB dense kernel through a single SM.)
+__global__ void __launch_bounds__(256)
+rescnn_dense_kernel(const float* __restrict__ x, const float* __restrict__ wd, const float* __restrict__ bd,
+                    float* __restrict__ emb, int H, int feat, int n_out) {
+    extern __shared__ float m[];                            // [feat] means, then [8][32] partial sums
     float* red = m + feat;
     const float* xb = x + (long long)blockIdx.x * H * feat;
     for (int f = threadIdx.x; f < feat; f += blockDim.x) {
@@ -105,26 +119,42 @@ __global__ void rescnn_tail_kernel(const float* __restrict__ x, const float* __r
         m[f] = s / (float)H;
     }
     __syncthreads();
-    const int n = threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.y * 32 + lane;
+    const int k0 = (int)((long long)feat * warp / 8), k1 = (int)((long long)feat * (warp + 1) / 8);
     float v = 0.f;
     if (n < n_out) {
-        for (int k = 0; k < feat; ++k) v = fmaf(m[k], wd[(long long)k * n_out + n], v);
-        v += bd[n];
+#pragma unroll 16
+        for (int k = k0; k < k1; ++k) v = fmaf(m[k], wd[(long long)k * n_out + n], v);
     }
-    float sq = (n < n_out) ? v * v : 0.f;
+    red[warp * 32 + lane] = v;
+    __syncthreads();
+    if (warp == 0 && n < n_out) {
+        float t = bd[n];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += red[q * 32 + lane];
+        emb[(long long)blockIdx.x * n_out + n] = t;
+    }
+}
+
+// K.l2_normalize(axis=1): x / sqrt(max(sum(x^2), 1e-12)), in place; one block per utterance, blockDim.x == n_out (<= 1024)
+__global__ void rescnn_l2norm_kernel(float* __restrict__ emb, int n_out) {
+    __shared__ float red[32];
+    const int n = threadIdx.x;
+    const float v = emb[(long long)blockIdx.x * n_out + n];
+    float sq = v * v;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+    if ((n & 31) == 0) red[n >> 5] = sq;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        float t = (threadIdx.x < (blockDim.x + 31) / 32) ? red[threadIdx.x] : 0.f;
+    if (n < 32) {
+        float t = (n < (int)(blockDim.x >> 5)) ? red[n] : 0.f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (threadIdx.x == 0) red[0] = t;
+        if (n == 0) red[0] = t;
     }
     __syncthreads();
-    // K.l2_normalize: x * rsqrt(max(sum(x^2), 1e-12))
-    if (n < n_out) emb[(long long)blockIdx.x * n_out + n] = v / sqrtf(fmaxf(red[0], 1e-12f));
+    emb[(long long)blockIdx.x * n_out + n] = v / sqrtf(fmaxf(red[0], 1e-12f));
 }
 
 inline int same_out(int in, int stride) { return (in + stride - 1) / stride; }
@@ -140,13 +170,12 @@ void launch_conv_t(const float* x, const float* w, const float* sc, const float*
                    int W, int Cin, int Cout, int stride, cudaStream_t s) {
     const int Hout = same_out(H, stride), Wout = same_out(W, stride);
     const int wtiles = (Wout + PIX - 1) / PIX;
-    // 128 threads (4 warps of 32 output channels) unless that leaves most SMs without a block (the late, small stages)
-    int threads = Cout < 128 ? ((Cout + 31) / 32) * 32 : 128;
-    if (threads == 128 && (long long)wtiles * Hout * (Cout / 128) * B < 148) threads = 64;
-    dim3 grid(wtiles * Hout, (Cout + threads - 1) / threads, B);
-    const size_t smem = (size_t)K * ((PIX - 1) * stride + K) * CI_CHUNK * sizeof(float);
-    rescnn_conv_kernel<K, PIX><<<grid, threads, smem, s>>>(x, w, sc, sh, res, out, H, W, Cin, Hout, Wout, Cout, stride,
-                                                            same_pad_before(H, K, stride), same_pad_before(W, K, stride));
+    const int nchunks = (Cin + CI_CHUNK - 1) / CI_CHUNK;
+    const int nwarps = nchunks < MAX_WARPS ? nchunks : MAX_WARPS;
+    dim3 grid(wtiles * Hout, (Cout + 31) / 32, B);
+    const size_t smem = (size_t)nwarps * K * ((PIX - 1) * stride + K) * CI_CHUNK * sizeof(float);
+    rescnn_conv_kernel<K, PIX><<<grid, 32 * nwarps, smem, s>>>(x, w, sc, sh, res, out, H, W, Cin, Hout, Wout, Cout, stride,
+                                                                same_pad_before(H, K, stride), same_pad_before(W, K, stride));
 }
 
 int launch_conv(const float* x, const float* w, const float* sc, const float* sh, const float* res, float* out, int B,
@@ -218,9 +247,11 @@ extern "C" int cmtts_rescnn_forward(const int32_t* cfg, const void* const* w, co
     }
     const int feat = W * Cin;
     CMTTS_REQUIRE(feat <= 8192, "rescnn: feature width too large for the tail kernel");
-    if (g_cmtts_prof_on) cmtts_prof_note("rescnn_tail mean + dense + l2norm", 2.0 * B * feat * NOUT, 4.0 * ((double)B * H * feat + (double)feat * NOUT));
-    rescnn_tail_kernel<<<B, NOUT, (feat + 32) * sizeof(float), s>>>(cur, (const float*)w[3 * CONVS], (const float*)w[3 * CONVS + 1], emb,
-                                                                     H, feat, NOUT);
+    if (g_cmtts_prof_on) cmtts_prof_note("rescnn_dense mean + dense", 2.0 * B * feat * NOUT, 4.0 * ((double)B * H * feat + (double)feat * NOUT));
+    rescnn_dense_kernel<<<dim3(B, NOUT / 32), 256, (feat + 256) * sizeof(float), s>>>(cur, (const float*)w[3 * CONVS],
+                                                                                     (const float*)w[3 * CONVS + 1], emb, H, feat, NOUT);
+    CMTTS_CHECK_LAUNCH();
+    rescnn_l2norm_kernel<<<B, NOUT, 0, s>>>(emb, NOUT);
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }
