@@ -24,7 +24,7 @@ constexpr int MAX_WARPS = 4;
 // SPLIT OVER THE BLOCK'S WARPS by 32-channel chunk (warp w takes chunks w, w + nwarps, ...); partial sums meet in shared
 // memory.  Per (chunk, tap) a thread first issues all 32 weight loads (one coalesced 128-byte line per input channel across
 // the warp) and only then runs the 32 x PIX FMAs: the first version loaded 4 weights, used them, loaded the next 4 — one L2
-// round trip per 16 FMAs, 873 us for a 512 -> 512 layer on a 10 x 4 map (ncu launch list, profiles/launches_r4e_rescnn_summary.txt).
+// round trip per 16 FMAs, 873 us for a 512 -> 512 layer on a 10 x 4 map (ncu launch list, profiles/launches_r4_rescnn_before_summary.txt).
 // grid: (ceil(Wout / PIX) * Hout, Cout / 32, B); block: 32 * min(4, Cin / 32 rounded up) threads
 template <int K, int PIX>
 __global__ void __launch_bounds__(32 * MAX_WARPS)
