@@ -1110,6 +1110,7 @@ extern "C" int cmtts_variance_token_tc(const cmtts_dims* d, const void* const* w
     if (d->multi_speaker) {
         CMTTS_REQUIRE(spker_embeds != nullptr && spk_emb != nullptr, "Speaker embedding should not be None");
         ConvParams p = conv_same(spker_embeds, 1, B, d->spk_dim, F(w, ix.spk_w), F(w, ix.spk_b), C, 1, 1, spk_emb);
+        p.few_rows_ok = 1;          // B rows: the 128-row tile kernel ran this on ONE CTA (40-54 us); see few_rows_linear_kernel
         CMTTS_TRY(launch_conv1d_simt(p, s));
         CMTTS_TRY(launch_add_rowvec(x, spk_emb, B, T, C, s));
     }
@@ -1127,11 +1128,14 @@ extern "C" int cmtts_variance_token_tc(const cmtts_dims* d, const void* const* w
         const int h = d->cwt_hidden;
         ConvParams p = conv_same(out1, 1, B, C, F(w, ix.st0), F(w, ix.st0 + 1), h, 1, 1, st1);
         p.x_ld = T * C; p.act = ACT_RELU;
+        p.few_rows_ok = 1;          // B rows: the 128-row tile kernel ran this on ONE CTA (40-54 us); see few_rows_linear_kernel
         CMTTS_TRY(launch_conv1d_simt(p, s));
         p = conv_same(st1, 1, B, h, F(w, ix.st0 + 2), F(w, ix.st0 + 3), h, 1, 1, st2);
         p.act = ACT_RELU;
+        p.few_rows_ok = 1;          // B rows: the 128-row tile kernel ran this on ONE CTA (40-54 us); see few_rows_linear_kernel
         CMTTS_TRY(launch_conv1d_simt(p, s));
         p = conv_same(st2, 1, B, h, F(w, ix.st0 + 4), F(w, ix.st0 + 5), 4, 1, 1, f0_stats);
+        p.few_rows_ok = 1;          // B rows: the 128-row tile kernel ran this on ONE CTA (40-54 us); see few_rows_linear_kernel
         CMTTS_TRY(launch_conv1d_simt(p, s));
     }
     return CMTTS_OK;
