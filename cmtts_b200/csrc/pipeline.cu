@@ -678,8 +678,8 @@ extern "C" int cmtts_denoiser_cond_tc(const cmtts_dims* d, const void* const* w,
     CMTTS_REQUIRE(ws_bytes >= cmtts_denoiser_cond_tc_workspace_bytes(d, B_, L_), "denoiser_cond_tc: workspace too small");
     CMTTS_REQUIRE(C % 128 == 0 && H % 64 == 0, "denoiser_cond_tc: channel counts must suit the 128x128x64 UMMA tiling");
     CMTTS_REQUIRE((long long)B * (L + 1) < (1ll << 31), "denoiser_cond_tc: too many rows");
-    CMTTS_REQUIRE(cond && cond_proj && ((uintptr_t)cond_proj % 16) == 0, "denoiser_cond_tc: null or misaligned tensor");
     if (B == 0 || L == 0) return CMTTS_OK;
+    CMTTS_REQUIRE(cond && cond_proj && ((uintptr_t)cond_proj % 16) == 0, "denoiser_cond_tc: null or misaligned tensor");
     const int Lp = L + 1, R = B * Lp;
     Carver cv(ws, ws_bytes);
     __half* c_hi = cv.take<__half>((size_t)R * H);
@@ -725,8 +725,8 @@ extern "C" int cmtts_denoiser_forward_tc(const cmtts_dims* d, const void* const*
     CMTTS_REQUIRE(C % 128 == 0 && H % 64 == 0, "denoiser_tc: channel counts must suit the 128x128x64 UMMA tiling");
     CMTTS_REQUIRE(M <= 128, "denoiser_tc: n_mels must be <= 128");
     CMTTS_REQUIRE((long long)B * (L + 1) < (1ll << 31), "denoiser_tc: too many rows");
+    if (B == 0 || L == 0) return CMTTS_OK;                  // an empty shard (more ranks than utterances): nothing to do, null tensors are fine
     CMTTS_REQUIRE(cond_proj != nullptr && ((uintptr_t)cond_proj % 16) == 0, "denoiser_tc: conditioner projections (cmtts_denoiser_cond_tc) missing");
-    if (B == 0 || L == 0) return CMTTS_OK;
     const int Lp = L + 1, R = B * Lp;
     Carver cv(ws, ws_bytes);
     float* v = cv.take<float>((size_t)R * C);

@@ -334,3 +334,24 @@ def test_acoustic_path_is_batch_invariant_under_global_padding(ds, B, lo, hi, T,
         assert torch.equal(sub["mel_lens"], full["mel_lens"][rows])
         assert torch.equal(sub["mel"], full["mel"][rows])
         assert torch.equal(sub["wav_i16"], full["wav_i16"][rows])
+
+
+@pytest.mark.parametrize("precision", ["tc", "fp32"])
+def test_empty_batch_through_the_pipeline(precision):
+    """A rank of a sharded run can hold ZERO utterances (more GPUs than rows): every stage has to accept B = 0 and return
+    empty tensors (the 8-rank equality check caught `denoiser_forward_tc` rejecting its null conditioner planes — no
+    single-GPU test ran an empty batch)."""
+    from cmtts_b200.synthesize import Pipeline
+    spec = ModelSpec.preset("VCTK")
+    sd = synthetic.make_acoustic_state_dict(spec, seed=0)
+    ck = synthetic.make_hifigan_checkpoint(spec.hifigan, seed=7)
+    pipe = Pipeline(spec, sd, ck["generator"], DEV, precision=precision)
+    texts = torch.zeros(0, 9, dtype=torch.int64)
+    out = pipe(texts, torch.zeros(0, dtype=torch.int64), torch.zeros(0, spec.ext_speaker_dim), T=4)
+    torch.cuda.synchronize()
+    assert out["mel"].shape[0] == 0 and out["wav_i16"].shape[0] == 0 and out["mel_lens"].numel() == 0
+    # and a real batch afterwards on the same pipeline (grow-only workspaces sized by the empty call)
+    batch = synthetic.make_batch(spec, 2, 5, 9, seed=1)
+    out = pipe(batch["texts"], batch["src_lens"], batch["spker_embeds"], T=2)
+    torch.cuda.synchronize()
+    assert out["mel"].shape[0] == 2 and torch.isfinite(out["mel"]).all()

@@ -44,7 +44,8 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     full_size = "--full" in sys.argv
     ok = True
-    cases = [("VCTK", 6, 8, 30, 4), ("LJSpeech", 4, 20, 45, 2), ("LJSpeech", 2 * world + 1, 10, 30, 1)]   # last: uneven shards
+    cases = [("VCTK", 6, 8, 30, 4), ("LJSpeech", 4, 20, 45, 2), ("LJSpeech", 2 * world + 1, 10, 30, 1),   # third: uneven shards
+             ("VCTK", max(world - 1, 1), 8, 30, 2)]                                                   # fourth: the last rank holds NO rows
     if full_size:
         cases.append(("LJSpeech", 32 * world, 80, 115, 4))
     for ds, B, lo, hi, T in cases:
