@@ -38,12 +38,13 @@ def _stamp():
 
 
 def kernel_stamp() -> str:
-    """Digest of the sources of the hot path's kernels only (everything but the off-path speaker encoder): what a committed
-    ncu capture under profiles/ is tied to (profiles/roofline_traffic_r2.json, bench.py `traffic_same_build`)."""
+    """Digest of the sources of the kernels a committed ncu capture under profiles/ is keyed by (the tcgen05 kernels and the
+    row kernels: umma_*.cu / .cuh, rowops.cu, common.cuh — not the host orchestration in pipeline.cu, nor the attention /
+    SIMT / speaker-encoder kernels, which the traffic table does not list): profiles/roofline_traffic_r2.json carries it
+    and bench.py reports `traffic_same_build` from it."""
     h = hashlib.sha256()
-    for f in sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh"))):
-        if os.path.basename(f) == "rescnn.cu":
-            continue
+    for f in sorted(glob.glob(os.path.join(CSRC, "umma_*.cu")) + glob.glob(os.path.join(CSRC, "umma_*.cuh"))) + [
+            os.path.join(CSRC, "rowops.cu"), os.path.join(CSRC, "common.cuh")]:
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())

@@ -13,9 +13,10 @@
 
 namespace {
 
-constexpr int QT = 8;  // queries (warps) per CTA
-
-template <int D>
+// QT = queries (warps) per CTA.  Every CTA streams ALL keys and values of its (utterance, head) through shared memory, so
+// the K / V traffic is proportional to the number of CTAs: 16 queries per CTA when that still leaves >= one CTA per SM
+// (C2: 960 -> 512 CTAs, half the re-reads), 8 otherwise.  A warp's arithmetic does not depend on QT: results are bitwise equal.
+template <int D, int QT>
 __global__ void __launch_bounds__(QT * 32) attention_kernel(const float* __restrict__ qkv,
                                                             const long long* __restrict__ src_lens,
                                                             float* __restrict__ out, int T, int C) {
@@ -95,11 +96,16 @@ int launch_attention(const float* qkv, const long long* src_lens, float* out, in
     if (B == 0 || T == 0) return CMTTS_OK;
     CMTTS_REQUIRE(heads > 0 && C % heads == 0, "attention: C % heads");
     const int D = C / heads;
+    const bool wide = (long long)((T + 15) / 16) * heads * B >= 148;
+    const int QT = wide ? 16 : 8;
     dim3 grid((T + QT - 1) / QT, heads, B);
-    if (D == 128) attention_kernel<128><<<grid, QT * 32, 0, s>>>(qkv, src_lens, out, T, C);
-    else if (D == 64) attention_kernel<64><<<grid, QT * 32, 0, s>>>(qkv, src_lens, out, T, C);
-    else if (D == 32) attention_kernel<32><<<grid, QT * 32, 0, s>>>(qkv, src_lens, out, T, C);
+#define CMTTS_ATT(D_) do { if (wide) attention_kernel<D_, 16><<<grid, 16 * 32, 0, s>>>(qkv, src_lens, out, T, C); \
+                           else attention_kernel<D_, 8><<<grid, 8 * 32, 0, s>>>(qkv, src_lens, out, T, C); } while (0)
+    if (D == 128) CMTTS_ATT(128);
+    else if (D == 64) CMTTS_ATT(64);
+    else if (D == 32) CMTTS_ATT(32);
     else { cmtts_set_error("attention: head_dim must be 32, 64 or 128", __FILE__, __LINE__); return CMTTS_ERR_UNSUPPORTED; }
+#undef CMTTS_ATT
     CMTTS_CHECK_LAUNCH();
     return CMTTS_OK;
 }
