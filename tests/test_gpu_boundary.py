@@ -240,3 +240,60 @@ def test_cuda_graph_path_matches_eager():
     graphed(*args, T=4)
     torch.cuda.synchronize()
     assert torch.equal(a["wav_i16"], keep)
+
+
+@needs_configs
+def test_zero_shot_protocol_ref_audio(tmp_path):
+    """synthesize_zeroshot_lj.py:89-102: the batch's speaker embeddings are replaced by the DeepSpeaker embedding of ONE
+    reference recording.  `CMTotalTTSSynthesize.synthesize(batch, ref_audio=...)` must equal `synthesize` on a batch that
+    already carries that embedding, and the embedding must be the speaker encoder's (oracle-checked in
+    tests/test_speaker_encoder.py) for the window the reference's random draw picks."""
+    import random
+
+    from scipy.io import wavfile
+
+    from cmtts_b200 import speaker_encoder as SE
+
+    ck = None
+    for root in (os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref"), "/root/reference"):
+        p = os.path.join(root, "deepspeaker", "pretrained_models", "ResCNN_triplet_training_checkpoint_265.h5")
+        if os.path.isfile(p):
+            ck = p
+            break
+    if ck is None:
+        pytest.skip("reference DeepSpeaker checkpoint not staged")
+    pre, model_cfg, train = _reference_configs("VCTK", tmp_path)
+    spec = ModelSpec.from_reference_configs(pre, model_cfg, train)
+    model_path = str(tmp_path / "ckpt")
+    synthetic.write_acoustic_checkpoint(model_path, spec, seed=4, step=0)
+    args = argparse.Namespace(T=2, mode="batch", speaker_id="p225", teacher_forced=False, restore_step=0, model="naive")
+    tool = S.CMTotalTTSSynthesize(model_path, 0, args, pre, model_cfg, train, device=DEV)
+    wav = str(tmp_path / "ref.wav")
+    wavfile.write(wav, SE.SAMPLE_RATE, (synthetic.make_voice_like(2.5, SE.SAMPLE_RATE, seed=5) * 32767).astype(np.int16))
+
+    b = synthetic.make_batch(spec, 3, 7, 15, seed=21)
+    as7 = lambda emb: S.to_device((["u0", "u1", "u2"], ["t0", "t1", "t2"], b["speakers"].numpy(), b["texts"].numpy(),
+                                   b["src_lens"].numpy(), int(b["src_lens"].max()), emb), DEV)
+    noise = draw_noise(9, (3, 1, 1000, spec.n_mels), 3)
+
+    class Cut:                                   # replayed noise, cut to whatever length the embedding leads to
+        def __init__(self):
+            self.it = iter(noise)
+
+        def randn(self, *shape, device=None, **_):
+            return next(self.it)[:, :, : shape[2]].contiguous().to(device)
+
+        def randn_like(self, x):
+            return self.randn(*x.shape, device=x.device)
+
+    random.seed(123)
+    out_zs = tool.synthesize(as7(b["spker_embeds"].numpy()), generator=Cut(), ref_audio=wav, speaker_ckpt=ck)
+    random.seed(123)                             # the same window of the recording (batcher.py:25 draws it with `random`)
+    emb = SE.get_deep_speaker_emb(filepath=wav, batch_size=3, device=DEV, ckpt_path=ck)
+    assert emb.shape == (3, 512) and float((emb.norm(dim=1) - 1).abs().max()) < 1e-5
+    out_pre = tool.synthesize(as7(emb.cpu().numpy()), generator=Cut())
+    torch.cuda.synchronize()
+    assert torch.equal(out_zs[11], out_pre[11]) and torch.equal(out_zs[0], out_pre[0])
+    # and it is NOT what the batch's own embeddings give
+    out_own = tool.synthesize(as7(b["spker_embeds"].numpy()), generator=Cut())
+    assert out_own[0].shape != out_zs[0].shape or not torch.equal(out_own[0], out_zs[0])
